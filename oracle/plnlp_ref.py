@@ -1,0 +1,309 @@
+"""Oracle restatement of the reference's own hot-path files (functional style).
+
+TEST INFRASTRUCTURE -- see ``oracle/__init__.py``.  Pinned by the fixtures under
+``tests/golden/`` which were produced by running the REAL reference package
+(``/root/reference/plnlp``) here -- see ``tests/golden/make_golden.py``.
+
+Each function cites the reference lines it follows.  Everything is plain torch
+on CPU (fp32 by default, fp64 when the inputs are fp64).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import pyg, sparse
+from .ogb_eval import hits_at_k, mrr_dict
+
+# ---------------------------------------------------------------------------
+# encoders  (plnlp/layer.py:7-45)
+# ---------------------------------------------------------------------------
+
+
+def conv_forward(kind, p, x, adj_t):
+    """One conv.  ``p`` is a dict of tensors with PyG's parameter names.
+    SAGE: lin_l.weight, lin_l.bias, lin_r.weight; GCN: lin.weight, bias."""
+    if kind == "SAGE":
+        agg = sparse.matmul(adj_t.set_value(None), x, reduce="mean")
+        return F.linear(agg, p["lin_l.weight"], p["lin_l.bias"]) + F.linear(x, p["lin_r.weight"])
+    if kind == "GCN":
+        z = F.linear(x, p["lin.weight"])
+        return sparse.matmul(adj_t, z, reduce="sum") + p["bias"]
+    raise NotImplementedError(kind)
+
+
+def encoder_forward(kind, layers, x, adj_t, keep_masks=None, p_drop=0.0):
+    """layer.py:18-27.  Every conv but the last is followed by relu + dropout; the
+    last conv is bare unless the net has exactly one layer, in which case it too is
+    followed by relu + dropout.  ``keep_masks[i]`` (0/1 tensor, optional) replaces
+    the RNG: activation *= mask / (1 - p_drop)."""
+    L = len(layers)
+    for i, p in enumerate(layers):
+        x = conv_forward(kind, p, x, adj_t)
+        if i < L - 1 or L == 1:
+            x = torch.relu(x)
+            if keep_masks is not None and p_drop > 0:
+                x = x * keep_masks[i].to(x.dtype) / (1.0 - p_drop)
+    return x
+
+
+# ---------------------------------------------------------------------------
+# predictors  (plnlp/layer.py:66-87, 167-176)
+# ---------------------------------------------------------------------------
+def mlp_score(lins, x_i, x_j, keep_masks=None, p_drop=0.0):
+    """layer.py:80-87.  ``lins`` = [(W, b), ...]; output [P, out]."""
+    x = x_i * x_j
+    for i, (W, b) in enumerate(lins[:-1]):
+        x = torch.relu(F.linear(x, W, b))
+        if keep_masks is not None and p_drop > 0:
+            x = x * keep_masks[i].to(x.dtype) / (1.0 - p_drop)
+    W, b = lins[-1]
+    return F.linear(x, W, b)
+
+
+def dot_score(x_i, x_j):
+    """layer.py:174-176; output [P]."""
+    return (x_i * x_j).sum(-1)
+
+
+# ---------------------------------------------------------------------------
+# losses  (plnlp/loss.py:5-14, 31-35) + closed-form gradients
+# ---------------------------------------------------------------------------
+def pair_loss(kind, pos_out, neg_out, num_neg, weight=None):
+    p = pos_out.reshape(-1, 1)
+    n = neg_out.reshape(-1, num_neg)
+    if kind == "AUC":
+        return (1 - (p - n)).square().sum()
+    if kind == "HingeAUC":
+        return (1 - (p - n)).clamp(min=0).square().sum()
+    if kind == "WeightedHingeAUC":
+        w = weight.reshape(-1, 1)
+        return (w * (w - (p - n)).clamp(min=0).square()).sum()
+    raise NotImplementedError(kind)
+
+
+def pair_loss_grad(kind, pos_out, neg_out, num_neg, weight=None):
+    """Closed-form d loss / d pos [B], d loss / d neg [B, num_neg]."""
+    p = pos_out.reshape(-1, 1)
+    n = neg_out.reshape(-1, num_neg)
+    if kind == "AUC":
+        t = 1 - (p - n)
+        g = 2 * t
+    elif kind == "HingeAUC":
+        t = (1 - (p - n)).clamp(min=0)
+        g = 2 * t
+    elif kind == "WeightedHingeAUC":
+        w = weight.reshape(-1, 1)
+        t = (w - (p - n)).clamp(min=0)
+        g = 2 * w * t
+    else:
+        raise NotImplementedError(kind)
+    return -g.sum(1), g
+
+
+def select_loss(name, has_weight):
+    """model.py:107-126 dispatch restricted to the in-scope losses: unknown names
+    and weighted losses without a weight fall back to AUC."""
+    if name == "HingeAUC":
+        return "HingeAUC"
+    if name == "WeightedHingeAUC" and has_weight:
+        return "WeightedHingeAUC"
+    return "AUC"
+
+
+# ---------------------------------------------------------------------------
+# negative samplers  (plnlp/negative_sample.py:6-20, 31-43)
+# ---------------------------------------------------------------------------
+def global_neg_sample(edge_index, num_nodes, num_samples, num_neg):
+    ei, _ = pyg.add_self_loops(edge_index, num_nodes=num_nodes)
+    neg = pyg.negative_sampling(ei, num_nodes=num_nodes, num_neg_samples=num_samples * num_neg)
+    src, dst = neg[0], neg[1]
+    want = num_samples * num_neg
+    if neg.size(1) < want:
+        extra = torch.randperm(neg.size(1))[: want - neg.size(1)]
+        src, dst = torch.cat([src, src[extra]]), torch.cat([dst, dst[extra]])
+    return torch.stack([src, dst], -1).reshape(-1, num_neg, 2)
+
+
+def local_neg_sample(pos_edges, num_nodes, num_neg):
+    E = pos_edges.size(0)
+    src = pos_edges[:, 0].reshape(-1, 1).repeat(1, num_neg).reshape(-1)
+    dst = torch.randint(0, num_nodes, (num_neg * E,), dtype=torch.long)
+    return torch.stack([src, dst], -1).reshape(-1, num_neg, 2)
+
+
+# ---------------------------------------------------------------------------
+# edge assembly  (plnlp/utils.py:7-41)
+# ---------------------------------------------------------------------------
+def eval_edges(split, split_edge):
+    tr = split_edge["train"]
+    if "edge" in tr:
+        return split_edge[split]["edge"], split_edge[split]["edge_neg"]
+    s, t = split_edge[split]["source_node"], split_edge[split]["target_node"]
+    tn = split_edge[split]["target_node_neg"]
+    pos = torch.stack([s, t]).t()
+    neg = torch.stack([s.repeat_interleave(tn.size(1)), tn.reshape(-1)]).t()
+    return pos, neg
+
+
+def train_pos_edges(split_edge):
+    tr = split_edge["train"]
+    if "edge" in tr:
+        return tr["edge"]
+    return torch.stack([tr["source_node"], tr["target_node"]]).t()
+
+
+# ---------------------------------------------------------------------------
+# evaluation glue  (plnlp/utils.py:44-80)
+# ---------------------------------------------------------------------------
+def evaluate_hits(pos_val, neg_val, pos_test, neg_test):
+    return {f"Hits@{K}": (hits_at_k(pos_val, neg_val, K), hits_at_k(pos_test, neg_test, K))
+            for K in (20, 50, 100)}
+
+
+def evaluate_mrr(pos_val, neg_val, pos_test, neg_test):
+    v = mrr_dict(pos_val, neg_val.view(pos_val.shape[0], -1))["mrr_list"].mean().item()
+    t = mrr_dict(pos_test, neg_test.view(pos_test.shape[0], -1))["mrr_list"].mean().item()
+    return {"MRR": (v, t)}
+
+
+# ---------------------------------------------------------------------------
+# the model: a CPU trainer with the reference's step semantics (model.py)
+# ---------------------------------------------------------------------------
+class OracleModel:
+    """Functional restatement of ``BaseModel`` (model.py:45-226) for the in-scope
+    configurations.  Parameters live in plain leaf tensors so tests can inject and
+    read them by name:
+
+      emb                       [N, emb_hidden]          (model.py:229-249)
+      enc.{i}.<pyg name>        per conv                 (layer.py:30-45)
+      pred.{i}.weight/.bias     MLP head only            (layer.py:69-74)
+    """
+
+    def __init__(self, *, num_nodes, emb_hidden, gnn_hidden, mlp_hidden, gnn_layers, mlp_layers,
+                 encoder="SAGE", predictor="MLP", loss="AUC", lr=1e-3, dropout=0.0,
+                 clip_norm=2.0, num_node_feats=0, use_node_feats=False, train_node_emb=True,
+                 dtype=torch.float32):
+        self.kind, self.pred_kind, self.loss_name = encoder.upper(), predictor.upper(), loss
+        self.dropout, self.clip_norm, self.lr = dropout, clip_norm, lr
+        self.use_node_feats, self.train_node_emb = use_node_feats, train_node_emb
+        self.num_nodes = num_nodes
+        in_dim = 0
+        self.params = {}
+        g = torch.Generator().manual_seed(1234)
+
+        def uni(shape, bound):
+            return ((torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * bound).to(dtype)
+
+        if use_node_feats:
+            in_dim += num_node_feats
+        if (not use_node_feats) or train_node_emb:
+            self.params["emb"] = uni((num_nodes, emb_hidden), math.sqrt(6.0 / (num_nodes + emb_hidden)))
+            in_dim += emb_hidden
+        self.in_dim = in_dim
+        for i in range(gnn_layers):
+            fi = in_dim if i == 0 else gnn_hidden
+            b = 1.0 / math.sqrt(fi)
+            if self.kind == "SAGE":
+                self.params[f"enc.{i}.lin_l.weight"] = uni((gnn_hidden, fi), b)
+                self.params[f"enc.{i}.lin_l.bias"] = uni((gnn_hidden,), b)
+                self.params[f"enc.{i}.lin_r.weight"] = uni((gnn_hidden, fi), b)
+            else:
+                self.params[f"enc.{i}.lin.weight"] = uni((gnn_hidden, fi), math.sqrt(6.0 / (fi + gnn_hidden)))
+                self.params[f"enc.{i}.bias"] = torch.zeros(gnn_hidden, dtype=dtype)
+        self.gnn_layers = gnn_layers
+        self.mlp_layers = mlp_layers if self.pred_kind == "MLP" else 0
+        for i in range(self.mlp_layers):
+            fi = mlp_hidden
+            fo = 1 if i == mlp_layers - 1 else mlp_hidden
+            b = 1.0 / math.sqrt(fi)
+            self.params[f"pred.{i}.weight"] = uni((fo, fi), b)
+            self.params[f"pred.{i}.bias"] = uni((fo,), b)
+        for v in self.params.values():
+            v.requires_grad_(True)
+        self._make_optimizer()
+
+    def _make_optimizer(self):
+        # parameter order of model.py:81-83: encoder, predictor, embedding
+        order = [k for k in self.params if k.startswith("enc.")] + \
+                [k for k in self.params if k.startswith("pred.")] + \
+                [k for k in self.params if k == "emb"]
+        self.optimizer = torch.optim.Adam([self.params[k] for k in order], lr=self.lr)
+
+    def load(self, state):
+        with torch.no_grad():
+            for k, v in state.items():
+                self.params[k].copy_(v)
+
+    def state(self):
+        return {k: v.detach().clone() for k, v in self.params.items()}
+
+    # -- pieces --------------------------------------------------------------
+    def input_feat(self, x):
+        """model.py:98-105"""
+        if self.use_node_feats:
+            if self.train_node_emb:
+                return torch.cat([self.params["emb"], x], dim=-1)
+            return x
+        return self.params["emb"]
+
+    def enc_layers(self):
+        out = []
+        for i in range(self.gnn_layers):
+            pre = f"enc.{i}."
+            out.append({k[len(pre):]: v for k, v in self.params.items() if k.startswith(pre)})
+        return out
+
+    def encode(self, x, adj_t, keep_masks=None):
+        return encoder_forward(self.kind, self.enc_layers(), self.input_feat(x), adj_t,
+                               keep_masks, self.dropout)
+
+    def score(self, h, edges, keep_masks=None):
+        """edges [P, 2] -> scores [P]"""
+        xi, xj = h[edges[:, 0]], h[edges[:, 1]]
+        if self.pred_kind == "DOT":
+            return dot_score(xi, xj)
+        lins = [(self.params[f"pred.{i}.weight"], self.params[f"pred.{i}.bias"])
+                for i in range(self.mlp_layers)]
+        return mlp_score(lins, xi, xj, keep_masks, self.dropout).reshape(-1)
+
+    # -- one optimisation step (model.py:148-171) ------------------------------
+    def step(self, x, adj_t, pos_edge, neg_edge, num_neg, weight=None, do_update=True):
+        """pos_edge [B,2]; neg_edge [B,num_neg,2].  Returns (loss, h)."""
+        self.optimizer.zero_grad()
+        h = self.encode(x, adj_t)
+        pos_out = self.score(h, pos_edge)
+        neg_out = self.score(h, neg_edge.reshape(-1, 2))
+        kind = select_loss(self.loss_name, weight is not None)
+        loss = pair_loss(kind, pos_out, neg_out, num_neg, weight)
+        loss.backward()
+        if do_update:
+            if self.clip_norm >= 0:
+                torch.nn.utils.clip_grad_norm_(
+                    [v for k, v in self.params.items() if k.startswith("enc.")], self.clip_norm)
+                pp = [v for k, v in self.params.items() if k.startswith("pred.")]
+                if pp:
+                    torch.nn.utils.clip_grad_norm_(pp, self.clip_norm)
+            self.optimizer.step()
+        return loss.detach(), h.detach()
+
+    def train_epoch(self, x, adj_t, pos_train, neg_train, perms, num_neg, weight=None):
+        """model.py:128-173 with the shuffles (``perms``: list of index tensors) and
+        the negatives supplied.  Returns the reference's reported loss."""
+        tot = cnt = 0
+        for perm in perms:
+            w = weight[perm] if weight is not None else None
+            loss, _ = self.step(x, adj_t, pos_train[perm], neg_train[perm], num_neg, w)
+            tot += loss.item() * perm.numel()
+            cnt += perm.numel()
+        return tot / cnt
+
+    @torch.no_grad()
+    def predict(self, x, adj_t, edges, batch_size=65536):
+        """model.py:175-194 (encoder once; mean row appended so index -1 resolves)."""
+        h = self.encode(x, adj_t)
+        h = torch.cat([h, h.mean(0, keepdim=True)], 0)
+        return torch.cat([self.score(h, edges[i:i + batch_size])
+                          for i in range(0, edges.size(0), batch_size)])

@@ -1,0 +1,100 @@
+"""Oracle restatement of the torch_geometric 2.0.1 pieces the reference uses.
+
+TEST INFRASTRUCTURE -- see ``oracle/__init__.py``.  torch_geometric is pinned by
+/root/reference/README.md:19 (pyg 2.0.1) but is neither vendored nor installable
+here, so its published behaviour is restated for exactly these call sites:
+
+* ``SAGEConv(in, out)`` / ``GCNConv(in, out, normalize=False)``
+                                  (/root/reference/plnlp/layer.py:4,30-45)
+* ``negative_sampling(edge_index, num_nodes, num_neg_samples, method='sparse')``
+  and ``add_self_loops``          (/root/reference/plnlp/negative_sample.py:3,8-10)
+
+Assumptions (parity of this layer is unpinned by the reference):
+ (7) SAGEConv drops adjacency values before aggregating (``set_value(None)``), uses
+     mean aggregation, and returns ``lin_l(agg) + lin_r(x)`` with a bias only in
+     ``lin_l``; ``normalize=False`` and ``root_weight=True`` are the defaults.
+ (8) GCNConv(normalize=False) = bias-free linear, then valued SpMM (sum), then
+     ``+ bias``.
+ (9) PyG 2.0.1 ``negative_sampling(method='sparse')``: linear ids ``row*N+col``;
+     oversampling factor ``alpha = |1/(1 - 1.1*E/N^2)|``; draws ``int(alpha*n)``
+     DISTINCT ids with python ``random.sample``; removes ids that are existing
+     edges (``numpy.isin``); truncates to ``n``; returns ``[2, <=n]``.
+"""
+from __future__ import annotations
+
+import math
+import random
+
+import numpy as np
+import torch
+
+from .sparse import matmul
+
+
+def _glorot(w):
+    a = math.sqrt(6.0 / (w.size(-2) + w.size(-1)))
+    torch.nn.init.uniform_(w, -a, a)
+
+
+class SAGEConv(torch.nn.Module):
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin_l = torch.nn.Linear(in_channels, out_channels, bias=True)
+        self.lin_r = torch.nn.Linear(in_channels, out_channels, bias=False)
+
+    def reset_parameters(self):
+        self.lin_l.reset_parameters()
+        self.lin_r.reset_parameters()
+
+    def forward(self, x, adj_t):
+        agg = matmul(adj_t.set_value(None), x, reduce="mean")
+        return self.lin_l(agg) + self.lin_r(x)
+
+
+class GCNConv(torch.nn.Module):
+    def __init__(self, in_channels, out_channels, normalize=False):
+        super().__init__()
+        assert not normalize, "the reference only uses normalize=False (layer.py:45)"
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin = torch.nn.Linear(in_channels, out_channels, bias=False)
+        self.bias = torch.nn.Parameter(torch.zeros(out_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        _glorot(self.lin.weight)
+        torch.nn.init.zeros_(self.bias)
+
+    def forward(self, x, adj_t):
+        x = self.lin(x)
+        out = matmul(adj_t, x, reduce="sum")
+        return out + self.bias
+
+
+class _Unavailable(torch.nn.Module):
+    def __init__(self, *a, **k):
+        raise NotImplementedError("out of scope (SURVEY.md section 2.1 rows 2)")
+
+
+GraphConv = TransformerConv = _Unavailable
+
+
+def add_self_loops(edge_index, edge_weight=None, num_nodes=None):
+    N = int(num_nodes) if num_nodes is not None else int(edge_index.max()) + 1
+    loop = torch.arange(N, dtype=edge_index.dtype)
+    return torch.cat([edge_index, torch.stack([loop, loop])], dim=1), edge_weight
+
+
+def negative_sampling(edge_index, num_nodes=None, num_neg_samples=None, method="sparse"):
+    N = int(num_nodes) if num_nodes is not None else int(edge_index.max()) + 1
+    n = int(num_neg_samples) if num_neg_samples is not None else edge_index.size(1)
+    size = N * N
+    n = min(n, size - edge_index.size(1))
+    row, col = edge_index
+    idx = row * N + col
+    alpha = abs(1 / (1 - 1.1 * (edge_index.size(1) / size)))
+    k = min(int(alpha * n), size)
+    perm = torch.tensor(random.sample(range(size), k), dtype=torch.int64)
+    mask = torch.from_numpy(np.isin(perm.numpy(), idx.numpy())).to(torch.bool)
+    perm = perm[~mask][:n]
+    return torch.stack([perm // N, perm % N], dim=0)
