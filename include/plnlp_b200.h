@@ -1,0 +1,196 @@
+/* plnlp_b200.h -- C ABI of the B200 (sm_100a) kernels behind the PLNLP hot path.
+ *
+ * The reference (zhitao-wang/PLNLP) is pure Python and has no FFI of its own; the
+ * "interface each entry point replaces" is therefore the third-party kernel call made
+ * at a reference line.  Every entry point below cites that reference file:line.
+ *
+ * Conventions
+ *  - plain `extern "C"`, raw DEVICE pointers + int64 sizes + a `cudaStream_t` passed as
+ *    `void*`; no torch types, no exceptions, no allocation, no retained pointers.
+ *  - the caller owns every buffer, including workspaces (sized with the documented
+ *    formulas / the *_workspace_bytes helpers).
+ *  - return value: 0 = ok; < 0 = invalid argument (PLNLP_E_*); > 0 = the cudaError_t of a
+ *    failed launch.  Kernels are enqueued asynchronously on `stream`.
+ *  - no CPU fallback and no other-arch dispatch: the library is built for sm_100a only.
+ *  - all matrices are row-major with an explicit leading dimension in ELEMENTS.
+ */
+#ifndef PLNLP_B200_H
+#define PLNLP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLNLP_ABI_VERSION 1
+
+#define PLNLP_E_NULL       (-1)  /* required pointer is NULL            */
+#define PLNLP_E_SIZE       (-2)  /* negative / inconsistent size         */
+#define PLNLP_E_ALIGN      (-3)  /* pointer / leading dim not aligned    */
+#define PLNLP_E_UNSUPPORTED (-4) /* valid but not implemented combination */
+#define PLNLP_E_WORKSPACE  (-5)  /* workspace too small                  */
+#define PLNLP_E_DEVICE     (-6)  /* current device is not sm_100         */
+
+/* loss kinds: /root/reference/plnlp/loss.py:5-8, 11-14, 31-35 */
+#define PLNLP_LOSS_AUC 0
+#define PLNLP_LOSS_HINGE_AUC 1
+#define PLNLP_LOSS_WEIGHTED_HINGE_AUC 2
+
+/* GEMM epilogue activations */
+#define PLNLP_ACT_NONE 0
+#define PLNLP_ACT_RELU 1        /* relu, then inverted dropout when drop_p > 0 (layer.py:21-22, 84-85) */
+#define PLNLP_ACT_RELU_GRAD 2   /* C = acc * (aux > 0 ? 1/(1-drop_p) : 0): backward of the above       */
+
+int plnlp_abi_version(void);
+/* 0 when the CURRENT cuda device is compute capability 10.x, PLNLP_E_DEVICE otherwise. */
+int plnlp_check_device(void);
+/* number of kernels this library has launched since load (process-wide, for bench.py's
+ * `gpu_launches`); reading it does not synchronise. */
+int64_t plnlp_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * CSR row-gather SpMM (replaces torch_sparse.matmul under SAGEConv / GCNConv,
+ * /root/reference/plnlp/layer.py:20,23, and its autograd backward which runs the same
+ * kernel on the transposed structure, model.py:161).
+ *
+ *   out[r, :] = epi( (sum_{p in row r} val[p] * x[col[p], :]) / row_div[r] )
+ *   epi(v) = dropout(relu(v + bias))   (each stage optional)
+ *
+ * The row set is described by a PLAN (built once per graph by the host, see
+ * plnlp_b200/graph.py): work item i covers stored entries [item_ptr[i], item_ptr[i+1]) of row
+ * item_row[i].  Rows no longer than the plan's chunk are one item (item_slot = -1, written
+ * straight to `out`, accumulated strictly in CSR order -> bit-identical to the in-order CPU
+ * loop).  Longer (hub) rows are split into several items that write fp32 partial sums to
+ * partial[item_slot], combined in slot order by a second fixed-order pass (deterministic).
+ *   fix_row[j] / fix_ptr[j..j+1] : split row j and its range of partial slots.
+ * val == NULL: value-less adjacency.  row_div == NULL: no division (sum); SAGE mean passes
+ * row_div[r] = max(row_nnz, 1) and gets the IEEE division upstream performs.
+ * F: feature width; x/out leading dims in floats.  16-byte vector loads are used when F,
+ * ldx, ldo are multiples of 4 and the bases are 16-byte aligned; otherwise 8- or 4-byte.
+ */
+int plnlp_spmm_csr_f32(const int32_t* item_ptr, const int32_t* item_row, const int32_t* item_slot,
+                       int64_t n_items, const int32_t* col, const float* val,
+                       const float* row_div, const float* bias, int relu, float drop_p, uint64_t seed,
+                       const float* x, int64_t ldx, float* out, int64_t ldo, int64_t F,
+                       float* partial, const int32_t* fix_ptr, const int32_t* fix_row, int64_t n_fix,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Dense layers (replace torch.nn.Linear -> cuBLAS sgemm under SAGEConv.lin_l/lin_r,
+ * GCNConv.lin, MLPPredictor.lins: layer.py:20,23,82-86, and their two backward GEMMs).
+ *
+ *   C = act( op(A) . op(B) + beta * C + bias )       op(A): M x K, op(B): K x N
+ *   transa = 0: A[m*lda + k]     transa = 1: A[k*lda + m]
+ *   transb = 0: B[k*ldb + n]     transb = 1: B[n*ldb + k]   (torch Linear weight layout)
+ * split_k > 1 needs workspace of split_k*M*N floats; partials are reduced in split order
+ * (deterministic).  aux (ldaux) is the forward activation for PLNLP_ACT_RELU_GRAD.
+ * plnlp_gemm_f32 is the exact-fp32 CUDA-core path (FFMA, fp32 accumulate).
+ */
+int plnlp_gemm_f32(int transa, int transb, int64_t M, int64_t N, int64_t K,
+                   const float* A, int64_t lda, const float* B, int64_t ldb,
+                   float* C, int64_t ldc, float beta, const float* bias, int act,
+                   const float* aux, int64_t ldaux, float drop_p, uint64_t seed,
+                   float* workspace, int64_t workspace_bytes, int split_k, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Edge scoring (replaces h[edge[0]], h[edge[1]] advanced indexing + MLPPredictor /
+ * DotPredictor, model.py:152-156,180 and layer.py:80-87,174-176).
+ * `edges` is the reference's own int64 [P, 2] tensor (row p = (src, dst)).  h has n_rows rows;
+ * a negative node index i addresses row n_rows + i, like the python indexing it replaces
+ * (model.py:191-194 appends a mean row so that index -1 resolves).
+ */
+/* out[p, :] = h[src_p, :] * h[dst_p, :] */
+int plnlp_gather_hadamard_f32(const float* h, int64_t ldh, int64_t n_rows, const int64_t* edges, int64_t P, int64_t H,
+                              float* out, int64_t ldo, void* stream);
+/* score[p] = sum_d h[src_p, d] * h[dst_p, d]   (DotPredictor) */
+int plnlp_edge_dot_fwd_f32(const float* h, int64_t ldh, int64_t n_rows, const int64_t* edges, int64_t P, int64_t H,
+                           float* score, void* stream);
+/* last MLP layer (out_channels = 1): score[p] = a[p, :] . w + b[0] */
+int plnlp_mlp_out_fwd_f32(const float* a, int64_t lda, const float* w, const float* b, int64_t P,
+                          int64_t H, float* score, void* stream);
+/* backward of the above fused with the relu/dropout mask of `a`:
+ *   dz[p, j] = dscore[p] * w[j] * (a[p, j] > 0 ? drop_scale : 0)     (mask_a != 0)
+ *   dw[j] = sum_p dscore[p] * a[p, j];  db[0] = sum_p dscore[p]
+ * workspace: plnlp_mlp_out_bwd_workspace_bytes(P, H) bytes.  Deterministic. */
+int64_t plnlp_mlp_out_bwd_workspace_bytes(int64_t P, int64_t H);
+int plnlp_mlp_out_bwd_f32(const float* a, int64_t lda, const float* w, const float* dscore, int64_t P,
+                          int64_t H, int mask_a, float drop_scale, float* dz, int64_t lddz, float* dw,
+                          float* db, void* workspace, int64_t workspace_bytes, void* stream);
+/* Backward of the endpoint gather (replaces index_put_(accumulate=True), model.py:161).
+ *   g[p, :] = da[p, :]            (MLP head; da = d loss / d hadamard)       or
+ *   g[p, :] = dscore[p]           (DOT head; da == NULL)
+ *   grad_h[src_p] += g[p] * h[dst_p];   grad_h[dst_p] += g[p] * h[src_p]
+ * _atomic: red.global.add (order non-deterministic).  _sorted: one warp per node segment of
+ * the node-sorted incidence list (entry = 2*p + side), fixed summation order; grad_h rows of
+ * listed nodes are OVERWRITTEN, the caller zero-fills grad_h first. */
+int plnlp_edge_scatter_atomic_f32(const float* h, int64_t ldh, int64_t n_rows, const int64_t* edges, int64_t P, int64_t H,
+                                  const float* da, int64_t ldda, const float* dscore, float* grad_h,
+                                  int64_t ldg, void* stream);
+int plnlp_edge_scatter_sorted_f32(const float* h, int64_t ldh, int64_t n_rows, const int64_t* edges, int64_t P, int64_t H,
+                                  const float* da, int64_t ldda, const float* dscore,
+                                  const int64_t* seg_ptr, const int64_t* seg_node, int64_t n_seg,
+                                  const int64_t* entry, float* grad_h, int64_t ldg, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Pairwise losses + d loss / d score in one pass (replaces loss.py:5-8, 11-14, 31-35 and
+ * their autograd mirror).  pos [B], neg [B, num_neg] (row i = negatives of positive i,
+ * model.py:153), weight [B] (WeightedHingeAUC only).  loss[0] = SUM over pairs (not mean).
+ * workspace: plnlp_pair_loss_workspace_bytes(B) bytes, contents arbitrary. Deterministic. */
+int64_t plnlp_pair_loss_workspace_bytes(int64_t B);
+int plnlp_pair_loss_f32(int kind, const float* pos, const float* neg, const float* weight, int64_t B,
+                        int num_neg, float* loss, float* dpos, float* dneg, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Elementwise / reductions around the layers.
+ */
+/* dx = dy * (y > 0 ? scale : 0): backward of relu(+dropout) given the forward OUTPUT y
+ * (layer.py:21-22, 25-26). */
+int plnlp_relu_drop_bwd_f32(const float* y, int64_t ldy, const float* dy, int64_t lddy, float scale,
+                            int64_t rows, int64_t cols, float* dx, int64_t lddx, void* stream);
+/* out[c] = scale * sum_r x[r, c]  (bias gradients; mean row of h, model.py:193).
+ * workspace: plnlp_colsum_workspace_bytes(rows, cols). Deterministic. */
+int64_t plnlp_colsum_workspace_bytes(int64_t rows, int64_t cols);
+int plnlp_colsum_f32(const float* x, int64_t ldx, int64_t rows, int64_t cols, float scale, float* out,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Negative samplers (replace negative_sample.py:6-20 and 31-43; both run on the HOST in
+ * the reference).  Outputs use the reference layout: int64 [E, num_neg, 2].
+ */
+/* local: src = pos[e, 0] repeated, dst ~ U[0, num_nodes) from Philox4x32-10(seed). */
+int plnlp_local_neg_sample(const int64_t* pos_edges, int64_t E, int64_t num_nodes, int num_neg,
+                           uint64_t seed, int64_t* out, void* stream);
+/* global, stage 1: draw n_cand candidate cells (r, c) ~ U[0,N)^2; a candidate is VALID when
+ * r != c and r*N + c is not in the sorted id list `edge_ids` (n_edges entries; the existing
+ * edges, id = edge_index[0]*N + edge_index[1]).  Valid candidates are inserted into an
+ * open-addressing table (table_keys / table_first, `table_size` a power of two >= 2*n_cand,
+ * pre-filled with 0xFF bytes) keeping, per distinct id, the SMALLEST candidate index
+ * (deterministic).  cand_ids[i] = id or -1 when invalid. */
+int plnlp_global_neg_candidates(const int64_t* edge_ids, int64_t n_edges, int64_t num_nodes,
+                                int64_t n_cand, uint64_t seed, int64_t* cand_ids,
+                                unsigned long long* table_keys, int* table_first, int64_t table_size,
+                                void* stream);
+/* stage 2: keep[i] = 1 iff candidate i is valid and is the first occurrence of its id. */
+int plnlp_global_neg_keep(const int64_t* cand_ids, int64_t n_cand, const unsigned long long* table_keys,
+                          const int* table_first, int64_t table_size, uint8_t* keep, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Ranking metrics (replace ogb Evaluator._eval_hits / _eval_mrr on CPU tensors,
+ * utils.py:49-56, 67-76).
+ */
+/* kth[0] = K-th largest element of neg[0..n) (1-based K <= n).  workspace >= 8192 bytes. */
+int plnlp_kth_largest_f32(const float* neg, int64_t n, int64_t K, float* kth, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+/* count[0] = #{ i : pos[i] > thresh[0] }  (strict, as ogb). */
+int plnlp_count_greater_f32(const float* pos, int64_t n, const float* thresh,
+                            unsigned long long* count, void* stream);
+/* per row r of neg [S, K]: gt[r] = #{neg > pos[r]}, ge[r] = #{neg >= pos[r]}. */
+int plnlp_mrr_counts_f32(const float* pos, const float* neg, int64_t ldn, int64_t S, int64_t K,
+                         int32_t* gt, int32_t* ge, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLNLP_B200_H */

@@ -1,0 +1,114 @@
+"""ctypes binding of the C-ABI library ``libplnlp_b200.so`` (see include/plnlp_b200.h).
+
+This is the ONLY way the python package reaches the kernels: raw device pointers
+(``tensor.data_ptr()``), int64 sizes and the current CUDA stream handle.  There is no
+CPU fallback: if the shared library is missing, or a kernel is asked to run on
+non-CUDA tensors, a ``RuntimeError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_float, c_int, c_int64, c_uint64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libplnlp_b200.so")
+
+_P, _I, _L, _F, _U = c_void_p, c_int, c_int64, c_float, c_uint64
+
+# name -> (restype, argtypes); mirrors include/plnlp_b200.h declaration by declaration
+SIGNATURES = {
+    "plnlp_abi_version": (c_int, []),
+    "plnlp_check_device": (c_int, []),
+    "plnlp_launch_count": (c_int64, []),
+    "plnlp_spmm_csr_f32": (c_int, [_P, _P, _P, _L, _P, _P, _P, _P, _I, _F, _U, _P, _L, _P, _L, _L, _P, _P, _P, _L, _P]),
+    "plnlp_gemm_f32": (c_int, [_I, _I, _L, _L, _L, _P, _L, _P, _L, _P, _L, _F, _P, _I, _P, _L, _F, _U, _P, _L, _I, _P]),
+    "plnlp_gather_hadamard_f32": (c_int, [_P, _L, _L, _P, _L, _L, _P, _L, _P]),
+    "plnlp_edge_dot_fwd_f32": (c_int, [_P, _L, _L, _P, _L, _L, _P, _P]),
+    "plnlp_mlp_out_fwd_f32": (c_int, [_P, _L, _P, _P, _L, _L, _P, _P]),
+    "plnlp_mlp_out_bwd_workspace_bytes": (c_int64, [_L, _L]),
+    "plnlp_mlp_out_bwd_f32": (c_int, [_P, _L, _P, _P, _L, _L, _I, _F, _P, _L, _P, _P, _P, _L, _P]),
+    "plnlp_edge_scatter_atomic_f32": (c_int, [_P, _L, _L, _P, _L, _L, _P, _L, _P, _P, _L, _P]),
+    "plnlp_edge_scatter_sorted_f32": (c_int, [_P, _L, _L, _P, _L, _L, _P, _L, _P, _P, _P, _L, _P, _P, _L, _P]),
+    "plnlp_pair_loss_workspace_bytes": (c_int64, [_L]),
+    "plnlp_pair_loss_f32": (c_int, [_I, _P, _P, _P, _L, _I, _P, _P, _P, _P, _L, _P]),
+    "plnlp_relu_drop_bwd_f32": (c_int, [_P, _L, _P, _L, _F, _L, _L, _P, _L, _P]),
+    "plnlp_colsum_workspace_bytes": (c_int64, [_L, _L]),
+    "plnlp_colsum_f32": (c_int, [_P, _L, _L, _L, _F, _P, _P, _L, _P]),
+    "plnlp_local_neg_sample": (c_int, [_P, _L, _L, _I, _U, _P, _P]),
+    "plnlp_global_neg_candidates": (c_int, [_P, _L, _L, _L, _U, _P, _P, _P, _L, _P]),
+    "plnlp_global_neg_keep": (c_int, [_P, _L, _P, _P, _L, _P, _P]),
+    "plnlp_kth_largest_f32": (c_int, [_P, _L, _L, _P, _P, _L, _P]),
+    "plnlp_count_greater_f32": (c_int, [_P, _L, _P, _P, _P]),
+    "plnlp_mrr_counts_f32": (c_int, [_P, _P, _L, _L, _L, _P, _P, _P]),
+}
+
+_ERRORS = {-1: "required pointer is NULL", -2: "bad size", -3: "misaligned pointer / leading dimension",
+           -4: "unsupported combination", -5: "workspace too small", -6: "device is not sm_100"}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises RuntimeError when it has not been built:
+    the product has no other execution path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C plnlp_b200/csrc`). plnlp_b200 has no CPU or eager fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if lib.plnlp_abi_version() != 1:
+        raise RuntimeError("libplnlp_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc, name):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise RuntimeError(f"{name}: invalid argument ({_ERRORS.get(rc, rc)})")
+    raise RuntimeError(f"{name}: CUDA launch failed with cudaError {rc}")
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    """device pointer of a CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("plnlp_b200 kernels need CUDA tensors; there is no CPU path")
+    return t.data_ptr()
+
+
+def launch_count():
+    return int(load().plnlp_launch_count())
+
+
+class _Workspace:
+    """Caller-owned scratch buffers, grown on demand and reused (per device, per tag)."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, tag, nbytes, device):
+        key = (tag, device)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._bufs[key] = buf
+        return buf
+
+
+workspace = _Workspace()

@@ -1,0 +1,517 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels.
+
+Every op here launches hand-written sm_100a kernels through ``_lib`` (ctypes) on the current
+CUDA stream.  Nothing falls back to eager PyTorch arithmetic: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream, workspace
+from .graph import structure_of
+
+ACT_NONE, ACT_RELU, ACT_RELU_GRAD = 0, 1, 2
+LOSS_KINDS = {"AUC": 0, "HingeAUC": 1, "WeightedHingeAUC": 2}
+
+# which scatter kernel backs the endpoint-gather backward: "sorted" (deterministic, default)
+# or "atomic" (red.global.add, order non-deterministic)
+SCATTER_MODE = "sorted"
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"plnlp_b200 kernels are fp32; got {t.dtype}")
+    if not t.is_cuda:
+        raise RuntimeError("plnlp_b200 kernels need CUDA tensors; there is no CPU path")
+    return t
+
+
+def _rowmajor(t):
+    """2-D tensor usable as a row-major matrix with a leading dimension (no copy when the
+    inner stride is 1, e.g. column slices of a weight)."""
+    _f32c(t)
+    if t.dim() != 2:
+        raise RuntimeError("expected a 2-D tensor")
+    if t.stride(1) != 1 and t.size(1) != 1:
+        t = t.contiguous()
+    if t.size(1) == 1 and t.stride(0) < 1:
+        t = t.contiguous()
+    return t
+
+
+def _ld(t):
+    return t.stride(0) if t.size(0) > 1 else max(t.size(1), t.stride(0))
+
+
+def new_seed():
+    """64-bit Philox seed drawn from torch's CPU generator (reproducible under manual_seed,
+    never touches the device)."""
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+# ---------------------------------------------------------------------------
+# raw launches
+# ---------------------------------------------------------------------------
+def spmm_raw(plan, x, use_val, div_rows, bias=None, relu=False, drop_p=0.0, seed=0, out=None):
+    lib = _lib.load()
+    x = _rowmajor(x)
+    F = x.size(1)
+    if x.size(0) != plan.n_cols:
+        raise RuntimeError(f"SpMM shape mismatch: adjacency has {plan.n_cols} columns, x has {x.size(0)} rows")
+    if out is None:
+        out = torch.empty(plan.n_rows, F, dtype=torch.float32, device=x.device)
+    partial = None
+    if plan.n_fix:
+        partial = workspace.get("spmm_partial", plan.n_partial * F * 4, x.device)
+    val = plan.val if use_val else None
+    check(lib.plnlp_spmm_csr_f32(ptr(plan.item_ptr), ptr(plan.item_row), ptr(plan.item_slot), plan.n_items,
+                                 ptr(plan.col), ptr(val), ptr(plan.row_cnt if div_rows else None), ptr(bias),
+                                 int(relu), float(drop_p), int(seed), ptr(x), _ld(x), ptr(out), _ld(out), F,
+                                 ptr(partial), ptr(plan.fix_ptr), ptr(plan.fix_row), plan.n_fix, stream()),
+          "plnlp_spmm_csr_f32")
+    return out
+
+
+def gemm_raw(A, B, transa=False, transb=False, C=None, beta=0.0, bias=None, act=ACT_NONE, aux=None,
+             drop_p=0.0, seed=0, split_k=None):
+    """C = act(op(A) @ op(B) + beta*C + bias); A, B row-major with leading dimensions."""
+    lib = _lib.load()
+    A, B = _rowmajor(A), _rowmajor(B)
+    M, K = (A.size(1), A.size(0)) if transa else (A.size(0), A.size(1))
+    K2, N = (B.size(1), B.size(0)) if transb else (B.size(0), B.size(1))
+    if K != K2:
+        raise RuntimeError(f"GEMM inner dimensions differ: {K} vs {K2}")
+    if C is None:
+        C = torch.empty(M, N, dtype=torch.float32, device=A.device)
+        beta = 0.0
+    if split_k is None:
+        tiles = ((M + 127) // 128) * ((N + 127) // 128)
+        split_k = 1
+        if tiles < 148 and K >= 2048:
+            split_k = int(min(max(1, (2 * 148) // tiles), K // 512, 64))
+    ws = None
+    ws_bytes = 0
+    if split_k > 1:
+        ws_bytes = split_k * M * N * 4
+        ws = workspace.get("gemm_splitk", ws_bytes, A.device)
+    check(lib.plnlp_gemm_f32(int(transa), int(transb), M, N, K, ptr(A), _ld(A), ptr(B), _ld(B), ptr(C), _ld(C),
+                             float(beta), ptr(bias), int(act), ptr(aux), _ld(aux) if aux is not None else 0,
+                             float(drop_p), int(seed), ptr(ws), ws_bytes, int(split_k), stream()),
+          "plnlp_gemm_f32")
+    return C
+
+
+def colsum_raw(x, scale=1.0):
+    lib = _lib.load()
+    x = _rowmajor(x)
+    rows, cols = x.shape
+    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    nbytes = lib.plnlp_colsum_workspace_bytes(rows, cols)
+    ws = workspace.get("colsum", nbytes, x.device)
+    check(lib.plnlp_colsum_f32(ptr(x), _ld(x), rows, cols, float(scale), ptr(out), ptr(ws), nbytes, stream()),
+          "plnlp_colsum_f32")
+    return out
+
+
+def relu_drop_bwd_raw(y, dy, scale):
+    lib = _lib.load()
+    y, dy = _rowmajor(y), _rowmajor(dy)
+    dx = torch.empty(y.shape, dtype=torch.float32, device=y.device)
+    check(lib.plnlp_relu_drop_bwd_f32(ptr(y), _ld(y), ptr(dy), _ld(dy), float(scale), y.size(0), y.size(1),
+                                      ptr(dx), _ld(dx), stream()), "plnlp_relu_drop_bwd_f32")
+    return dx
+
+
+def _edges_i64(edges):
+    if edges.dtype != torch.int64 or not edges.is_cuda:
+        raise RuntimeError("edges must be a CUDA int64 [P, 2] tensor")
+    if edges.dim() != 2 or edges.size(1) != 2:
+        raise RuntimeError("edges must have shape [P, 2]")
+    return edges.contiguous()
+
+
+def gather_hadamard_raw(h, edges):
+    lib = _lib.load()
+    h, edges = _rowmajor(h), _edges_i64(edges)
+    P, H = edges.size(0), h.size(1)
+    out = torch.empty(P, H, dtype=torch.float32, device=h.device)
+    check(lib.plnlp_gather_hadamard_f32(ptr(h), _ld(h), h.size(0), ptr(edges), P, H, ptr(out), H, stream()),
+          "plnlp_gather_hadamard_f32")
+    return out
+
+
+def edge_dot_raw(h, edges):
+    lib = _lib.load()
+    h, edges = _rowmajor(h), _edges_i64(edges)
+    P, H = edges.size(0), h.size(1)
+    score = torch.empty(P, dtype=torch.float32, device=h.device)
+    check(lib.plnlp_edge_dot_fwd_f32(ptr(h), _ld(h), h.size(0), ptr(edges), P, H, ptr(score), stream()),
+          "plnlp_edge_dot_fwd_f32")
+    return score
+
+
+def mlp_out_fwd_raw(a, w, b):
+    lib = _lib.load()
+    a = _rowmajor(a)
+    w = _f32c(w).reshape(-1).contiguous()
+    P, H = a.shape
+    score = torch.empty(P, dtype=torch.float32, device=a.device)
+    check(lib.plnlp_mlp_out_fwd_f32(ptr(a), _ld(a), ptr(w), ptr(b), P, H, ptr(score), stream()),
+          "plnlp_mlp_out_fwd_f32")
+    return score
+
+
+def mlp_out_bwd_raw(a, w, dscore, mask_a, drop_scale):
+    """-> dz [P,H], dw [H], db [1]"""
+    lib = _lib.load()
+    a = _rowmajor(a)
+    w = _f32c(w).reshape(-1).contiguous()
+    dscore = _f32c(dscore).contiguous()
+    P, H = a.shape
+    dz = torch.empty(P, H, dtype=torch.float32, device=a.device)
+    dw = torch.empty(H, dtype=torch.float32, device=a.device)
+    db = torch.empty(1, dtype=torch.float32, device=a.device)
+    nbytes = lib.plnlp_mlp_out_bwd_workspace_bytes(P, H)
+    ws = workspace.get("mlp_out_bwd", nbytes, a.device)
+    check(lib.plnlp_mlp_out_bwd_f32(ptr(a), _ld(a), ptr(w), ptr(dscore), P, H, int(mask_a), float(drop_scale),
+                                    ptr(dz), H, ptr(dw), ptr(db), ptr(ws), nbytes, stream()),
+          "plnlp_mlp_out_bwd_f32")
+    return dz, dw, db
+
+
+def edge_scatter_raw(h, edges, da=None, dscore=None, mode=None):
+    """grad_h [n_rows, H] of the endpoint gather; da [P,H] (MLP head) or dscore [P] (DOT)."""
+    lib = _lib.load()
+    mode = mode or SCATTER_MODE
+    h, edges = _rowmajor(h), _edges_i64(edges)
+    P, H, n_rows = edges.size(0), h.size(1), h.size(0)
+    if da is not None:
+        da = _rowmajor(da)
+    if dscore is not None:
+        dscore = _f32c(dscore).contiguous()
+    grad_h = torch.zeros(n_rows, H, dtype=torch.float32, device=h.device)
+    ldda = _ld(da) if da is not None else 0
+    if mode == "atomic":
+        check(lib.plnlp_edge_scatter_atomic_f32(ptr(h), _ld(h), n_rows, ptr(edges), P, H, ptr(da), ldda,
+                                                ptr(dscore), ptr(grad_h), H, stream()),
+              "plnlp_edge_scatter_atomic_f32")
+        return grad_h
+    # node-sorted incidence list: key = node * 2P + (2p + side) is unique -> any sort is deterministic
+    flat = edges.reshape(-1)                          # entry id t = 2p + side  <->  flat[t]
+    flat = torch.where(flat < 0, flat + n_rows, flat)
+    key = flat * (2 * P) + torch.arange(2 * P, device=edges.device)
+    skey, _ = torch.sort(key)
+    entry = skey % (2 * P)
+    node = torch.div(skey, 2 * P, rounding_mode="floor")
+    seg_node, counts = torch.unique_consecutive(node, return_counts=True)
+    seg_ptr = torch.zeros(seg_node.numel() + 1, dtype=torch.int64, device=edges.device)
+    seg_ptr[1:] = torch.cumsum(counts, 0)
+    check(lib.plnlp_edge_scatter_sorted_f32(ptr(h), _ld(h), n_rows, ptr(edges), P, H, ptr(da), ldda, ptr(dscore),
+                                            ptr(seg_ptr), ptr(seg_node), seg_node.numel(), ptr(entry),
+                                            ptr(grad_h), H, stream()), "plnlp_edge_scatter_sorted_f32")
+    return grad_h
+
+
+def pair_loss_raw(kind, pos, neg, num_neg, weight=None):
+    """-> loss [1], dpos [B], dneg [B*num_neg]"""
+    lib = _lib.load()
+    pos = _f32c(pos).reshape(-1).contiguous()
+    neg = _f32c(neg).reshape(-1).contiguous()
+    B = pos.numel()
+    if neg.numel() != B * num_neg:
+        raise RuntimeError(f"neg_out has {neg.numel()} scores, expected {B} x {num_neg}")
+    if weight is not None:
+        weight = _f32c(weight).reshape(-1).contiguous()
+    loss = torch.empty(1, dtype=torch.float32, device=pos.device)
+    dpos = torch.empty(B, dtype=torch.float32, device=pos.device)
+    dneg = torch.empty(B * num_neg, dtype=torch.float32, device=pos.device)
+    nbytes = lib.plnlp_pair_loss_workspace_bytes(B)
+    ws = workspace.get("pair_loss", nbytes, pos.device)
+    check(lib.plnlp_pair_loss_f32(int(kind), ptr(pos), ptr(neg), ptr(weight), B, int(num_neg), ptr(loss), ptr(dpos),
+                                  ptr(dneg), ptr(ws), nbytes, stream()), "plnlp_pair_loss_f32")
+    return loss, dpos, dneg
+
+
+# ---------------------------------------------------------------------------
+# autograd Functions
+# ---------------------------------------------------------------------------
+class SpMM(torch.autograd.Function):
+    """out = epi(A @ x) with A given by ``adj``; reduce 'sum' uses the stored values, 'mean'
+    drops them (SAGEConv) and divides by max(row_nnz, 1).  Optional fused epilogue
+    bias -> relu -> dropout (GCNConv + layer.py:21-22).  Backward runs the same kernel on the
+    cached transposed structure."""
+
+    @staticmethod
+    def forward(ctx, x, bias, adj, reduce, relu, drop_p, seed):
+        st = structure_of(adj)
+        mean = reduce == "mean"
+        plan = st.fwd_noval if mean else st.fwd
+        out = spmm_raw(plan, x, use_val=not mean, div_rows=mean, bias=bias, relu=relu, drop_p=drop_p, seed=seed)
+        ctx.st, ctx.mean, ctx.relu, ctx.drop_p = st, mean, relu, drop_p
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(out if (relu or drop_p > 0) else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        g = _rowmajor(g)
+        if out is not None:
+            g = relu_drop_bwd_raw(out, g, 1.0 / (1.0 - ctx.drop_p))
+        gb = colsum_raw(g) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            plan = ctx.st.bwd_mean if ctx.mean else ctx.st.bwd
+            gx = spmm_raw(plan, g, use_val=True if ctx.mean else ctx.st.has_value, div_rows=False)
+        return gx, gb, None, None, None, None, None
+
+
+def spmm(adj, x, reduce="sum", bias=None, relu=False, drop_p=0.0, seed=0):
+    if reduce == "add":
+        reduce = "sum"
+    if reduce not in ("sum", "mean"):
+        raise NotImplementedError(f"reduce={reduce!r}")
+    return SpMM.apply(x, bias, adj, reduce, bool(relu), float(drop_p), int(seed))
+
+
+class FusedLinear(torch.autograd.Function):
+    """Y = act( sum_i X_i @ W_i^T + bias ), act in {none, relu(+dropout)}.
+
+    One or more (X_i, W_i) pairs accumulate into one output through the GEMM's beta=1 path, so
+    SAGEConv's lin_l(agg) + lin_r(x) and the concat-free ``[emb | x] @ W^T`` never materialise an
+    intermediate.  W_i may be a column slice of a larger weight (leading dimension respected)."""
+
+    @staticmethod
+    def forward(ctx, bias, act, drop_p, seed, n, *xw):
+        xs, ws = xw[:n], xw[n:]
+        Y = None
+        for i, (x, w) in enumerate(zip(xs, ws)):
+            last = i == n - 1
+            Y = gemm_raw(x, w, transb=True, C=Y, beta=0.0 if i == 0 else 1.0,
+                         bias=bias if i == 0 else None,
+                         act=act if last else ACT_NONE, drop_p=drop_p if last else 0.0, seed=seed)
+        ctx.n, ctx.act, ctx.drop_p = n, act, drop_p
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(Y if act == ACT_RELU else None, *xs, *ws)
+        return Y
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = ctx.saved_tensors
+        Y, n = saved[0], ctx.n
+        xs, ws = saved[1:1 + n], saved[1 + n:]
+        g = _rowmajor(g)
+        if Y is not None:
+            g = relu_drop_bwd_raw(Y, g, 1.0 / (1.0 - ctx.drop_p))
+        gb = colsum_raw(g) if (ctx.has_bias and ctx.needs_input_grad[0]) else None
+        gxs, gws = [], []
+        for i in range(n):
+            gx = gemm_raw(g, ws[i]) if ctx.needs_input_grad[5 + i] else None          # dX = dY @ W
+            gw = gemm_raw(g, xs[i], transa=True) if ctx.needs_input_grad[5 + n + i] else None  # dW = dY^T @ X
+            gxs.append(gx)
+            gws.append(gw)
+        return (gb, None, None, None, None, *gxs, *gws)
+
+
+def fused_linear(xs, ws, bias=None, act=ACT_NONE, drop_p=0.0, seed=0):
+    xs, ws = list(xs), list(ws)
+    return FusedLinear.apply(bias, int(act), float(drop_p), int(seed), len(xs), *xs, *ws)
+
+
+class GatherHadamard(torch.autograd.Function):
+    """h[edges[:,0]] * h[edges[:,1]] in one kernel (model.py:155-156 + layer.py:81)."""
+
+    @staticmethod
+    def forward(ctx, h, edges):
+        ctx.save_for_backward(h, edges)
+        return gather_hadamard_raw(h, edges)
+
+    @staticmethod
+    def backward(ctx, g):
+        h, edges = ctx.saved_tensors
+        return edge_scatter_raw(h, edges, da=g), None
+
+
+class EdgeDot(torch.autograd.Function):
+    """DotPredictor over gathered endpoints: score[p] = <h[src_p], h[dst_p]>."""
+
+    @staticmethod
+    def forward(ctx, h, edges):
+        ctx.save_for_backward(h, edges)
+        return edge_dot_raw(h, edges)
+
+    @staticmethod
+    def backward(ctx, g):
+        h, edges = ctx.saved_tensors
+        return edge_scatter_raw(h, edges, dscore=g), None
+
+
+class MLPOut(torch.autograd.Function):
+    """last MLPPredictor layer (out_channels = 1): a @ w^T + b -> [P, 1]."""
+
+    @staticmethod
+    def forward(ctx, a, w, b):
+        ctx.save_for_backward(a, w)
+        ctx.has_b = b is not None
+        return mlp_out_fwd_raw(a, w, b).reshape(-1, 1)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, w = ctx.saved_tensors
+        dz, dw, db = mlp_out_bwd_raw(a, w, g.reshape(-1), mask_a=False, drop_scale=1.0)
+        return dz, dw.reshape(w.shape), (db if ctx.has_b else None)
+
+
+class PairLoss(torch.autograd.Function):
+    """loss.py:5-14, 31-35: forward and d loss / d score from one kernel."""
+
+    @staticmethod
+    def forward(ctx, pos_out, neg_out, weight, kind, num_neg):
+        loss, dpos, dneg = pair_loss_raw(kind, pos_out, neg_out, num_neg, weight)
+        ctx.save_for_backward(dpos, dneg)
+        ctx.shapes = (pos_out.shape, neg_out.shape)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        dpos, dneg = ctx.saved_tensors
+        return (dpos * g).reshape(ctx.shapes[0]), (dneg * g).reshape(ctx.shapes[1]), None, None, None
+
+
+def pair_loss(name, pos_out, neg_out, num_neg, weight=None):
+    return PairLoss.apply(pos_out, neg_out, weight, LOSS_KINDS[name], int(num_neg))
+
+
+class EdgeScoreLoss(torch.autograd.Function):
+    """The fused scoring step of BaseModel.train (model.py:152-160): gather both endpoints of
+    every positive and negative pair, Hadamard, predictor head, pairwise loss and d loss / d score,
+    returning the scalar loss; backward produces grad_h and the predictor parameter gradients
+    without autograd recording the per-pair intermediates.
+
+    head = 'MLP': params = (W_0, b_0, ..., W_{L-1}, b_{L-1}) with the last layer [1, H];
+    head = 'DOT': no params.
+    """
+
+    @staticmethod
+    def forward(ctx, h, edges, weight, head, kind, num_neg, n_pos, drop_p, seed, *params):
+        edges = _edges_i64(edges)
+        drops = []
+        if head == "DOT":
+            score = edge_dot_raw(h, edges)
+            acts = []
+        else:
+            L = len(params) // 2
+            a = gather_hadamard_raw(h, edges)
+            acts = [a]
+            for i in range(L - 1):
+                s = seed + 7919 * (i + 1)
+                a = gemm_raw(a, params[2 * i], transb=True, bias=params[2 * i + 1], act=ACT_RELU,
+                             drop_p=drop_p, seed=s)
+                acts.append(a)
+                drops.append(s)
+            score = mlp_out_fwd_raw(a, params[2 * (L - 1)], params[2 * (L - 1) + 1])
+        loss, dpos, dneg = pair_loss_raw(kind, score[:n_pos], score[n_pos:], num_neg, weight)
+        ctx.head, ctx.drop_p, ctx.n_params = head, drop_p, len(params)
+        ctx.save_for_backward(h, edges, dpos, dneg, *acts, *params)
+        ctx.n_acts = len(acts)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = ctx.saved_tensors
+        h, edges, dpos, dneg = saved[:4]
+        acts = saved[4:4 + ctx.n_acts]
+        params = saved[4 + ctx.n_acts:]
+        dscore = torch.cat([dpos, dneg]) * g
+        if ctx.head == "DOT":
+            gh = edge_scatter_raw(h, edges, dscore=dscore)
+            return (gh,) + (None,) * 8
+        L = len(params) // 2
+        scale = 1.0 / (1.0 - ctx.drop_p)
+        grads = [None] * len(params)
+        # last layer: dz w.r.t. the pre-activation of the previous hidden layer (mask fused)
+        dz, dw, db = mlp_out_bwd_raw(acts[-1], params[2 * (L - 1)], dscore, mask_a=(L > 1), drop_scale=scale)
+        grads[2 * (L - 1)] = dw.reshape(params[2 * (L - 1)].shape)
+        grads[2 * (L - 1) + 1] = db.reshape(params[2 * (L - 1) + 1].shape)
+        for i in range(L - 2, -1, -1):
+            W = params[2 * i]
+            grads[2 * i] = gemm_raw(dz, acts[i], transa=True)            # dW_i = dZ_i^T @ A_{i-1}
+            grads[2 * i + 1] = colsum_raw(dz)
+            if i > 0:   # dA_{i-1} = dZ_i @ W_i, masked by relu/dropout of layer i-1
+                dz = gemm_raw(dz, W, act=ACT_RELU_GRAD, aux=acts[i], drop_p=ctx.drop_p)
+            else:
+                dz = gemm_raw(dz, W)                                      # d loss / d hadamard
+        gh = edge_scatter_raw(h, edges, da=dz)
+        return (gh,) + (None,) * 8 + tuple(grads)
+
+
+def edge_score_loss(h, pos_edge, neg_edge, num_neg, loss_name, weight=None, head="MLP", params=(),
+                    drop_p=0.0, seed=0):
+    """pos_edge [B,2], neg_edge [B*num_neg,2] (negatives of positive i in rows i*k..i*k+k-1)."""
+    edges = torch.cat([pos_edge, neg_edge], 0)
+    return EdgeScoreLoss.apply(h, edges, weight, head, LOSS_KINDS[loss_name], int(num_neg), pos_edge.size(0),
+                               float(drop_p), int(seed), *params)
+
+
+# ---------------------------------------------------------------------------
+# samplers and ranking (no autograd)
+# ---------------------------------------------------------------------------
+def local_neg_sample_raw(pos_edges, num_nodes, num_neg, seed):
+    lib = _lib.load()
+    pos_edges = _edges_i64(pos_edges)
+    E = pos_edges.size(0)
+    out = torch.empty(E, num_neg, 2, dtype=torch.int64, device=pos_edges.device)
+    check(lib.plnlp_local_neg_sample(ptr(pos_edges), E, int(num_nodes), int(num_neg), int(seed), ptr(out),
+                                     stream()), "plnlp_local_neg_sample")
+    return out
+
+
+def global_neg_candidates_raw(edge_ids_sorted, num_nodes, n_cand, seed):
+    """-> (cand_ids [n_cand] int64, keep [n_cand] uint8)"""
+    lib = _lib.load()
+    dev = edge_ids_sorted.device
+    table_size = 1
+    while table_size < 2 * max(n_cand, 1):
+        table_size *= 2
+    keys = torch.full((table_size,), -1, dtype=torch.int64, device=dev)
+    first = torch.full((table_size,), -1, dtype=torch.int32, device=dev)
+    cand = torch.empty(n_cand, dtype=torch.int64, device=dev)
+    keep = torch.empty(n_cand, dtype=torch.uint8, device=dev)
+    check(lib.plnlp_global_neg_candidates(ptr(edge_ids_sorted), edge_ids_sorted.numel(), int(num_nodes), n_cand,
+                                          int(seed), ptr(cand), ptr(keys), ptr(first), table_size, stream()),
+          "plnlp_global_neg_candidates")
+    check(lib.plnlp_global_neg_keep(ptr(cand), n_cand, ptr(keys), ptr(first), table_size, ptr(keep), stream()),
+          "plnlp_global_neg_keep")
+    return cand, keep
+
+
+def kth_largest_raw(x, K):
+    lib = _lib.load()
+    x = _f32c(x).reshape(-1).contiguous()
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    ws = workspace.get("kth", 8192, x.device)
+    check(lib.plnlp_kth_largest_f32(ptr(x), x.numel(), int(K), ptr(out), ptr(ws), 8192, stream()),
+          "plnlp_kth_largest_f32")
+    return out
+
+
+def count_greater_raw(x, thresh):
+    lib = _lib.load()
+    x = _f32c(x).reshape(-1).contiguous()
+    cnt = torch.empty(1, dtype=torch.int64, device=x.device)
+    check(lib.plnlp_count_greater_f32(ptr(x), x.numel(), ptr(thresh), ptr(cnt), stream()),
+          "plnlp_count_greater_f32")
+    return cnt
+
+
+def mrr_counts_raw(pos, neg):
+    lib = _lib.load()
+    pos = _f32c(pos).reshape(-1).contiguous()
+    neg = _rowmajor(neg)
+    S, K = neg.shape
+    gt = torch.empty(S, dtype=torch.int32, device=pos.device)
+    ge = torch.empty(S, dtype=torch.int32, device=pos.device)
+    check(lib.plnlp_mrr_counts_f32(ptr(pos), ptr(neg), _ld(neg), S, K, ptr(gt), ptr(ge), stream()),
+          "plnlp_mrr_counts_f32")
+    return gt, ge

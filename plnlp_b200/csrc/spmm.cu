@@ -1,0 +1,236 @@
+// CSR row-gather SpMM for sm_100a: out[r,:] = epi( (sum_{p in row r} val[p] * x[col[p],:]) / row_div[r] )
+//
+// Replaces torch_sparse.matmul under SAGEConv / GCNConv (/root/reference/plnlp/layer.py:20,23)
+// and its backward (same kernel on the transposed structure).
+//
+// Design (HBM/L2-bound gather, no tensor cores):
+//  * one warp per work item (a whole row, or a <=chunk slice of a hub row -- see the plan in
+//    plnlp_b200/graph.py); lanes own fixed feature columns, so each output element is
+//    accumulated strictly in CSR order (bit-identical to the in-order CPU loop for unsplit rows).
+//  * column indices are fetched 32 at a time (one coalesced 128 B load) and broadcast by shuffle;
+//  * feature rows are gathered with 16-byte loads, NB neighbours x U vectors per lane in flight
+//    (8 independent 16 B loads per lane) before any of them is consumed;
+//  * valued accumulation uses separate fp32 multiply and add (no FMA contraction) so that the
+//    result equals the reference CPU loop bit for bit; the kernel is memory-bound, the extra
+//    instruction is free.
+#include "common.cuh"
+
+namespace plnlp {
+
+struct SpmmParams {
+    const int32_t* item_ptr;
+    const int32_t* item_row;
+    const int32_t* item_slot;
+    int64_t n_items;
+    const int32_t* col;
+    const float* val;
+    const float* row_div;
+    const float* bias;
+    int relu;
+    float drop_p;
+    uint64_t seed;
+    const float* x;
+    int64_t ldx;
+    float* out;
+    int64_t ldo;
+    int F;
+    float* partial;
+    const int32_t* fix_ptr;
+    const int32_t* fix_row;
+    int64_t n_fix;
+};
+
+// finished-row epilogue for the VEC features starting at column f of row `row`
+template <int VEC>
+__device__ __forceinline__ void finish_store(const SpmmParams& p, int row, int f, float (&a)[VEC]) {
+    if (p.row_div) {
+        const float d = __ldg(p.row_div + row);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) a[e] = a[e] / d;
+    }
+    if (p.bias) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) a[e] += __ldg(p.bias + f + e);
+    }
+    if (p.relu) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) a[e] = fmaxf(a[e], 0.0f);
+    }
+    if (p.drop_p > 0.0f) {
+        const float s = 1.0f / (1.0f - p.drop_p);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const uint64_t idx = static_cast<uint64_t>(row) * static_cast<uint64_t>(p.F) + (f + e);
+            a[e] = dropout_keep(p.seed, idx, p.drop_p) ? a[e] * s : 0.0f;
+        }
+    }
+    store_vec<VEC>(p.out + static_cast<int64_t>(row) * p.ldo + f, a);
+}
+
+template <int VEC, int U, int NB, bool HAS_VAL, bool PRED>
+__device__ __forceinline__ void gather_block(const float* __restrict__ xb, int64_t ldx, int c, float v,
+                                             int j, int n, const bool (&act)[U], float (&acc)[U][VEC]) {
+    float t[NB][U][VEC];
+    float vv[NB];
+    bool ok[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int jj = j + b;
+        const int cj = __shfl_sync(0xffffffffu, c, jj & 31);
+        vv[b] = HAS_VAL ? __shfl_sync(0xffffffffu, v, jj & 31) : 1.0f;
+        ok[b] = !PRED || (jj < n);
+        const float* row = xb + static_cast<int64_t>(cj) * ldx;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (ok[b] && act[u]) {
+                load_vec<VEC>(t[b][u], row + u * 32 * VEC);
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) t[b][u][e] = 0.0f;
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        if (ok[b]) {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e)
+                    acc[u][e] = HAS_VAL ? __fadd_rn(acc[u][e], __fmul_rn(vv[b], t[b][u][e]))
+                                        : __fadd_rn(acc[u][e], t[b][u][e]);
+        }
+    }
+}
+
+template <int VEC, int U, bool HAS_VAL>
+__global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
+    constexpr int NB = (U == 1) ? 8 : (U == 2) ? 4 : 2;
+    const int lane = threadIdx.x & 31;
+    const int64_t item = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= p.n_items) return;
+    const int fbase = blockIdx.y * (32 * VEC * U) + lane * VEC;
+    bool act[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) act[u] = (fbase + u * 32 * VEC) < p.F;
+
+    float acc[U][VEC];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[u][e] = 0.0f;
+
+    const int beg = __ldg(p.item_ptr + item), end = __ldg(p.item_ptr + item + 1);
+    const float* __restrict__ xb = p.x + fbase;
+    for (int base = beg; base < end; base += 32) {
+        const int n = min(32, end - base);
+        int c = 0;
+        float v = 0.0f;
+        if (lane < n) {
+            c = __ldg(p.col + base + lane);
+            if (HAS_VAL) v = __ldg(p.val + base + lane);
+        }
+        if (n == 32) {
+#pragma unroll 1
+            for (int j = 0; j < 32; j += NB)
+                gather_block<VEC, U, NB, HAS_VAL, false>(xb, p.ldx, c, v, j, n, act, acc);
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < n; j += NB)
+                gather_block<VEC, U, NB, HAS_VAL, true>(xb, p.ldx, c, v, j, n, act, acc);
+        }
+    }
+
+    const int row = __ldg(p.item_row + item);
+    const int slot = __ldg(p.item_slot + item);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (!act[u]) continue;
+        const int f = fbase + u * 32 * VEC;
+        if (slot >= 0) {
+            store_vec<VEC>(p.partial + static_cast<int64_t>(slot) * p.F + f, acc[u]);
+        } else {
+            finish_store<VEC>(p, row, f, acc[u]);
+        }
+    }
+}
+
+// second pass for split (hub) rows: sum the partial slots in slot order, then the epilogue
+template <int VEC, int U>
+__global__ void __launch_bounds__(256) spmm_fix_kernel(const SpmmParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= p.n_fix) return;
+    const int fbase = blockIdx.y * (32 * VEC * U) + lane * VEC;
+    const int s0 = __ldg(p.fix_ptr + j), s1 = __ldg(p.fix_ptr + j + 1);
+    const int row = __ldg(p.fix_row + j);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int f = fbase + u * 32 * VEC;
+        if (f >= p.F) continue;
+        float a[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) a[e] = 0.0f;
+        for (int s = s0; s < s1; ++s) {
+            float t[VEC];
+            load_vec<VEC>(t, p.partial + static_cast<int64_t>(s) * p.F + f);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) a[e] = __fadd_rn(a[e], t[e]);
+        }
+        finish_store<VEC>(p, row, f, a);
+    }
+}
+
+template <int VEC, int U>
+static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
+    const int per = 32 * VEC * U;
+    const unsigned slabs = static_cast<unsigned>(ceil_div(p.F, per));
+    const dim3 block(256);
+    if (p.n_items > 0) {
+        const dim3 grid(static_cast<unsigned>(ceil_div(p.n_items, 8)), slabs);
+        if (p.val) spmm_csr_kernel<VEC, U, true><<<grid, block, 0, st>>>(p);
+        else       spmm_csr_kernel<VEC, U, false><<<grid, block, 0, st>>>(p);
+        PLNLP_LAUNCH_CHECK();
+    }
+    if (p.n_fix > 0) {
+        const dim3 grid(static_cast<unsigned>(ceil_div(p.n_fix, 8)), slabs);
+        spmm_fix_kernel<VEC, U><<<grid, block, 0, st>>>(p);
+        PLNLP_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+template <int VEC>
+static int dispatch_u(const SpmmParams& p, cudaStream_t st) {
+    const int64_t lanes_needed = ceil_div(p.F, VEC);
+    if (lanes_needed <= 32) return launch_spmm<VEC, 1>(p, st);
+    if (lanes_needed <= 64) return launch_spmm<VEC, 2>(p, st);
+    return launch_spmm<VEC, 4>(p, st);
+}
+
+}  // namespace plnlp
+
+extern "C" int plnlp_spmm_csr_f32(const int32_t* item_ptr, const int32_t* item_row, const int32_t* item_slot,
+                                  int64_t n_items, const int32_t* col, const float* val,
+                                  const float* row_div, const float* bias, int relu, float drop_p,
+                                  uint64_t seed, const float* x, int64_t ldx, float* out, int64_t ldo,
+                                  int64_t F, float* partial, const int32_t* fix_ptr, const int32_t* fix_row,
+                                  int64_t n_fix, void* stream) {
+    using namespace plnlp;
+    PLNLP_REQUIRE(n_items >= 0 && n_fix >= 0 && F > 0 && F < (1 << 30), PLNLP_E_SIZE);
+    if (n_items == 0) return 0;
+    PLNLP_REQUIRE(item_ptr && item_row && item_slot && x && out, PLNLP_E_NULL);
+    PLNLP_REQUIRE(ldx >= F && ldo >= F, PLNLP_E_SIZE);
+    PLNLP_REQUIRE(drop_p >= 0.0f && drop_p < 1.0f, PLNLP_E_SIZE);
+    if (n_fix > 0) PLNLP_REQUIRE(partial && fix_ptr && fix_row, PLNLP_E_NULL);
+    SpmmParams p{item_ptr, item_row, item_slot, n_items, col, val, row_div, bias, relu, drop_p, seed,
+                 x, ldx, out, ldo, static_cast<int>(F), partial, fix_ptr, fix_row, n_fix};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool v4 = (F % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned(x, 16) && aligned(out, 16) &&
+                    (!partial || aligned(partial, 16));
+    const bool v2 = (F % 2 == 0) && (ldx % 2 == 0) && (ldo % 2 == 0) && aligned(x, 8) && aligned(out, 8) &&
+                    (!partial || aligned(partial, 8));
+    if (v4) return dispatch_u<4>(p, st);
+    if (v2) return dispatch_u<2>(p, st);
+    return dispatch_u<1>(p, st);
+}

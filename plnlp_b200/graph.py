@@ -1,0 +1,283 @@
+"""Adjacency holder and the per-graph structure cache behind the SpMM kernels.
+
+``CSRGraph`` is the adjacency object of this package.  It exposes the subset of the
+``torch_sparse.SparseTensor`` surface the reference touches (``csr()``, ``coo()``,
+``size()``, ``set_value()``, ``to_symmetric()``, ``set_diag()``, ``sum(dim=1)``, row / column
+broadcast multiplication, ``t()``, ``to()``), built from torch index ops on whatever device
+the tensors live on, so ``/root/reference/main.py:81-83,109-110,177-179`` style graph
+preparation works on it unchanged.  A real ``torch_sparse.SparseTensor`` is accepted anywhere
+a ``CSRGraph`` is (duck-typed through ``.csr()`` / ``.size()``).
+
+``structure_of(adj)`` returns the cached device-side structure the kernels consume: int32
+column indices, fp32 values, the SpMM work plan (rows cut into <= chunk slices so hub rows
+of power-law graphs do not serialise one warp), and the same for the transposed matrix used by
+the backward pass.  The adjacency is constant for a whole run (main.py:175-186), so this is
+built once.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class CSRGraph:
+    def __init__(self, rowptr, col, value=None, sparse_sizes=None, row=None):
+        self._rowptr = rowptr.to(torch.int64)
+        self._col = col.to(torch.int64)
+        self._value = value
+        if sparse_sizes is None:
+            sparse_sizes = (rowptr.numel() - 1, rowptr.numel() - 1)
+        self._sizes = (int(sparse_sizes[0]), int(sparse_sizes[1]))
+        self._row = row
+
+    # ---- construction -----------------------------------------------------
+    @staticmethod
+    def from_coo(row, col, value=None, sparse_sizes=None, is_sorted=False):
+        """SparseTensor(row=, col=, value=) (main.py:124-126): sort by (row, col), keep duplicates."""
+        if sparse_sizes is None:
+            n = int(torch.max(torch.stack([row.max(), col.max()]))) + 1 if row.numel() else 0
+            sparse_sizes = (n, n)
+        M, N = int(sparse_sizes[0]), int(sparse_sizes[1])
+        row, col = row.to(torch.int64), col.to(torch.int64)
+        if not is_sorted:
+            perm = torch.argsort(row * N + col, stable=True)
+            row, col = row[perm], col[perm]
+            if value is not None:
+                value = value[perm]
+        rowptr = torch.zeros(M + 1, dtype=torch.int64, device=row.device)
+        if row.numel():
+            rowptr[1:] = torch.cumsum(torch.bincount(row, minlength=M), 0)
+        return CSRGraph(rowptr, col, value, (M, N), row=row)
+
+    @staticmethod
+    def from_edge_index(edge_index, edge_weight=None, num_nodes=None):
+        """``T.ToSparseTensor()`` (main.py:81): adj_t[dst, src]."""
+        N = int(num_nodes) if num_nodes is not None else int(edge_index.max()) + 1
+        return CSRGraph.from_coo(edge_index[1], edge_index[0], edge_weight, (N, N))
+
+    # ---- torch_sparse-like accessors ---------------------------------------
+    def size(self, dim):
+        return self._sizes[dim]
+
+    def sizes(self):
+        return list(self._sizes)
+
+    def sparse_sizes(self):
+        return self._sizes
+
+    def nnz(self):
+        return self._col.numel()
+
+    @property
+    def device(self):
+        return self._col.device
+
+    def has_value(self):
+        return self._value is not None
+
+    def csr(self):
+        return self._rowptr, self._col, self._value
+
+    def _rows(self):
+        if self._row is None:
+            cnt = self._rowptr[1:] - self._rowptr[:-1]
+            self._row = torch.repeat_interleave(
+                torch.arange(self._sizes[0], device=self._col.device), cnt, output_size=self._col.numel())
+        return self._row
+
+    def coo(self):
+        return self._rows(), self._col, self._value
+
+    def set_value(self, value, layout=None):
+        return CSRGraph(self._rowptr, self._col, value, self._sizes, row=self._row)
+
+    def to(self, device, *args, **kwargs):
+        mv = lambda t: None if t is None else t.to(device)  # noqa: E731
+        return CSRGraph(mv(self._rowptr), mv(self._col), mv(self._value), self._sizes, row=mv(self._row))
+
+    def cuda(self):
+        return self.to("cuda")
+
+    def t(self):
+        row, col, value = self.coo()
+        return CSRGraph.from_coo(col, row, value, (self._sizes[1], self._sizes[0]))
+
+    def to_symmetric(self):
+        """main.py:110: union of (r,c) and (c,r), sorted, duplicates merged (values summed)."""
+        N = max(self._sizes)
+        row, col, value = self.coo()
+        key = torch.cat([row * N + col, col * N + row])
+        if value is None:
+            key = torch.unique(key)
+            return CSRGraph.from_coo(torch.div(key, N, rounding_mode="floor"), key % N, None, (N, N), True)
+        ukey, inv = torch.unique(key, return_inverse=True)
+        v = torch.zeros(ukey.numel(), dtype=value.dtype, device=value.device)
+        v.index_add_(0, inv, torch.cat([value, value]))
+        return CSRGraph.from_coo(torch.div(ukey, N, rounding_mode="floor"), ukey % N, v, (N, N), True)
+
+    def set_diag(self):
+        """utils.py:84: drop the stored diagonal, add one unit entry per row."""
+        M, N = self._sizes
+        row, col, value = self.coo()
+        keep = row != col
+        d = torch.arange(min(M, N), dtype=torch.int64, device=col.device)
+        nval = None
+        if value is not None:
+            nval = torch.cat([value[keep], torch.ones(d.numel(), dtype=value.dtype, device=col.device)])
+        return CSRGraph.from_coo(torch.cat([row[keep], d]), torch.cat([col[keep], d]), nval, (M, N))
+
+    def sum(self, dim=1):
+        if dim != 1:
+            raise NotImplementedError("only row sums are used by the reference (utils.py:85,93)")
+        if self._value is None:
+            return self._rowptr[1:] - self._rowptr[:-1]
+        out = torch.zeros(self._sizes[0], dtype=self._value.dtype, device=self._value.device)
+        return out.index_add_(0, self._rows(), self._value)
+
+    def _scaled(self, dense):
+        M, N = self._sizes
+        if dense.dim() == 2 and dense.size(0) == M and dense.size(1) == 1:
+            f = dense.reshape(-1)[self._rows()]
+        elif dense.dim() == 2 and dense.size(0) == 1 and dense.size(1) == N:
+            f = dense.reshape(-1)[self._col]
+        else:
+            raise NotImplementedError("only [M,1] / [1,N] broadcasts are used by the reference (utils.py:88,96)")
+        return self.set_value(f if self._value is None else f.to(self._value.dtype) * self._value)
+
+    def __mul__(self, dense):
+        return self._scaled(dense)
+
+    def __rmul__(self, dense):
+        return self._scaled(dense)
+
+    def to_dense(self):
+        M, N = self._sizes
+        v = self._value if self._value is not None else torch.ones(self.nnz(), device=self._col.device)
+        out = torch.zeros(M, N, dtype=v.dtype, device=v.device)
+        return out.index_put_((self._rows(), self._col), v, accumulate=True)
+
+
+SparseTensor = CSRGraph  # name used by main.py-style code
+
+
+# ---------------------------------------------------------------------------
+# SpMM work plan + structure cache
+# ---------------------------------------------------------------------------
+class SpmmPlan:
+    """Device arrays consumed by ``plnlp_spmm_csr_f32`` for one CSR matrix."""
+
+    __slots__ = ("n_rows", "n_cols", "nnz", "chunk", "col", "val", "item_ptr", "item_row", "item_slot",
+                 "n_items", "fix_ptr", "fix_row", "n_fix", "n_partial", "row_cnt")
+
+    def alg_bytes(self, F, elem=4):
+        """ALGORITHMIC bytes of one launch: gathered rows + indices +
+        values + row pointers + output write."""
+        return (self.nnz * F * elem + self.nnz * 4 + (self.nnz * 4 if self.val is not None else 0)
+                + (self.n_rows + 1) * 8 + self.n_rows * F * elem)
+
+
+def _pick_chunk(nnz, n_rows):
+    # aim for >= ~19k warp-items (148 SMs x 32 resident warps x 4) while never splitting
+    # rows shorter than 64 entries and never letting one warp walk more than 1024
+    target = max(nnz // 19000, 1)
+    chunk = ((target + 31) // 32) * 32
+    return int(min(1024, max(64, chunk)))
+
+
+def build_plan(rowptr, col, val, n_rows, n_cols, chunk=None):
+    dev = col.device
+    nnz = col.numel()
+    if nnz >= 2 ** 31 - 1 or n_rows >= 2 ** 31 - 1:
+        raise RuntimeError("plnlp_b200 SpMM plans use int32 offsets: nnz and rows must be < 2^31")
+    if chunk is None:
+        chunk = _pick_chunk(nnz, n_rows)
+    deg = rowptr[1:] - rowptr[:-1]
+    n_it = torch.clamp((deg + chunk - 1) // chunk, min=1)
+    n_items = int(n_it.sum())
+    rows = torch.arange(n_rows, device=dev)
+    item_row = torch.repeat_interleave(rows, n_it, output_size=n_items)
+    first = torch.cumsum(n_it, 0) - n_it
+    k = torch.arange(n_items, device=dev) - first[item_row]
+    item_beg = rowptr[:-1][item_row] + k * chunk
+    item_ptr = torch.cat([item_beg, torch.tensor([nnz], device=dev, dtype=torch.int64)])
+    multi_row = n_it > 1
+    multi_item = multi_row[item_row]
+    slot = torch.cumsum(multi_item.to(torch.int64), 0) - 1
+    item_slot = torch.where(multi_item, slot, torch.full_like(slot, -1))
+    fix_row = torch.nonzero(multi_row).reshape(-1)
+    fix_cnt = n_it[fix_row]
+    fix_ptr = torch.zeros(fix_row.numel() + 1, dtype=torch.int64, device=dev)
+    if fix_row.numel():
+        fix_ptr[1:] = torch.cumsum(fix_cnt, 0)
+    p = SpmmPlan()
+    p.n_rows, p.n_cols, p.nnz, p.chunk = int(n_rows), int(n_cols), int(nnz), int(chunk)
+    p.col = col.to(torch.int32).contiguous()
+    p.val = None if val is None else val.to(torch.float32).contiguous()
+    p.item_ptr = item_ptr.to(torch.int32).contiguous()
+    p.item_row = item_row.to(torch.int32).contiguous()
+    p.item_slot = item_slot.to(torch.int32).contiguous()
+    p.n_items = n_items
+    p.fix_ptr = fix_ptr.to(torch.int32).contiguous()
+    p.fix_row = fix_row.to(torch.int32).contiguous()
+    p.n_fix = int(fix_row.numel())
+    p.n_partial = int(fix_ptr[-1]) if fix_row.numel() else 0
+    p.row_cnt = torch.clamp(deg, min=1).to(torch.float32).contiguous()  # mean divisor, max(row_nnz, 1)
+    return p
+
+
+class Structure:
+    """Everything the encoder kernels need about one adjacency, forward and transposed."""
+
+    def __init__(self, adj, chunk=None):
+        rowptr, col, val = adj.csr()
+        if not col.is_cuda:
+            raise RuntimeError("plnlp_b200 needs the adjacency on a CUDA device; there is no CPU path")
+        M, N = adj.size(0), adj.size(1)
+        rowptr, col = rowptr.to(torch.int64), col.to(torch.int64)
+        self.n_rows, self.n_cols = M, N
+        self.has_value = val is not None
+        # forward plans: valued (GCN, 'sum') and value-less (SAGE drops values, 'mean')
+        self.fwd = build_plan(rowptr, col, val, M, N, chunk)
+        self.fwd_noval = self.fwd if val is None else _share_plan(self.fwd, None)
+        # transposed structure (backward): sort entries by (col, row)
+        deg = rowptr[1:] - rowptr[:-1]
+        row = torch.repeat_interleave(torch.arange(M, device=col.device), deg, output_size=col.numel())
+        perm = torch.argsort(col * M + row, stable=True)
+        t_row, t_col = col[perm], row[perm]
+        t_rowptr = torch.zeros(N + 1, dtype=torch.int64, device=col.device)
+        if t_row.numel():
+            t_rowptr[1:] = torch.cumsum(torch.bincount(t_row, minlength=N), 0)
+        t_val = None if val is None else val.to(torch.float32)[perm]
+        self.bwd = build_plan(t_rowptr, t_col, t_val, N, M, chunk)
+        # mean backward: A^T D^-1 g  ->  transposed entries carry 1/max(deg_row,1) of their source row
+        inv = 1.0 / torch.clamp(deg, min=1).to(torch.float32)
+        self.bwd_mean = _share_plan(self.bwd, inv[t_col].contiguous())
+        self.symmetric = bool(M == N and torch.equal(t_rowptr, rowptr) and torch.equal(t_col, col))
+        if self.symmetric:  # share the index arrays, halve the footprint
+            for p in (self.bwd, self.bwd_mean):
+                p.col, p.item_ptr, p.item_row, p.item_slot = (self.fwd.col, self.fwd.item_ptr,
+                                                              self.fwd.item_row, self.fwd.item_slot)
+                p.fix_ptr, p.fix_row = self.fwd.fix_ptr, self.fwd.fix_row
+
+
+def _share_plan(plan, val):
+    q = SpmmPlan()
+    for s in SpmmPlan.__slots__:
+        setattr(q, s, getattr(plan, s))
+    q.val = val
+    return q
+
+
+_CACHE = {}
+
+
+def structure_of(adj):
+    """Cached ``Structure`` of an adjacency object (CSRGraph or torch_sparse.SparseTensor)."""
+    key = id(adj)
+    hit = _CACHE.get(key)
+    if hit is not None and hit[0] is adj:
+        return hit[1]
+    st = Structure(adj)
+    if len(_CACHE) > 16:
+        _CACHE.clear()
+    _CACHE[key] = (adj, st)
+    return st

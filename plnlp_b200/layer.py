@@ -1,0 +1,221 @@
+"""Encoders and link predictors with the reference's module surface
+(/root/reference/plnlp/layer.py), running on the plnlp_b200 kernels.
+
+Differences a user can see: none for the in-scope classes (same constructor arguments, same
+``.convs`` / ``.lins`` containers, same parameter names, same ``forward`` signatures and output
+shapes).  Internally relu + dropout are fused into the producing kernel's epilogue and the conv
+modules additionally accept a tuple of input blocks so ``[emb | x]`` is never concatenated.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _ops
+
+
+def _as_parts(x):
+    return list(x) if isinstance(x, (tuple, list)) else [x]
+
+
+def _split_cols(weight, parts):
+    """column blocks of ``weight`` matching the widths of ``parts`` (views, no copy)."""
+    if len(parts) == 1:
+        return [weight]
+    out, c = [], 0
+    for p in parts:
+        out.append(weight[:, c:c + p.size(1)])
+        c += p.size(1)
+    if c != weight.size(1):
+        raise RuntimeError(f"input blocks have {c} columns, the layer expects {weight.size(1)}")
+    return out
+
+
+def _kaiming_linear_(weight, bias):
+    """torch.nn.Linear's default init (what PyG 2.0.1's SAGEConv lins use)."""
+    torch.nn.init.kaiming_uniform_(weight, a=math.sqrt(5))
+    if bias is not None:
+        bound = 1.0 / math.sqrt(weight.size(1)) if weight.size(1) > 0 else 0.0
+        torch.nn.init.uniform_(bias, -bound, bound)
+
+
+class _Lin(torch.nn.Module):
+    """parameter holder named like torch.nn.Linear (``weight`` [out, in], optional ``bias``)."""
+
+    def __init__(self, in_channels, out_channels, bias=True):
+        super().__init__()
+        self.in_features, self.out_features = in_channels, out_channels
+        self.weight = torch.nn.Parameter(torch.empty(out_channels, in_channels))
+        self.bias = torch.nn.Parameter(torch.empty(out_channels)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        _kaiming_linear_(self.weight, self.bias)
+
+    def forward(self, x, act=_ops.ACT_NONE, drop_p=0.0):
+        lead = x.shape[:-1]
+        y = _ops.fused_linear([x.reshape(-1, x.size(-1))], [self.weight], self.bias, act, drop_p,
+                              _ops.new_seed() if drop_p > 0 else 0)
+        return y.reshape(*lead, self.out_features)
+
+
+class SAGEConv(torch.nn.Module):
+    """mean-aggregating GraphSAGE conv: lin_l(mean_{j in N(i)} x_j) + lin_r(x_i), adjacency values
+    ignored (what ``SAGEConv(in, out)`` of PyG 2.0.1 computes at layer.py:36).  Parameters:
+    lin_l.weight, lin_l.bias, lin_r.weight."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin_l = _Lin(in_channels, out_channels, bias=True)
+        self.lin_r = _Lin(in_channels, out_channels, bias=False)
+
+    def reset_parameters(self):
+        self.lin_l.reset_parameters()
+        self.lin_r.reset_parameters()
+
+    def forward(self, x, adj_t, act=_ops.ACT_NONE, drop_p=0.0):
+        parts = _as_parts(x)
+        aggs = [_ops.spmm(adj_t, p, reduce="mean") for p in parts]
+        wl, wr = _split_cols(self.lin_l.weight, parts), _split_cols(self.lin_r.weight, parts)
+        return _ops.fused_linear(aggs + parts, wl + wr, self.lin_l.bias, act, drop_p,
+                                 _ops.new_seed() if drop_p > 0 else 0)
+
+
+class GCNConv(torch.nn.Module):
+    """``GCNConv(in, out, normalize=False)`` (layer.py:45): A_hat @ (x W^T) + bias with the
+    pre-normalised adjacency.  Parameters: lin.weight (glorot), bias (zeros)."""
+
+    def __init__(self, in_channels, out_channels, normalize=False):
+        super().__init__()
+        if normalize:
+            raise NotImplementedError("the reference pre-normalises the adjacency (main.py:177-179)")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin = _Lin(in_channels, out_channels, bias=False)
+        self.bias = torch.nn.Parameter(torch.zeros(out_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        a = math.sqrt(6.0 / (self.in_channels + self.out_channels))
+        torch.nn.init.uniform_(self.lin.weight, -a, a)
+        torch.nn.init.zeros_(self.bias)
+
+    def forward(self, x, adj_t, act=_ops.ACT_NONE, drop_p=0.0):
+        parts = _as_parts(x)
+        z = _ops.fused_linear(parts, _split_cols(self.lin.weight, parts))
+        return _ops.spmm(adj_t, z, reduce="sum", bias=self.bias, relu=(act == _ops.ACT_RELU),
+                         drop_p=drop_p, seed=_ops.new_seed() if drop_p > 0 else 0)
+
+
+class BaseGNN(torch.nn.Module):
+    """layer stacking of layer.py:7-27: relu + dropout after every conv but the last; a 1-layer
+    net also applies them to its only conv."""
+
+    def __init__(self, dropout, num_layers):
+        super().__init__()
+        self.convs = torch.nn.ModuleList()
+        self.dropout = dropout
+        self.num_layers = num_layers
+
+    def reset_parameters(self):
+        for conv in self.convs:
+            conv.reset_parameters()
+
+    def forward(self, x, adj_t):
+        p = self.dropout if self.training else 0.0
+        last = len(self.convs) - 1
+        for i, conv in enumerate(self.convs):
+            fused = i < last or self.num_layers == 1
+            x = conv(x, adj_t, act=_ops.ACT_RELU if fused else _ops.ACT_NONE, drop_p=p if fused else 0.0)
+        return x
+
+
+def _stack(conv_cls, in_channels, hidden_channels, out_channels, num_layers):
+    dims = [in_channels] + [hidden_channels] * (num_layers - 1) + [out_channels]
+    return [conv_cls(dims[i], dims[i + 1]) for i in range(num_layers)]
+
+
+class SAGE(BaseGNN):
+    def __init__(self, in_channels, hidden_channels, out_channels, num_layers, dropout):
+        super().__init__(dropout, num_layers)
+        self.convs.extend(_stack(SAGEConv, in_channels, hidden_channels, out_channels, num_layers))
+
+
+class GCN(BaseGNN):
+    def __init__(self, in_channels, hidden_channels, out_channels, num_layers, dropout):
+        super().__init__(dropout, num_layers)
+        self.convs.extend(_stack(GCNConv, in_channels, hidden_channels, out_channels, num_layers))
+
+
+class MLPPredictor(torch.nn.Module):
+    """layer.py:66-87: Hadamard of the two endpoint embeddings -> (Linear, relu, dropout) x (L-1)
+    -> Linear(-> out_channels).  ``forward(x_i, x_j)`` -> [B, out_channels]."""
+
+    def __init__(self, in_channels, hidden_channels, out_channels, num_layers, dropout):
+        super().__init__()
+        dims = [in_channels] + [hidden_channels] * (num_layers - 1) + [out_channels]
+        self.lins = torch.nn.ModuleList(_Lin(dims[i], dims[i + 1]) for i in range(num_layers))
+        self.dropout = dropout
+
+    def reset_parameters(self):
+        for lin in self.lins:
+            lin.reset_parameters()
+
+    def _tail(self, x):
+        p = self.dropout if self.training else 0.0
+        for lin in self.lins[:-1]:
+            x = lin(x, act=_ops.ACT_RELU, drop_p=p)
+        last = self.lins[-1]
+        if last.out_features == 1:
+            return _ops.MLPOut.apply(x, last.weight, last.bias)
+        return last(x)
+
+    def forward(self, x_i, x_j):
+        return self._tail(x_i * x_j)
+
+    def score_edges(self, h, edges):
+        """predictor(h[edges[:,0]], h[edges[:,1]]) with the gather and Hadamard fused."""
+        return self._tail(_ops.GatherHadamard.apply(h, edges))
+
+    def flat_params(self):
+        out = []
+        for lin in self.lins:
+            out += [lin.weight, lin.bias]
+        return out
+
+
+class DotPredictor(torch.nn.Module):
+    """layer.py:167-176: sum(x_i * x_j, -1) -> [B]."""
+
+    def reset_parameters(self):
+        return
+
+    def forward(self, x_i, x_j):
+        h = torch.cat([x_i, x_j], 0)
+        n = x_i.size(0)
+        ar = torch.arange(n, device=x_i.device)
+        return _ops.EdgeDot.apply(h, torch.stack([ar, ar + n], 1))
+
+    def score_edges(self, h, edges):
+        return _ops.EdgeDot.apply(h, edges)
+
+    def flat_params(self):
+        return []
+
+
+def _out_of_scope(name, where):
+    class _Stub(torch.nn.Module):
+        def __init__(self, *args, **kwargs):
+            raise NotImplementedError(
+                f"{name} ({where}) is outside the hot-path scope of plnlp_b200 (SURVEY.md section 8f)")
+    _Stub.__name__ = _Stub.__qualname__ = name
+    return _Stub
+
+
+WSAGE = _out_of_scope("WSAGE", "layer.py:48-54")
+Transformer = _out_of_scope("Transformer", "layer.py:57-63")
+MLPCatPredictor = _out_of_scope("MLPCatPredictor", "layer.py:90-116")
+MLPDotPredictor = _out_of_scope("MLPDotPredictor", "layer.py:119-139")
+MLPBilPredictor = _out_of_scope("MLPBilPredictor", "layer.py:142-164")
+BilinearPredictor = _out_of_scope("BilinearPredictor", "layer.py:179-189")

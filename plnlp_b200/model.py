@@ -1,0 +1,259 @@
+"""``BaseModel`` with the reference's constructor / train / test surface
+(/root/reference/plnlp/model.py), re-plumbed on the plnlp_b200 kernels.
+
+What changes underneath (results are the reference's):
+  * negatives are sampled on the GPU, the epoch permutation is drawn on the GPU;
+  * ``[emb | x]`` is never concatenated, the first conv consumes the two blocks;
+  * endpoint gather + Hadamard + predictor + pairwise loss + d loss/d score run as one fused
+    autograd node (``_ops.EdgeScoreLoss``);
+  * the running loss is accumulated on the device: ONE host sync per epoch instead of one per
+    batch (model.py:170);
+  * ``test`` encodes once (the reference recomputes an identical ``h``, model.py:190,204) and
+    ranks on the GPU.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _ops
+from .layer import *  # noqa: F401,F403
+from .layer import GCN, SAGE, DotPredictor, MLPPredictor
+from .loss import *  # noqa: F401,F403
+from .utils import *  # noqa: F401,F403
+from .utils import evaluate_hits, evaluate_mrr, get_pos_neg_edges
+
+_IN_SCOPE_LOSSES = ('AUC', 'HingeAUC', 'WeightedHingeAUC')
+
+
+class BaseModel(object):
+    """Same keyword arguments as model.py:45-48."""
+
+    def __init__(self, lr, dropout, grad_clip_norm, gnn_num_layers, mlp_num_layers, emb_hidden_channels,
+                 gnn_hidden_channels, mlp_hidden_channels, num_nodes, num_node_feats, gnn_encoder_name,
+                 predictor_name, loss_func, optimizer_name, device, use_node_feats, train_node_emb,
+                 pretrain_emb=None):
+        device = torch.device(device)
+        if device.type != 'cuda':
+            raise RuntimeError("plnlp_b200.BaseModel runs on a CUDA (sm_100) device only; there is no CPU path")
+        self.loss_func_name = loss_func
+        self.num_nodes = num_nodes
+        self.num_node_feats = num_node_feats
+        self.use_node_feats = use_node_feats
+        self.train_node_emb = train_node_emb
+        self.clip_norm = grad_clip_norm
+        self.device = device
+
+        self.input_channels, self.emb = create_input_layer(
+            num_nodes=num_nodes, num_node_feats=num_node_feats, hidden_channels=emb_hidden_channels,
+            use_node_feats=use_node_feats, train_node_emb=train_node_emb, pretrain_emb=pretrain_emb)
+        if self.emb is not None:
+            self.emb = self.emb.to(device)
+
+        self.encoder = create_gnn_layer(input_channels=self.input_channels, hidden_channels=gnn_hidden_channels,
+                                        num_layers=gnn_num_layers, dropout=dropout,
+                                        encoder_name=gnn_encoder_name).to(device)
+        self.predictor = create_predictor_layer(hidden_channels=mlp_hidden_channels, num_layers=mlp_num_layers,
+                                                dropout=dropout, predictor_name=predictor_name)
+        if self.predictor is None:
+            raise NotImplementedError(f"predictor {predictor_name!r}")
+        self.predictor = self.predictor.to(device)
+
+        # same parameter order as model.py:81-83: encoder, predictor, embedding
+        self.para_list = list(self.encoder.parameters()) + list(self.predictor.parameters())
+        if self.emb is not None:
+            self.para_list += list(self.emb.parameters())
+
+        trainable = [p for p in self.para_list if p.requires_grad]
+        if optimizer_name == 'AdamW':
+            self.optimizer = torch.optim.AdamW(trainable, lr=lr, fused=True)
+        elif optimizer_name == 'SGD':
+            self.optimizer = torch.optim.SGD(trainable, lr=lr, momentum=0.9, weight_decay=1e-5, nesterov=True)
+        else:
+            self.optimizer = torch.optim.Adam(trainable, lr=lr, fused=True)
+        self.last_epoch_stats = {}
+
+    # ------------------------------------------------------------------
+    def param_init(self):
+        self.encoder.reset_parameters()
+        self.predictor.reset_parameters()
+        if self.emb is not None:
+            torch.nn.init.xavier_uniform_(self.emb.weight)
+
+    def input_parts(self, data):
+        """the blocks of the encoder input, in the column order of model.py:98-105."""
+        if self.use_node_feats:
+            x = data.x
+            if x.device != self.device:
+                x = x.to(self.device)
+            x = x.to(torch.float32)
+            if self.train_node_emb:
+                return (self.emb.weight, x)
+            return (x,)
+        return (self.emb.weight,)
+
+    def create_input_feat(self, data):
+        """model.py:98-105 (materialised; the training loop uses ``input_parts`` instead)."""
+        parts = self.input_parts(data)
+        return parts[0] if len(parts) == 1 else torch.cat(parts, dim=-1)
+
+    def _loss_name(self, has_margin):
+        """model.py:107-126 restricted to the in-scope losses: weighted losses without a margin and
+        unknown names use AUC; out-of-scope names raise instead of silently changing objective."""
+        name = self.loss_func_name
+        if name == 'HingeAUC':
+            return 'HingeAUC'
+        if name == 'WeightedHingeAUC':
+            return 'WeightedHingeAUC' if has_margin else 'AUC'
+        if name in ('CE', 'InfoNCE', 'LogRank') or (name in ('AdaAUC', 'WeightedAUC', 'AdaHingeAUC') and has_margin):
+            raise NotImplementedError(f"loss {name!r} is outside the hot-path scope (SURVEY.md section 8f)")
+        return 'AUC'
+
+    def calculate_loss(self, pos_out, neg_out, num_neg, margin=None):
+        return _ops.pair_loss(self._loss_name(margin is not None), pos_out, neg_out, num_neg, margin)
+
+    # ------------------------------------------------------------------
+    def train_batch(self, data, pos_edge, neg_edge, num_neg, weight_margin=None):
+        """one optimisation step (model.py:148-167).  pos_edge [B,2], neg_edge [B*num_neg,2].
+        Returns the batch loss as a 0-d device tensor (no host sync)."""
+        self.optimizer.zero_grad(set_to_none=True)
+        h = self.encoder(self.input_parts(data), data.adj_t)
+        head = 'DOT' if isinstance(self.predictor, DotPredictor) else 'MLP'
+        p = self.predictor.dropout if (head == 'MLP' and self.predictor.training) else 0.0
+        loss = _ops.edge_score_loss(h, pos_edge, neg_edge, num_neg, self._loss_name(weight_margin is not None),
+                                    weight=weight_margin if self.loss_func_name == 'WeightedHingeAUC' else None,
+                                    head=head, params=self.predictor.flat_params(), drop_p=p,
+                                    seed=_ops.new_seed() if p > 0 else 0)
+        loss.backward()
+        if self.clip_norm >= 0:
+            torch.nn.utils.clip_grad_norm_(self.encoder.parameters(), self.clip_norm)
+            pp = list(self.predictor.parameters())
+            if pp:
+                torch.nn.utils.clip_grad_norm_(pp, self.clip_norm)
+        self.optimizer.step()
+        return loss.detach()
+
+    def train(self, data, split_edge, batch_size, neg_sampler_name, num_neg, perms=None, neg_edges=None,
+              max_batches=None):
+        """model.py:128-173.  Extensions (all optional): ``perms`` (iterable of index tensors) and
+        ``neg_edges`` ([E,num_neg,2]) replace the shuffle / sampler so a run can be replayed;
+        ``max_batches`` stops early (bench time-boxing)."""
+        self.encoder.train()
+        self.predictor.train()
+        if neg_edges is None:
+            pos_train_edge, neg_train_edge = get_pos_neg_edges(
+                'train', split_edge, edge_index=data.edge_index, num_nodes=self.num_nodes,
+                neg_sampler_name=neg_sampler_name, num_neg=num_neg, device=self.device)
+        else:
+            pos_train_edge = self._train_pos(split_edge)
+            neg_train_edge = neg_edges.to(self.device)
+        pos_train_edge = pos_train_edge.to(self.device)
+        margin = split_edge['train']['weight'].to(self.device).to(torch.float32) \
+            if 'weight' in split_edge['train'] else None
+
+        E = pos_train_edge.size(0)
+        if perms is None:
+            order = torch.randperm(E, device=self.device)
+            perms = [order[i:i + batch_size] for i in range(0, E, batch_size)]
+        total_loss = torch.zeros((), dtype=torch.float64, device=self.device)
+        total_examples = 0
+        for it, perm in enumerate(perms):
+            if max_batches is not None and it >= max_batches:
+                break
+            perm = perm.to(self.device)
+            pos_edge = pos_train_edge[perm]
+            neg_edge = neg_train_edge[perm].reshape(-1, 2)
+            w = margin[perm] if margin is not None else None
+            loss = self.train_batch(data, pos_edge, neg_edge, num_neg, w)
+            total_loss += loss.double() * perm.numel()
+            total_examples += perm.numel()
+        self.last_epoch_stats = {'batches': it + 1 if total_examples else 0, 'examples': total_examples}
+        return (total_loss / max(total_examples, 1)).item()   # the one host sync of the epoch
+
+    def _train_pos(self, split_edge):
+        tr = split_edge['train']
+        if 'edge' in tr:
+            return tr['edge']
+        return torch.stack([tr['source_node'], tr['target_node']], dim=1)
+
+    # ------------------------------------------------------------------
+    @torch.no_grad()
+    def batch_predict(self, h, edges, batch_size):
+        """model.py:175-182; scores stay on the device."""
+        edges = edges.to(self.device)
+        preds = [self.predictor.score_edges(h, edges[i:i + batch_size]).reshape(-1)
+                 for i in range(0, edges.size(0), batch_size)]
+        return torch.cat(preds, dim=0) if preds else torch.empty(0, device=self.device)
+
+    @torch.no_grad()
+    def encode_for_test(self, data):
+        """model.py:189-194: eval-mode encoding plus the mean row that index -1 resolves to."""
+        h = self.encoder(self.input_parts(data), data.adj_t)
+        mean_h = _ops.colsum_raw(h, 1.0 / h.size(0)).reshape(1, -1)
+        return torch.cat([h, mean_h], dim=0)
+
+    @torch.no_grad()
+    def test(self, data, split_edge, batch_size, evaluator, eval_metric):
+        """model.py:184-226 -> {'Hits@20'|'Hits@50'|'Hits@100'|'MRR': (valid, test)}"""
+        self.encoder.eval()
+        self.predictor.eval()
+        h = self.encode_for_test(data)
+        pos_valid_edge, neg_valid_edge = get_pos_neg_edges('valid', split_edge, device=self.device)
+        pos_test_edge, neg_test_edge = get_pos_neg_edges('test', split_edge, device=self.device)
+        pos_valid_pred = self.batch_predict(h, pos_valid_edge, batch_size)
+        neg_valid_pred = self.batch_predict(h, neg_valid_edge, batch_size)
+        pos_test_pred = self.batch_predict(h, pos_test_edge, batch_size)
+        neg_test_pred = self.batch_predict(h, neg_test_edge, batch_size)
+        if eval_metric == 'hits':
+            return evaluate_hits(evaluator, pos_valid_pred, neg_valid_pred, pos_test_pred, neg_test_pred)
+        return evaluate_mrr(evaluator, pos_valid_pred, neg_valid_pred, pos_test_pred, neg_test_pred)
+
+
+def create_input_layer(num_nodes, num_node_feats, hidden_channels, use_node_feats=True,
+                       train_node_emb=False, pretrain_emb=None):
+    """model.py:229-249 -> (input width, embedding module or None)."""
+    emb, width = None, 0
+    pretrained = pretrain_emb is not None and pretrain_emb != ''
+    if use_node_feats:
+        width = num_node_feats
+        if train_node_emb:
+            emb = torch.nn.Embedding(num_nodes, hidden_channels)
+        elif pretrained:
+            emb = torch.nn.Embedding.from_pretrained(torch.load(pretrain_emb))
+    else:
+        emb = torch.nn.Embedding.from_pretrained(torch.load(pretrain_emb)) if pretrained \
+            else torch.nn.Embedding(num_nodes, hidden_channels)
+    if emb is not None:
+        width += emb.weight.size(1)
+    return width, emb
+
+
+def create_gnn_layer(input_channels, hidden_channels, num_layers, dropout=0, encoder_name='SAGE'):
+    """model.py:252-260"""
+    name = encoder_name.upper()
+    if name == 'GCN':
+        return GCN(input_channels, hidden_channels, hidden_channels, num_layers, dropout)
+    if name == 'WSAGE':
+        return WSAGE(input_channels, hidden_channels, hidden_channels, num_layers, dropout)  # noqa: F405
+    if name == 'TRANSFORMER':
+        return Transformer(input_channels, hidden_channels, hidden_channels, num_layers, dropout)  # noqa: F405
+    return SAGE(input_channels, hidden_channels, hidden_channels, num_layers, dropout)
+
+
+def create_predictor_layer(hidden_channels, num_layers, dropout=0, predictor_name='MLP'):
+    """model.py:263-276 (unknown names -> None, as in the reference)."""
+    name = predictor_name.upper()
+    if name == 'DOT':
+        return DotPredictor()
+    if name == 'MLP':
+        return MLPPredictor(hidden_channels, hidden_channels, 1, num_layers, dropout)
+    if name in ('BIL', 'MLPDOT', 'MLPBIL', 'MLPCAT'):
+        raise NotImplementedError(f"predictor {predictor_name!r} is outside the hot-path scope (SURVEY.md 8f)")
+    return None
+
+
+def adjust_lr(optimizer, decay_ratio, lr):
+    """model.py:279-286: linear decay floored at 1e-4 * lr."""
+    lr_ = max(lr * (1 - decay_ratio), lr * 0.0001)
+    for group in optimizer.param_groups:
+        group['lr'] = lr_
+    return lr_

@@ -1,0 +1,371 @@
+"""GPU parity tests (-m gpu): every CUDA kernel, called through the C ABI, against the CPU oracle
+on the same seeded inputs.  Bars (BASELINE.json north_star): index / integer work bit-exact;
+fp32 results within 1e-5 relative (max|a-b| / max|b|)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cspmm, ogb_eval, plnlp_ref, sparse
+from tests.helpers import rand_graph, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from plnlp_b200 import _lib, _ops
+    assert _lib.load().plnlp_check_device() == 0
+    return _ops
+
+
+def _to_gpu_graph(o):
+    from plnlp_b200.graph import CSRGraph
+    rowptr, col, val = o.csr()
+    return CSRGraph(rowptr.cuda(), col.cuda(), None if val is None else val.cuda(), o.sparse_sizes())
+
+
+# ------------------------------------------------------------------ SpMM
+@pytest.mark.parametrize("F", [1, 3, 50, 64, 128, 178, 200, 256, 512, 1024])
+@pytest.mark.parametrize("weighted,reduce", [(False, "mean"), (True, "sum"), (True, "mean"), (False, "sum")])
+def test_spmm_forward(ops, F, weighted, reduce):
+    N = 211                                  # not a multiple of 32
+    ei, w = rand_graph(N, 1500, seed=F, weighted=weighted, hub=True)
+    o = sparse.to_sparse_tensor(ei, w, N)
+    g = _to_gpu_graph(o)
+    x = torch.randn(N, F)
+    got = ops.spmm(g, x.cuda(), reduce).cpu()
+    oref = o.set_value(None) if reduce == "mean" else o
+    rowptr, col, val = oref.csr()
+    want = cspmm.spmm(rowptr, col, val, x, reduce)       # in-order fp32 loop
+    assert rel_err(got, want) < TOL
+    empty = (rowptr[1:] - rowptr[:-1]) == 0
+    assert empty.any() and torch.all(got[empty] == 0)
+
+
+def test_spmm_unsplit_rows_are_bit_exact(ops):
+    """rows that fit one work item are accumulated strictly in CSR order: identical bits to the
+    in-order CPU loop, valued and value-less"""
+    from plnlp_b200.graph import Structure
+    N, F = 300, 200
+    ei, w = rand_graph(N, 4000, seed=77, weighted=True)
+    for weights, reduce in ((w, "sum"), (None, "mean"), (None, "sum")):
+        o = sparse.to_sparse_tensor(ei, weights, N)
+        g = _to_gpu_graph(o)
+        st = Structure(g, chunk=1024)
+        assert st.fwd.n_fix == 0
+        x = torch.randn(N, F)
+        got = ops.spmm_raw(st.fwd, x.cuda(), use_val=weights is not None, div_rows=(reduce == "mean")).cpu()
+        rowptr, col, val = o.csr()
+        assert torch.equal(got, cspmm.spmm(rowptr, col, val, x, reduce))
+
+
+@pytest.mark.parametrize("chunk", [32, 64])
+def test_spmm_split_rows(ops, chunk):
+    from plnlp_b200.graph import Structure
+    N, F = 150, 96
+    ei, w = rand_graph(N, 3000, seed=5, weighted=True, hub=True)
+    o = sparse.to_sparse_tensor(ei, w, N)
+    st = Structure(_to_gpu_graph(o), chunk=chunk)
+    assert st.fwd.n_fix > 0
+    x = torch.randn(N, F)
+    got = ops.spmm_raw(st.fwd, x.cuda(), use_val=True, div_rows=False).cpu()
+    rowptr, col, val = o.csr()
+    assert rel_err(got, cspmm.spmm(rowptr, col, val, x, "sum", f64=True)) < TOL
+    got2 = ops.spmm_raw(st.fwd, x.cuda(), use_val=True, div_rows=False).cpu()
+    assert torch.equal(got, got2)            # deterministic
+
+
+@pytest.mark.parametrize("weighted,reduce", [(False, "mean"), (True, "sum")])
+def test_spmm_backward_nonsymmetric(ops, weighted, reduce):
+    N, F = 97, 40
+    ei, w = rand_graph(N, 700, seed=3, weighted=weighted, hub=True)   # directed: A^T != A
+    o = sparse.to_sparse_tensor(ei, w, N)
+    g = _to_gpu_graph(o)
+    x = torch.randn(N, F)
+    gout = torch.randn(N, F)
+    xg = x.cuda().requires_grad_(True)
+    ops.spmm(g, xg, reduce).backward(gout.cuda())
+    xc = x.clone().requires_grad_(True)
+    sparse.matmul(o.set_value(None) if reduce == "mean" else o, xc, reduce).backward(gout)
+    assert rel_err(xg.grad.cpu(), xc.grad) < TOL
+
+
+def test_spmm_fused_epilogue_and_grad(ops):
+    """GCN epilogue: relu(A z + bias), backward through the mask, bias gradient"""
+    N, F = 120, 64
+    ei, _ = rand_graph(N, 900, seed=4)
+    o = sparse.gcn_normalization(sparse.to_sparse_tensor(ei, None, N).to_symmetric())
+    g = _to_gpu_graph(o)
+    z, b, gout = torch.randn(N, F), torch.randn(F), torch.randn(N, F)
+    zg, bg = z.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    out = ops.spmm(g, zg, "sum", bias=bg, relu=True)
+    out.backward(gout.cuda())
+    zc, bc = z.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.relu(sparse.matmul(o, zc, "sum") + bc)
+    ref.backward(gout)
+    assert rel_err(out.cpu(), ref) < TOL
+    assert rel_err(zg.grad.cpu(), zc.grad) < TOL and rel_err(bg.grad.cpu(), bc.grad) < TOL
+
+
+def test_dropout_statistics_and_backward(ops):
+    N, F, p = 400, 128, 0.3
+    ei, _ = rand_graph(N, 6000, seed=6)
+    g = _to_gpu_graph(sparse.to_sparse_tensor(ei, None, N))
+    x = (torch.rand(N, F) + 0.5).cuda().requires_grad_(True)
+    out = ops.spmm(g, x, "sum", relu=True, drop_p=p, seed=1234)
+    base = ops.spmm(g, x.detach(), "sum", relu=True)
+    nz = base > 0
+    kept = (out != 0) & nz
+    frac = kept.sum().item() / nz.sum().item()
+    assert abs(frac - (1 - p)) < 0.02
+    assert rel_err(out[kept], base[kept] / (1 - p)) < 1e-6
+    out2 = ops.spmm(g, x.detach(), "sum", relu=True, drop_p=p, seed=1234)
+    assert torch.equal(out.detach(), out2)                      # same seed, same mask
+    out.sum().backward()
+    # gradient flows only through kept entries, scaled by 1/(1-p): d/dx = A^T (mask/(1-p))
+    gref = ops.spmm_raw(ops.structure_of(g).bwd, (kept.float() / (1 - p)), use_val=False, div_rows=False)
+    assert rel_err(x.grad, gref) < TOL
+
+
+# ------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (37, 19, 23), (128, 128, 16), (4267, 512, 512), (300, 200, 178),
+                                   (129, 257, 50), (512, 512, 4100)])
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])
+def test_gemm_layouts(ops, M, N, K, ta, tb):
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn((K, M) if ta else (M, K), generator=g)
+    B = torch.randn((N, K) if tb else (K, N), generator=g)
+    got = ops.gemm_raw(A.cuda(), B.cuda(), transa=ta, transb=tb).cpu()
+    want = ((A.t() if ta else A).double() @ (B.t() if tb else B).double())
+    assert rel_err(got, want) < TOL
+
+
+def test_gemm_splitk_deterministic_and_beta_bias(ops):
+    g = torch.Generator().manual_seed(1)
+    A, B = torch.randn(20000, 96, generator=g), torch.randn(20000, 130, generator=g)
+    C0, bias = torch.randn(96, 130, generator=g), torch.randn(130, generator=g)
+    outs = []
+    for _ in range(2):
+        C = C0.clone().cuda()
+        ops.gemm_raw(A.cuda(), B.cuda(), transa=True, C=C, beta=1.0, bias=bias.cuda(), split_k=7)
+        outs.append(C.cpu())
+    assert torch.equal(outs[0], outs[1])
+    want = A.double().t() @ B.double() + C0.double() + bias.double()
+    assert rel_err(outs[0], want) < TOL
+
+
+def test_gemm_views_with_leading_dimension(ops):
+    """column slices of a wider weight (concat-free [emb | x] @ W^T) and misaligned bases"""
+    g = torch.Generator().manual_seed(2)
+    W = torch.randn(200, 178, generator=g)
+    e, x = torch.randn(333, 50, generator=g), torch.randn(333, 128, generator=g)
+    Wg = W.cuda()
+    y = ops.gemm_raw(e.cuda(), Wg[:, :50], transb=True)
+    y = ops.gemm_raw(x.cuda(), Wg[:, 50:], transb=True, C=y, beta=1.0)
+    want = torch.cat([e, x], 1).double() @ W.double().t()
+    assert rel_err(y.cpu(), want) < TOL
+
+
+def test_fused_linear_autograd(ops):
+    g = torch.Generator().manual_seed(3)
+    a, x = torch.randn(90, 24, generator=g), torch.randn(90, 24, generator=g)
+    wl, wr, b = torch.randn(40, 24, generator=g), torch.randn(40, 24, generator=g), torch.randn(40, generator=g)
+    gout = torch.randn(90, 40, generator=g)
+    cu = [t.cuda().requires_grad_(True) for t in (a, x, wl, wr, b)]
+    y = ops.fused_linear([cu[0], cu[1]], [cu[2], cu[3]], cu[4], act=ops.ACT_RELU)
+    y.backward(gout.cuda())
+    cp = [t.clone().requires_grad_(True) for t in (a, x, wl, wr, b)]
+    yr = torch.relu(cp[0] @ cp[2].t() + cp[4] + cp[1] @ cp[3].t())
+    yr.backward(gout)
+    assert rel_err(y.cpu(), yr) < TOL
+    for u, v in zip(cu, cp):
+        assert rel_err(u.grad.cpu(), v.grad) < TOL
+
+
+# ------------------------------------------------------------------ edge scoring
+@pytest.mark.parametrize("H", [1, 12, 50, 200, 256, 512])
+def test_gather_hadamard_and_dot(ops, H):
+    g = torch.Generator().manual_seed(H)
+    N, P = 77, 501
+    h = torch.randn(N, H, generator=g)
+    edges = torch.randint(0, N, (P, 2), generator=g)
+    edges[5] = torch.tensor([-1, 3])                      # python-style negative index (model.py:191-194)
+    edges[6] = torch.tensor([9, 9])                       # self pair
+    want = h[edges[:, 0]] * h[edges[:, 1]]
+    assert torch.equal(ops.gather_hadamard_raw(h.cuda(), edges.cuda()).cpu(), want)
+    assert rel_err(ops.edge_dot_raw(h.cuda(), edges.cuda()).cpu(), want.double().sum(-1)) < TOL
+
+
+@pytest.mark.parametrize("mode", ["sorted", "atomic"])
+@pytest.mark.parametrize("head", ["mlp", "dot"])
+def test_edge_scatter(ops, mode, head):
+    g = torch.Generator().manual_seed(11)
+    N, P, H = 60, 700, 36
+    h = torch.randn(N, H, generator=g)
+    edges = torch.randint(0, N, (P, 2), generator=g)
+    edges[:40, 0] = 7                                       # a hot node
+    edges[3] = torch.tensor([5, 5])
+    hc = h.clone().requires_grad_(True)
+    if head == "mlp":
+        da = torch.randn(P, H, generator=g)
+        (hc[edges[:, 0]] * hc[edges[:, 1]] * da).sum().backward()
+        got = ops.edge_scatter_raw(h.cuda(), edges.cuda(), da=da.cuda(), mode=mode).cpu()
+    else:
+        ds = torch.randn(P, generator=g)
+        ((hc[edges[:, 0]] * hc[edges[:, 1]]).sum(-1) * ds).sum().backward()
+        got = ops.edge_scatter_raw(h.cuda(), edges.cuda(), dscore=ds.cuda(), mode=mode).cpu()
+    assert rel_err(got, hc.grad) < TOL
+    if mode == "sorted":
+        again = ops.edge_scatter_raw(h.cuda(), edges.cuda(), da=da.cuda() if head == "mlp" else None,
+                                     dscore=None if head == "mlp" else ds.cuda(), mode=mode).cpu()
+        assert torch.equal(got, again)
+
+
+def test_mlp_out_layer(ops):
+    g = torch.Generator().manual_seed(12)
+    P, H = 1000, 200
+    a = torch.relu(torch.randn(P, H, generator=g))
+    w, b, ds = torch.randn(1, H, generator=g), torch.randn(1, generator=g), torch.randn(P, generator=g)
+    s = ops.mlp_out_fwd_raw(a.cuda(), w.cuda(), b.cuda()).cpu()
+    assert rel_err(s, (a.double() @ w.double().t()).reshape(-1) + b.double()) < TOL
+    dz, dw, db = ops.mlp_out_bwd_raw(a.cuda(), w.cuda(), ds.cuda(), mask_a=True, drop_scale=1.0)
+    assert rel_err(dz.cpu(), ds[:, None] * w * (a > 0)) < TOL
+    assert rel_err(dw.cpu(), (ds.double()[:, None] * a.double()).sum(0)) < TOL
+    assert rel_err(db.cpu(), ds.double().sum().reshape(1)) < TOL
+
+
+@pytest.mark.parametrize("name", ["AUC", "HingeAUC", "WeightedHingeAUC"])
+@pytest.mark.parametrize("k", [1, 3])
+def test_pair_loss(ops, name, k):
+    g = torch.Generator().manual_seed(13)
+    B = 5000
+    pos, neg, w = torch.randn(B, generator=g), torch.randn(B * k, generator=g), torch.rand(B, generator=g) + 0.1
+    p, n = pos.cuda().requires_grad_(True), neg.cuda().requires_grad_(True)
+    loss = ops.pair_loss(name, p, n, k, w.cuda() if name == "WeightedHingeAUC" else None)
+    (loss * 0.5).backward()
+    want = plnlp_ref.pair_loss(name, pos.double(), neg.double(), k, w.double())
+    gp, gn = plnlp_ref.pair_loss_grad(name, pos, neg, k, w)
+    assert rel_err(loss.cpu(), want) < TOL
+    assert rel_err(p.grad.cpu(), 0.5 * gp) < TOL and rel_err(n.grad.cpu(), 0.5 * gn.reshape(-1)) < TOL
+
+
+def test_losses_against_reference_golden(ops, golden_dir):
+    import os
+    from plnlp_b200 import loss as L
+    G = torch.load(os.path.join(golden_dir, "losses.pt"))
+    for key, rec in G.items():
+        k = int(key[-1])
+        for name, fn in (("AUC", L.auc_loss), ("HingeAUC", L.hinge_auc_loss),
+                         ("WeightedHingeAUC", L.weighted_hinge_auc_loss)):
+            p, n = rec["pos"].cuda().requires_grad_(True), rec["neg"].cuda().requires_grad_(True)
+            args = (p, n, k, rec["weight"].cuda()) if name == "WeightedHingeAUC" else (p, n, k)
+            loss = fn(*args)
+            loss.backward()
+            assert loss.dim() == 0
+            assert rel_err(loss.cpu(), rec[name]["loss"]) < TOL
+            assert rel_err(p.grad.cpu(), rec[name]["gpos"]) < TOL
+            assert rel_err(n.grad.cpu(), rec[name]["gneg"]) < TOL
+
+
+def test_relu_bwd_and_colsum(ops):
+    g = torch.Generator().manual_seed(14)
+    y, dy = torch.randn(1234, 178, generator=g), torch.randn(1234, 178, generator=g)
+    assert torch.equal(ops.relu_drop_bwd_raw(y.cuda(), dy.cuda(), 2.0).cpu(), torch.where(y > 0, dy * 2.0, 0.0))
+    assert rel_err(ops.colsum_raw(y.cuda(), 0.5).cpu(), 0.5 * y.double().sum(0)) < TOL
+
+
+# ------------------------------------------------------------------ samplers
+def test_local_neg_sample(ops):
+    from plnlp_b200.negative_sample import local_neg_sample
+    torch.manual_seed(0)
+    N, E, k = 1000, 4001, 3
+    pos = torch.randint(0, N, (E, 2))
+    out = local_neg_sample(pos.cuda(), N, k)
+    assert out.shape == (E, k, 2) and out.dtype == torch.int64
+    out = out.cpu()
+    assert torch.equal(out[:, :, 0], pos[:, :1].expand(E, k))      # sources kept: bit-exact
+    dst = out[:, :, 1].reshape(-1)
+    assert dst.min() >= 0 and dst.max() < N
+    counts = torch.bincount(dst, minlength=N).double()
+    chi2 = ((counts - counts.mean()) ** 2 / counts.mean()).sum().item()
+    assert chi2 < N + 6 * (2 * N) ** 0.5                            # uniform within 6 sigma
+    torch.manual_seed(0)
+    pos2 = torch.randint(0, N, (E, 2))
+    assert torch.equal(local_neg_sample(pos2.cuda(), N, k).cpu(), out)   # reproducible under manual_seed
+
+
+def test_global_neg_sample(ops):
+    from plnlp_b200.negative_sample import global_neg_sample
+    torch.manual_seed(1)
+    N = 300
+    ei, _ = rand_graph(N, 9000, seed=15)
+    E, k = 5000, 3
+    out = global_neg_sample(ei.cuda(), N, E, k).cpu()
+    assert out.shape == (E, k, 2) and out.dtype == torch.int64
+    src, dst = out[..., 0].reshape(-1), out[..., 1].reshape(-1)
+    assert (src != dst).all()                                       # self loops excluded (negative_sample.py:8)
+    ids = src * N + dst
+    assert not np.isin(ids.numpy(), (ei[0] * N + ei[1]).numpy()).any()   # never an existing edge
+    assert ids.unique().numel() == ids.numel()                      # distinct
+    # roughly uniform over rows
+    counts = torch.bincount(src, minlength=N).double()
+    assert counts.min() > 0.3 * counts.mean() and counts.max() < 2.0 * counts.mean()
+
+
+def test_global_neg_sample_pads_when_short(ops):
+    from plnlp_b200.negative_sample import global_neg_sample
+    torch.manual_seed(2)
+    N = 12
+    ei, _ = rand_graph(N, 60, seed=16)
+    out = global_neg_sample(ei.cuda(), N, 100, 2).cpu()              # asks for more than exist
+    assert out.shape == (100, 2, 2)
+    ids = (out[..., 0] * N + out[..., 1]).reshape(-1)
+    assert not np.isin(ids.numpy(), (ei[0] * N + ei[1]).numpy()).any()
+    assert (out[..., 0] != out[..., 1]).all()
+
+
+# ------------------------------------------------------------------ ranking
+@pytest.mark.parametrize("n,K", [(1, 1), (50, 20), (1000, 100), (101882, 20), (101882, 50), (300000, 100)])
+def test_kth_largest_and_hits(ops, n, K):
+    from plnlp_b200.utils import hits_at_k
+    g = torch.Generator().manual_seed(n + K)
+    neg = torch.randn(n, generator=g)
+    neg[: n // 3] = neg[: n // 3].round(decimals=1)               # plenty of exact ties
+    if n > 10:
+        neg[3], neg[4] = 0.0, -0.0
+    pos = torch.randn(5000, generator=g).round(decimals=1)
+    kth = ops.kth_largest_raw(neg.cuda(), K).cpu()
+    assert torch.equal(kth, torch.topk(neg, K)[0][-1:])             # bit-exact
+    assert hits_at_k(pos.cuda(), neg.cuda(), K) == ogb_eval.hits_at_k(pos, neg, K)
+
+
+def test_hits_fewer_negatives_than_k(ops):
+    from plnlp_b200.utils import hits_at_k
+    assert hits_at_k(torch.randn(10).cuda(), torch.randn(5).cuda(), 20) == 1.0
+
+
+def test_mrr_counts(ops):
+    from plnlp_b200.utils import mrr_list
+    g = torch.Generator().manual_seed(17)
+    S, K = 997, 1000
+    pos, neg = torch.randn(S, generator=g), torch.randn(S, K, generator=g)
+    neg[:, 5] = pos                                              # an exact tie in every row
+    gt, ge = ops.mrr_counts_raw(pos.cuda(), neg.cuda())
+    ogt, oge = ogb_eval.mrr_ranks(pos, neg)
+    assert torch.equal(gt.cpu().long() + 1, ogt) and torch.equal(ge.cpu().long() + 1, oge)
+    assert torch.equal(mrr_list(pos.cuda(), neg.cuda()).cpu(), 1.0 / ogt.float())
+
+
+def test_eval_glue_against_reference_golden(ops, golden_dir):
+    import os
+    from plnlp_b200.utils import evaluate_hits, evaluate_mrr, get_pos_neg_edges
+    G = torch.load(os.path.join(golden_dir, "edges_eval.pt"))
+    h = G["hits"]
+    assert evaluate_hits(None, h["pv"], h["nv"], h["pt"], h["nt"]) == h["res"]
+    m = G["mrr"]
+    got = evaluate_mrr(None, m["pv"], m["nv"], m["pt"], m["nt"])["MRR"]
+    assert abs(got[0] - m["res"]["MRR"][0]) < 1e-6 and abs(got[1] - m["res"]["MRR"][1]) < 1e-6
+    c = G["citation_style"]
+    pos, neg = get_pos_neg_edges("valid", c["split"], device=torch.device("cuda"))
+    assert torch.equal(pos.cpu(), c["pos"]) and torch.equal(neg.cpu(), c["neg"])

@@ -1,0 +1,236 @@
+"""GPU parity tests (-m gpu) at module / trainer level.
+
+The golden fixtures under tests/golden/ hold outputs of the REAL reference package
+(tests/golden/make_golden.py): module forwards, and whole ``BaseModel.train`` epochs with the
+shuffles and negatives it used.  Here the same parameters, shuffles and negatives are replayed
+through plnlp_b200 on the GPU.  fp32 bar: 1e-5 relative per tensor for single ops / one step;
+multi-step trajectories (2 epochs of Adam) are checked at 2e-4 because Adam's 1/sqrt(v) amplifies
+rounding differences of near-zero gradients.
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import plnlp_ref, sparse
+from tests.helpers import rand_graph, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = torch.device("cuda")
+
+
+class Data:
+    pass
+
+
+def _gpu_graph(rowptr, col, val, n):
+    from plnlp_b200.graph import CSRGraph
+    return CSRGraph(rowptr.cuda(), col.cuda(), None if val is None else val.cuda(), (n, n))
+
+
+def _load_module(module, state):
+    module.load_state_dict({k: v.cuda() for k, v in state.items()})
+
+
+def test_predictors_against_reference_golden(golden_dir):
+    from plnlp_b200.layer import DotPredictor, MLPPredictor
+    G = torch.load(os.path.join(golden_dir, "predictors.pt"))
+    for key, rec in G.items():
+        if key == "dot":
+            out = DotPredictor()(rec["xi"].cuda(), rec["xj"].cuda())
+            assert out.shape == rec["out"].shape and rel_err(out.cpu(), rec["out"]) < TOL
+            continue
+        H, L = int(key.split("_")[1][1:]), int(key.split("_L")[1])
+        m = MLPPredictor(H, H, 1, L, 0.0).cuda()
+        _load_module(m, rec["state"])
+        m.eval()
+        out = m(rec["xi"].cuda(), rec["xj"].cuda())
+        assert out.shape == rec["out"].shape               # [B, 1]
+        assert rel_err(out.cpu(), rec["out"]) < TOL
+
+
+def test_encoders_against_reference_golden(golden_dir):
+    from plnlp_b200.graph import CSRGraph
+    from plnlp_b200.layer import GCN, SAGE
+    from plnlp_b200.utils import gcn_normalization
+    G = torch.load(os.path.join(golden_dir, "encoders.pt"))
+    gr = G["graph"]
+    N = gr["num_nodes"]
+    adj = CSRGraph.from_edge_index(gr["edge_index"].cuda(), gr["edge_weight"].cuda(), N)
+    adj_gcn = gcn_normalization(CSRGraph.from_edge_index(gr["edge_index"].cuda(), None, N))
+    # index work of graph preparation: bit-exact with what the reference pipeline produced
+    assert torch.equal(adj_gcn.csr()[0].cpu(), gr["gcn_rowptr"]) and torch.equal(adj_gcn.csr()[1].cpu(), gr["gcn_col"])
+    assert rel_err(adj_gcn.csr()[2].cpu(), gr["gcn_val"]) < 1e-6
+    for key, rec in G.items():
+        if key == "graph":
+            continue
+        kind, L = key.split("_L")
+        cls = SAGE if kind == "SAGE" else GCN
+        m = cls(rec["x"].size(1), 12, 12, int(L), 0.0).cuda()
+        _load_module(m, rec["state"])
+        m.eval()
+        out = m(rec["x"].cuda(), adj if kind == "SAGE" else adj_gcn)
+        assert rel_err(out.cpu(), rec["out"]) < TOL, key
+        # the concat-free tuple input gives the same result
+        out2 = m((rec["x"][:, :5].contiguous().cuda(), rec["x"][:, 5:].contiguous().cuda()),
+                 adj if kind == "SAGE" else adj_gcn)
+        assert rel_err(out2.cpu(), rec["out"]) < TOL, key
+
+
+def _build_model(cfg):
+    from plnlp_b200.model import BaseModel
+    return BaseModel(lr=cfg["lr"], dropout=0.0, grad_clip_norm=cfg["clip"], gnn_num_layers=cfg["gnn_layers"],
+                     mlp_num_layers=cfg["mlp_layers"], emb_hidden_channels=cfg["emb"],
+                     gnn_hidden_channels=cfg["hid"], mlp_hidden_channels=cfg["hid"], num_nodes=cfg["num_nodes"],
+                     num_node_feats=cfg["feats"], gnn_encoder_name=cfg["encoder"], predictor_name=cfg["predictor"],
+                     loss_func=cfg["loss"], optimizer_name="Adam", device=DEV, use_node_feats=cfg["use_feats"],
+                     train_node_emb=True)
+
+
+def _setup_run(R):
+    cfg = R["cfg"]
+    model = _build_model(cfg)
+    _load_module(model.encoder, R["init"]["encoder"])
+    _load_module(model.predictor, R["init"]["predictor"])
+    with torch.no_grad():
+        model.emb.weight.copy_(R["init"]["emb"].cuda())
+    data = Data()
+    data.adj_t = _gpu_graph(R["adj_rowptr"], R["adj_col"], R["adj_val"], cfg["num_nodes"])
+    data.edge_index = R["edge_index"].cuda()
+    data.x = None if R["x"] is None else R["x"].cuda()
+    return cfg, model, data
+
+
+@pytest.mark.parametrize("tag", ["ddi_like", "collab_like", "citation_like", "hinge_like"])
+@pytest.mark.parametrize("scatter", ["sorted", "atomic"])
+def test_first_step_gradients_match_reference(golden_dir, tag, scatter):
+    """one step from the reference's initial state with its first shuffle + negatives: loss and every
+    parameter gradient against the oracle (itself pinned to the reference by tests/test_oracle.py)"""
+    from plnlp_b200 import _ops
+    R = torch.load(os.path.join(golden_dir, "train_runs.pt"))[tag]
+    cfg, model, data = _setup_run(R)
+    _ops.SCATTER_MODE = scatter
+    try:
+        pos = plnlp_ref.train_pos_edges(R["split"])
+        perm, neg = R["perms"][0][0], R["negs"][0]
+        w = R["split"]["train"].get("weight")
+        model.encoder.train(); model.predictor.train()
+        model.clip_norm = -1.0                                    # look at raw gradients
+        loss = model.train_batch(data, pos[perm].cuda(), neg[perm].reshape(-1, 2).cuda(), cfg["num_neg"],
+                                 None if w is None else w[perm].cuda())
+    finally:
+        _ops.SCATTER_MODE = "sorted"
+    ref = plnlp_ref.OracleModel(num_nodes=cfg["num_nodes"], emb_hidden=cfg["emb"], gnn_hidden=cfg["hid"],
+                                mlp_hidden=cfg["hid"], gnn_layers=cfg["gnn_layers"], mlp_layers=cfg["mlp_layers"],
+                                encoder=cfg["encoder"], predictor=cfg["predictor"], loss=cfg["loss"], lr=cfg["lr"],
+                                clip_norm=-1.0, num_node_feats=cfg["feats"], use_node_feats=cfg["use_feats"])
+    st = {"enc." + k[len("convs."):]: v for k, v in R["init"]["encoder"].items()}
+    st.update({"pred." + k[len("lins."):]: v for k, v in R["init"]["predictor"].items()})
+    st["emb"] = R["init"]["emb"]
+    ref.load(st)
+    adj = sparse.SparseTensor(rowptr=R["adj_rowptr"], col=R["adj_col"], value=R["adj_val"],
+                              sparse_sizes=(cfg["num_nodes"],) * 2, is_sorted=True)
+    rloss, _ = ref.step(R["x"], adj, pos[perm], neg[perm], cfg["num_neg"], None if w is None else w[perm],
+                        do_update=False)
+    assert rel_err(loss.cpu(), rloss) < TOL
+    assert rel_err(model.emb.weight.grad.cpu(), ref.params["emb"].grad) < TOL
+    for name, p in model.encoder.named_parameters():
+        assert rel_err(p.grad.cpu(), ref.params["enc." + name[len("convs."):]].grad) < TOL, name
+    for name, p in model.predictor.named_parameters():
+        assert rel_err(p.grad.cpu(), ref.params["pred." + name[len("lins."):]].grad) < TOL, name
+
+
+@pytest.mark.parametrize("tag", ["ddi_like", "collab_like", "citation_like", "hinge_like"])
+def test_train_epochs_replay_reference(golden_dir, tag):
+    """BaseModel.train for the reference's 2 epochs (its shuffles, its negatives): reported loss,
+    final parameters, validation scores and metrics"""
+    R = torch.load(os.path.join(golden_dir, "train_runs.pt"))[tag]
+    cfg, model, data = _setup_run(R)
+    for ep in range(len(R["losses"])):
+        loss = model.train(data, R["split"], batch_size=cfg["batch_size"], neg_sampler_name=cfg["sampler"],
+                           num_neg=cfg["num_neg"], perms=R["perms"][ep], neg_edges=R["negs"][ep])
+        assert abs(loss - R["losses"][ep]) <= 2e-4 * abs(R["losses"][ep]), (ep, loss, R["losses"][ep])
+    for name, p in model.encoder.named_parameters():
+        assert rel_err(p.detach().cpu(), R["final"]["encoder"][name]) < 2e-4, name
+    for name, p in model.predictor.named_parameters():
+        assert rel_err(p.detach().cpu(), R["final"]["predictor"][name]) < 2e-4, name
+    assert rel_err(model.emb.weight.detach().cpu(), R["final"]["emb"]) < 2e-4
+    # scoring path (model.py:175-194)
+    model.encoder.eval(); model.predictor.eval()
+    h = model.encode_for_test(data)
+    assert rel_err(h.cpu(), R["scores"]["h"]) < 2e-4
+    from plnlp_b200.utils import get_pos_neg_edges
+    pv, nv = get_pos_neg_edges("valid", R["split"], device=DEV)
+    assert rel_err(model.batch_predict(h, pv, cfg["batch_size"]).cpu(), R["scores"]["pos_valid"]) < 2e-4
+    assert rel_err(model.batch_predict(h, nv, cfg["batch_size"]).cpu(), R["scores"]["neg_valid"]) < 2e-4
+    res = model.test(data, R["split"], batch_size=cfg["batch_size"], evaluator=None, eval_metric=cfg["metric"])
+    assert set(res) == set(R["test"])
+    for k in res:                     # ranks can move by one when scores differ in the last bits
+        for a, b in zip(res[k], R["test"][k]):
+            assert abs(a - b) <= 0.03, (k, res[k], R["test"][k])
+
+
+def test_train_end_to_end_with_gpu_samplers():
+    """the public call a user makes: BaseModel.train with the GPU samplers and shuffle; loss must
+    decrease over a few epochs; dropout > 0 exercised"""
+    from plnlp_b200.graph import CSRGraph
+    from plnlp_b200.model import BaseModel
+    torch.manual_seed(0)
+    N = 500
+    ei, _ = rand_graph(N, 4000, seed=21)
+    ei = ei[:, ei[0] != ei[1]]
+    und = torch.cat([ei, ei.flip(0)], 1)
+    data = Data()
+    data.adj_t = CSRGraph.from_edge_index(und.cuda(), None, N)
+    row, col, _ = data.adj_t.coo()
+    data.edge_index = torch.stack([col, row], 0)
+    data.x = None
+    split = {"train": {"edge": ei.t().contiguous()},
+             "valid": {"edge": torch.randint(0, N, (200, 2)), "edge_neg": torch.randint(0, N, (300, 2))},
+             "test": {"edge": torch.randint(0, N, (200, 2)), "edge_neg": torch.randint(0, N, (300, 2))}}
+    for sampler, pred, loss in (("global", "MLP", "AUC"), ("local", "DOT", "HingeAUC")):
+        m = BaseModel(lr=0.005, dropout=0.3, grad_clip_norm=2.0, gnn_num_layers=2, mlp_num_layers=2,
+                      emb_hidden_channels=64, gnn_hidden_channels=64, mlp_hidden_channels=64, num_nodes=N,
+                      num_node_feats=0, gnn_encoder_name="SAGE", predictor_name=pred, loss_func=loss,
+                      optimizer_name="Adam", device=DEV, use_node_feats=False, train_node_emb=True)
+        m.param_init()
+        losses = [m.train(data, split, batch_size=1024, neg_sampler_name=sampler, num_neg=3) for _ in range(6)]
+        assert all(l == l for l in losses) and losses[-1] < losses[0], losses
+        res = m.test(data, split, batch_size=1024, evaluator=None, eval_metric="hits")
+        assert set(res) == {"Hits@20", "Hits@50", "Hits@100"}
+        assert all(0.0 <= v <= 1.0 for pair in res.values() for v in pair)
+
+
+def test_full_size_ddi_shape_properties():
+    """BASELINE config 2 shape (N=4267, nnz~2.1M, F=512): size-independent properties instead of a
+    slow CPU comparison -- linearity of the SpMM, adjointness <A x, y> = <x, A^T y> of forward vs
+    backward kernels, mean-aggregation of a constant is the constant, determinism."""
+    from plnlp_b200 import _ops
+    from plnlp_b200.graph import CSRGraph
+    g = torch.Generator().manual_seed(5)
+    N, E, F = 4267, 1067911, 512
+    lo = torch.randint(0, N, (int(E * 1.3),), generator=g)
+    hi = torch.randint(0, N, (int(E * 1.3),), generator=g)
+    key = torch.unique(torch.minimum(lo, hi) * N + torch.maximum(lo, hi))
+    key = key[(key // N) != (key % N)][:E]
+    ei = torch.stack([key // N, key % N])
+    adj = CSRGraph.from_edge_index(torch.cat([ei, ei.flip(0)], 1).cuda(), None, N)
+    x, y = torch.randn(N, F, generator=g).cuda(), torch.randn(N, F, generator=g).cuda()
+    ax, ay = _ops.spmm(adj, x, "mean"), _ops.spmm(adj, y, "mean")
+    assert rel_err(_ops.spmm(adj, 2.0 * x - 3.0 * y, "mean"), 2.0 * ax - 3.0 * ay) < TOL
+    assert torch.equal(ax, _ops.spmm(adj, x, "mean"))
+    ones = torch.ones(N, F, device=DEV)
+    deg = adj.sum(dim=1)
+    assert rel_err(_ops.spmm(adj, ones, "mean")[deg > 0], ones[deg > 0]) < 1e-6
+    xr = x.clone().requires_grad_(True)
+    _ops.spmm(adj, xr, "mean").backward(y)
+    lhs = (ax.double() * y.double()).sum()
+    rhs = (x.double() * xr.grad.double()).sum()
+    assert abs(lhs - rhs) / abs(lhs) < 1e-6
+    # one sampled row against the in-order definition
+    rowptr, col, _ = adj.csr()
+    r = 1234
+    nb = col[rowptr[r]:rowptr[r + 1]]
+    want = x[nb].double().sum(0) / max(nb.numel(), 1)
+    assert rel_err(ax[r], want) < TOL

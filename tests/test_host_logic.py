@@ -1,0 +1,141 @@
+"""CPU tests (-m "not gpu") of the host-side logic of plnlp_b200: the CSRGraph adjacency holder
+against the oracle's torch_sparse restatement, the SpMM work plan (emulated in python), and the
+small pure-host pieces (adjust_lr, Logger, loss-name dispatch)."""
+import io
+
+import pytest
+import torch
+
+from oracle import sparse
+from plnlp_b200.graph import CSRGraph, build_plan
+from tests.helpers import rand_graph, rel_err
+
+
+def _same(a: CSRGraph, b: sparse.SparseTensor):
+    ra, ca, va = a.csr()
+    rb, cb, vb = b.csr()
+    assert torch.equal(ra, rb) and torch.equal(ca, cb)        # index work: bit-exact
+    assert (va is None) == (vb is None)
+    if va is not None:
+        assert torch.equal(va, vb)
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_csrgraph_matches_oracle_sparse(weighted):
+    N = 41
+    ei, w = rand_graph(N, 220, seed=8, weighted=weighted, hub=True)
+    g, o = CSRGraph.from_edge_index(ei, w, N), sparse.to_sparse_tensor(ei, w, N)
+    _same(g, o)
+    _same(g.to_symmetric(), o.to_symmetric())
+    _same(g.set_diag(), o.set_diag())
+    _same(g.t(), o.t())
+    assert torch.equal(g.sum(dim=1), o.sum(dim=1))
+    r1, c1, _ = g.coo()
+    r2, c2, _ = o.coo()
+    assert torch.equal(r1, r2) and torch.equal(c1, c2)
+
+
+def test_gcn_normalization_matches_oracle():
+    from plnlp_b200.utils import gcn_normalization
+    N = 37
+    ei, _ = rand_graph(N, 150, seed=9)
+    a = gcn_normalization(CSRGraph.from_edge_index(ei, None, N).to_symmetric())
+    b = sparse.gcn_normalization(sparse.to_sparse_tensor(ei, None, N).to_symmetric())
+    _same(a, b)
+
+
+def _emulate(plan, x, use_val, div):
+    """python emulation of csrc/spmm.cu driven by the plan arrays"""
+    F = x.size(1)
+    out = torch.full((plan.n_rows, F), float("nan"))
+    partial = torch.zeros(max(plan.n_partial, 1), F)
+    for i in range(plan.n_items):
+        b, e = int(plan.item_ptr[i]), int(plan.item_ptr[i + 1])
+        acc = torch.zeros(F)
+        for p in range(b, e):
+            v = plan.val[p] if (use_val and plan.val is not None) else 1.0
+            acc = acc + v * x[int(plan.col[p])]
+        s = int(plan.item_slot[i])
+        if s >= 0:
+            partial[s] = acc
+        else:
+            out[int(plan.item_row[i])] = acc
+    for j in range(plan.n_fix):
+        acc = torch.zeros(F)
+        for s in range(int(plan.fix_ptr[j]), int(plan.fix_ptr[j + 1])):
+            acc = acc + partial[s]
+        out[int(plan.fix_row[j])] = acc
+    if div:
+        out = out / plan.row_cnt[:, None]
+    return out
+
+
+@pytest.mark.parametrize("chunk", [4, 32, None])
+def test_spmm_plan_covers_every_row_once(chunk):
+    N = 53
+    ei, w = rand_graph(N, 300, seed=10, weighted=True, hub=True)
+    o = sparse.to_sparse_tensor(ei, w, N)
+    rowptr, col, val = o.csr()
+    plan = build_plan(rowptr, col, val, N, N, chunk)
+    assert int(plan.item_ptr[0]) == 0 and int(plan.item_ptr[-1]) == col.numel()
+    assert torch.all(plan.item_ptr[1:] >= plan.item_ptr[:-1])
+    if chunk is not None:
+        assert int((plan.item_ptr[1:] - plan.item_ptr[:-1]).max()) <= chunk
+        assert plan.n_fix > 0                      # the hub row is split
+    x = torch.randn(N, 6)
+    for reduce in ("sum", "mean"):
+        got = _emulate(plan, x, use_val=(reduce == "sum"), div=(reduce == "mean"))
+        adj = o if reduce == "sum" else o.set_value(None)
+        assert not torch.isnan(got).any()
+        assert rel_err(got, sparse.matmul(adj, x, reduce)) < 1e-5
+
+
+def test_adjust_lr_and_loss_dispatch():
+    from plnlp_b200.model import BaseModel, adjust_lr
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0)
+    assert adjust_lr(opt, 0.25, 0.01) == pytest.approx(0.0075)
+    assert opt.param_groups[0]["lr"] == pytest.approx(0.0075)
+    assert adjust_lr(opt, 1.0, 0.01) == pytest.approx(1e-6)
+    m = BaseModel.__new__(BaseModel)
+    m.loss_func_name = "WeightedHingeAUC"
+    assert m._loss_name(True) == "WeightedHingeAUC" and m._loss_name(False) == "AUC"
+    m.loss_func_name = "HingeAUC"
+    assert m._loss_name(False) == "HingeAUC"
+    m.loss_func_name = "something-else"
+    assert m._loss_name(False) == "AUC"
+    m.loss_func_name = "CE"
+    with pytest.raises(NotImplementedError):
+        m._loss_name(False)
+
+
+def test_logger_statistics():
+    from plnlp_b200.logger import Logger
+    lg = Logger(2)
+    for r, seq in enumerate([[(0.1, 0.2), (0.5, 0.3), (0.5, 0.4)], [(0.7, 0.6), (0.2, 0.9)]]):
+        for res in seq:
+            lg.add_result(r, res)
+    buf = io.StringIO()
+    lg.print_statistics(0, f=buf)
+    assert "Highest Eval Point: 2" in buf.getvalue() and "Final Test: 30.00" in buf.getvalue()
+    buf = io.StringIO()
+    lg.print_statistics(0, f=buf, last_best=True)
+    assert "Highest Eval Point: 3" in buf.getvalue() and "Final Test: 40.00" in buf.getvalue()
+    buf = io.StringIO()
+    lg.print_statistics(f=buf)
+    assert "Highest Valid: 60.00" in buf.getvalue() and "Final Test: 45.00" in buf.getvalue()
+
+
+def test_out_of_scope_names_exist_and_raise():
+    import plnlp_b200.layer as L
+    import plnlp_b200.loss as S
+    import plnlp_b200.negative_sample as NS
+    for name in ("WSAGE", "Transformer", "MLPCatPredictor", "MLPDotPredictor", "MLPBilPredictor",
+                 "BilinearPredictor"):
+        with pytest.raises(NotImplementedError):
+            getattr(L, name)(4, 4, 4, 1, 0.0)
+    for name in ("weighted_auc_loss", "adaptive_auc_loss", "adaptive_hinge_auc_loss", "log_rank_loss",
+                 "ce_loss", "info_nce_loss"):
+        with pytest.raises(NotImplementedError):
+            getattr(S, name)(None, None)
+    with pytest.raises(NotImplementedError):
+        NS.global_perm_neg_sample(None, 1, 1, 1)

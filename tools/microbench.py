@@ -1,0 +1,138 @@
+"""Per-kernel timings at the BASELINE shapes (CUDA events on the launching stream).
+Usage: python tools/microbench.py [ddi|citation2|sweep] ...   (run under gpurun)"""
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from plnlp_b200 import _ops  # noqa: E402
+from plnlp_b200.graph import CSRGraph, structure_of  # noqa: E402
+
+DEV = torch.device("cuda")
+PEAKS = {}
+try:
+    PEAKS = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+except Exception:
+    pass
+HBM = PEAKS.get("hbm_gbs", 6650.0)
+
+
+def timeit(fn, warm=3, iters=10, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def undirected_graph(N, E, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    lo = torch.randint(0, N, (int(E * 1.25),), generator=g, device=DEV)
+    hi = torch.randint(0, N, (int(E * 1.25),), generator=g, device=DEV)
+    key = torch.unique(torch.minimum(lo, hi) * N + torch.maximum(lo, hi))
+    key = key[(key // N) != (key % N)]
+    key = key[torch.randperm(key.numel(), device=DEV, generator=g)[:E]]
+    ei = torch.stack([key // N, key % N])
+    return torch.cat([ei, ei.flip(0)], 1)
+
+
+def powerlaw_graph(N, E, seed, alpha=2.1):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    # in-degree power law: destination drawn from a Zipf-like distribution over a random node order
+    u = torch.rand(E, generator=g, device=DEV)
+    dst_rank = (N * u.pow(alpha)).long().clamp(max=N - 1)
+    perm = torch.randperm(N, device=DEV, generator=g)
+    dst = perm[dst_rank]
+    src = torch.randint(0, N, (E,), generator=g, device=DEV)
+    return torch.stack([src, dst])
+
+
+def bench_spmm(name, adj, F, reduce, flush):
+    st = structure_of(adj)
+    plan = st.fwd_noval if reduce == "mean" else st.fwd
+    x = torch.randn(adj.size(1), F, device=DEV)
+    ms = timeit(lambda: _ops.spmm_raw(plan, x, use_val=reduce != "mean", div_rows=reduce == "mean"), flush=flush)
+    by = plan.alg_bytes(F) if reduce != "mean" else plan.alg_bytes(F) - (plan.nnz * 4 if plan.val is not None else 0)
+    print(f"[spmm] {name} F={F} {reduce}: {ms:.3f} ms  alg {by/1e9:.2f} GB -> {by/ms/1e6:.0f} GB/s "
+          f"({by/ms/1e6/HBM*100:.0f}% of measured HBM {HBM:.0f}) items={plan.n_items} chunk={plan.chunk} nfix={plan.n_fix}",
+          flush=True)
+    return ms
+
+
+def bench_gemm(M, N, K, ta=False, tb=True, **kw):
+    A = torch.randn((K, M) if ta else (M, K), device=DEV)
+    B = torch.randn((N, K) if tb else (K, N), device=DEV)
+    ms = timeit(lambda: _ops.gemm_raw(A, B, transa=ta, transb=tb, **kw))
+    fl = 2.0 * M * N * K
+    print(f"[gemm] M={M} N={N} K={K} ta={int(ta)} tb={int(tb)}: {ms:.3f} ms -> {fl/ms/1e9:.1f} TFLOP/s", flush=True)
+    return ms
+
+
+def ddi():
+    N, E, H, B, k = 4267, 1067911, 512, 65536, 3
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=DEV)
+    adj = CSRGraph.from_edge_index(undirected_graph(N, E, 0), None, N)
+    bench_spmm("ddi", adj, H, "mean", None)
+    bench_spmm("ddi(L2 flushed)", adj, H, "mean", flush)
+    P = B * (1 + k)
+    bench_gemm(N, H, H)
+    bench_gemm(P, H, H)                       # predictor layer 1 fwd
+    bench_gemm(P, H, H, tb=False)             # dA0 = dZ1 @ W1
+    bench_gemm(H, H, P, ta=True, tb=False)    # dW1 = dZ1^T @ A0 (split-k)
+    h = torch.randn(N, H, device=DEV)
+    edges = torch.randint(0, N, (P, 2), device=DEV)
+    ms = timeit(lambda: _ops.gather_hadamard_raw(h, edges))
+    print(f"[gather_hadamard] P={P} H={H}: {ms:.3f} ms -> {(P*H*4*3)/ms/1e6:.0f} GB/s (2 gathered rows + 1 written)")
+    da = torch.randn(P, H, device=DEV)
+    for mode in ("sorted", "atomic"):
+        ms = timeit(lambda: _ops.edge_scatter_raw(h, edges, da=da, mode=mode))
+        print(f"[edge_scatter {mode}] {ms:.3f} ms")
+    a = torch.relu(torch.randn(P, H, device=DEV))
+    w, b, ds = torch.randn(1, H, device=DEV), torch.randn(1, device=DEV), torch.randn(P, device=DEV)
+    ms = timeit(lambda: _ops.mlp_out_fwd_raw(a, w, b))
+    print(f"[mlp_out_fwd] {ms:.3f} ms -> {P*H*4/ms/1e6:.0f} GB/s")
+    ms = timeit(lambda: _ops.mlp_out_bwd_raw(a, w, ds, True, 1.0))
+    print(f"[mlp_out_bwd] {ms:.3f} ms -> {P*H*8/ms/1e6:.0f} GB/s")
+    pos, neg = torch.randn(B, device=DEV), torch.randn(B * k, device=DEV)
+    ms = timeit(lambda: _ops.pair_loss_raw(0, pos, neg, k))
+    print(f"[pair_loss] {ms:.3f} ms")
+
+
+def citation2(scale=1.0):
+    N, E, F = int(2927963 * scale), int(30561187 * scale), 200
+    ei = powerlaw_graph(N, E, 1)
+    t0 = time.time()
+    adj = CSRGraph.from_edge_index(ei, None, N).to_symmetric()
+    from plnlp_b200.utils import gcn_normalization
+    adj = gcn_normalization(adj)
+    st = structure_of(adj)
+    torch.cuda.synchronize()
+    print(f"citation2-shape graph: N={N} nnz={adj.nnz()} built in {time.time()-t0:.1f}s symmetric={st.symmetric} "
+          f"max_deg={int((adj.csr()[0][1:]-adj.csr()[0][:-1]).max())}")
+    bench_spmm("citation2", adj, F, "sum", None)
+    bench_spmm("citation2", adj, 128, "sum", None)
+    bench_spmm("citation2", adj, 256, "sum", None)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["ddi"]
+    print("device:", torch.cuda.get_device_name(0), "HBM peak (measured):", HBM)
+    if "ddi" in which:
+        ddi()
+    if "citation2" in which:
+        citation2()
+    if "citation2_small" in which:
+        citation2(0.25)
