@@ -13,7 +13,7 @@ import pytest
 import torch
 
 from oracle import plnlp_ref, sparse
-from tests.helpers import rand_graph, rel_err
+from tests.helpers import fp32_close, rand_graph, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -121,24 +121,35 @@ def test_first_step_gradients_match_reference(golden_dir, tag, scatter):
                                  None if w is None else w[perm].cuda())
     finally:
         _ops.SCATTER_MODE = "sorted"
-    ref = plnlp_ref.OracleModel(num_nodes=cfg["num_nodes"], emb_hidden=cfg["emb"], gnn_hidden=cfg["hid"],
-                                mlp_hidden=cfg["hid"], gnn_layers=cfg["gnn_layers"], mlp_layers=cfg["mlp_layers"],
-                                encoder=cfg["encoder"], predictor=cfg["predictor"], loss=cfg["loss"], lr=cfg["lr"],
-                                clip_norm=-1.0, num_node_feats=cfg["feats"], use_node_feats=cfg["use_feats"])
     st = {"enc." + k[len("convs."):]: v for k, v in R["init"]["encoder"].items()}
     st.update({"pred." + k[len("lins."):]: v for k, v in R["init"]["predictor"].items()})
     st["emb"] = R["init"]["emb"]
-    ref.load(st)
-    adj = sparse.SparseTensor(rowptr=R["adj_rowptr"], col=R["adj_col"], value=R["adj_val"],
-                              sparse_sizes=(cfg["num_nodes"],) * 2, is_sorted=True)
-    rloss, _ = ref.step(R["x"], adj, pos[perm], neg[perm], cfg["num_neg"], None if w is None else w[perm],
-                        do_update=False)
-    assert rel_err(loss.cpu(), rloss) < TOL
-    assert rel_err(model.emb.weight.grad.cpu(), ref.params["emb"].grad) < TOL
+    refs = {}
+    for dt in (torch.float32, torch.float64):
+        ref = plnlp_ref.OracleModel(num_nodes=cfg["num_nodes"], emb_hidden=cfg["emb"], gnn_hidden=cfg["hid"],
+                                    mlp_hidden=cfg["hid"], gnn_layers=cfg["gnn_layers"],
+                                    mlp_layers=cfg["mlp_layers"], encoder=cfg["encoder"],
+                                    predictor=cfg["predictor"], loss=cfg["loss"], lr=cfg["lr"], clip_norm=-1.0,
+                                    num_node_feats=cfg["feats"], use_node_feats=cfg["use_feats"], dtype=dt)
+        ref.load({k: v.to(dt) for k, v in st.items()})
+        val = R["adj_val"]
+        adj = sparse.SparseTensor(rowptr=R["adj_rowptr"], col=R["adj_col"], value=None if val is None else val.to(dt),
+                                  sparse_sizes=(cfg["num_nodes"],) * 2, is_sorted=True)
+        rloss, _ = ref.step(None if R["x"] is None else R["x"].to(dt), adj, pos[perm], neg[perm], cfg["num_neg"],
+                            None if w is None else w[perm].to(dt), do_update=False)
+        refs[dt] = (rloss, ref)
+    (l32, r32), (l64, r64) = refs[torch.float32], refs[torch.float64]
+    assert rel_err(loss.cpu(), l64) < TOL
+
+    def check(name, got, key):
+        ok, msg = fp32_close(got, r32.params[key].grad, r64.params[key].grad, TOL)
+        assert ok, f"{name}: {msg}"
+
+    check("emb", model.emb.weight.grad, "emb")
     for name, p in model.encoder.named_parameters():
-        assert rel_err(p.grad.cpu(), ref.params["enc." + name[len("convs."):]].grad) < TOL, name
+        check(name, p.grad, "enc." + name[len("convs."):])
     for name, p in model.predictor.named_parameters():
-        assert rel_err(p.grad.cpu(), ref.params["pred." + name[len("lins."):]].grad) < TOL, name
+        check(name, p.grad, "pred." + name[len("lins."):])
 
 
 @pytest.mark.parametrize("tag", ["ddi_like", "collab_like", "citation_like", "hinge_like"])
