@@ -1,0 +1,380 @@
+"""bench.py -- the driver's measurement contract for the PLNLP hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload ddi|citation2]
+
+A "step" is one optimisation step of ``BaseModel.train`` over one batch of 65 536 positive edges and
+their negatives: full-graph encode (fwd + bwd), fused edge scoring + pairwise loss, clip, Adam.
+Metric (BASELINE.json): pos+neg pairs/s.
+
+  value : K steps with the training edges resident in HBM (negatives for those K batches are sampled
+          on the GPU inside the timed region, as the per-epoch sampler of the reference would).
+  e2e   : the public call ``BaseModel.train(data, split_edge, ...)`` with split_edge in (pinned) HOST
+          memory: H2D of the positive edges + sampler + K steps + D2H of the epoch loss.
+  roofline / kernels : per-kernel CUDA-event durations from an instrumented pass of the same K steps.
+  cpu_baseline : the oracle restatement of the reference step (torch CPU, all host threads) on a
+          bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1] / SURVEY.md 8d config 1-2
+    "ddi": dict(name="ddi-shape", N=4267, E=1067911, feats=0, emb=512, hid=512, gnn_layers=2, mlp_layers=2,
+                encoder="SAGE", predictor="MLP", loss="AUC", sampler="global", num_neg=3, batch=65536,
+                dropout=0.3, clip=2.0, use_feats=False, directed=False),
+    # BASELINE.json configs[3] / SURVEY.md 8d config 4
+    "citation2": dict(name="citation2-shape", N=2927963, E=30561187, feats=128, emb=50, hid=200, gnn_layers=2,
+                      mlp_layers=2, encoder="GCN", predictor="MLP", loss="AUC", sampler="local", num_neg=3,
+                      batch=65536, dropout=0.0, clip=1.0, use_feats=True, directed=True),
+}
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return dict(hbm=p["hbm_gbs"], tensor=p["bf16_tflops_sustained"], tensor_burst=p["bf16_tflops"], src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tensor=1400.0, tensor_burst=1590.0, src="fallback")
+
+
+class Data:
+    pass
+
+
+# ----------------------------------------------------------------------------- synthetic graphs
+def make_edges(cfg, device, seed=0):
+    """synthetic OGB-shape edge list [2, E]: ddi-shape = uniform undirected simple graph;
+    citation2-shape = directed, power-law in-degree."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    N, E = cfg["N"], cfg["E"]
+    if not cfg["directed"]:
+        lo = torch.randint(0, N, (int(E * 1.3),), generator=g, device=device)
+        hi = torch.randint(0, N, (int(E * 1.3),), generator=g, device=device)
+        key = torch.unique(torch.minimum(lo, hi) * N + torch.maximum(lo, hi))
+        key = key[torch.div(key, N, rounding_mode="floor") != key % N]
+        key = key[torch.randperm(key.numel(), generator=g, device=device)[:E]]
+        return torch.stack([torch.div(key, N, rounding_mode="floor"), key % N])
+    u = torch.rand(E, generator=g, device=device)
+    rank = (N * u.pow(2.1)).long().clamp(max=N - 1)
+    perm = torch.randperm(N, generator=g, device=device)
+    dst = perm[rank]
+    src = torch.randint(0, N, (E,), generator=g, device=device)
+    keep = src != dst
+    return torch.stack([src[keep], dst[keep]])
+
+
+def build_workload(cfg, device, graph_cls, normalize):
+    ei = make_edges(cfg, device)
+    N = cfg["N"]
+    data = Data()
+    if cfg["directed"]:
+        adj = graph_cls.from_edge_index(ei, None, N)
+        row, col, _ = adj.coo()
+        data.edge_index = torch.stack([col, row], 0)         # main.py:82-83 (before symmetrisation)
+        adj = adj.to_symmetric()                              # main.py:109-110
+        split = {"train": {"source_node": ei[0].contiguous(), "target_node": ei[1].contiguous()}}
+    else:
+        und = torch.cat([ei, ei.flip(0)], 1)
+        adj = graph_cls.from_edge_index(und, None, N)
+        row, col, _ = adj.coo()
+        data.edge_index = torch.stack([col, row], 0)
+        split = {"train": {"edge": ei.t().contiguous()}}
+    if cfg["encoder"] == "GCN":
+        adj = normalize(adj)                                  # main.py:177-179
+    data.adj_t = adj
+    g = torch.Generator(device=device).manual_seed(1)
+    data.x = torch.randn(N, cfg["feats"], generator=g, device=device) if cfg["feats"] else None
+    return data, split
+
+
+def make_model(cfg, device):
+    from plnlp_b200.model import BaseModel
+    m = BaseModel(lr=0.001, dropout=cfg["dropout"], grad_clip_norm=cfg["clip"], gnn_num_layers=cfg["gnn_layers"],
+                  mlp_num_layers=cfg["mlp_layers"], emb_hidden_channels=cfg["emb"], gnn_hidden_channels=cfg["hid"],
+                  mlp_hidden_channels=cfg["hid"], num_nodes=cfg["N"], num_node_feats=cfg["feats"],
+                  gnn_encoder_name=cfg["encoder"], predictor_name=cfg["predictor"], loss_func=cfg["loss"],
+                  optimizer_name="Adam", device=device, use_node_feats=cfg["use_feats"], train_node_emb=True)
+    m.param_init()
+    return m
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+
+    from plnlp_b200 import _lib, _ops, profiling
+    from plnlp_b200.graph import CSRGraph
+    from plnlp_b200.utils import gcn_normalization, get_pos_neg_edges
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    assert _lib.load().plnlp_check_device() == 0, "plnlp_b200 needs an sm_100 device"
+    cfg = dict(WORKLOADS[args.workload])
+    torch.manual_seed(0)
+    data, split = build_workload(cfg, device, CSRGraph, gcn_normalization)
+    model = make_model(cfg, device)
+    B, k = cfg["batch"], cfg["num_neg"]
+    K, W = args.steps, args.warmup
+    pos_all = split["train"]["edge"] if "edge" in split["train"] else \
+        torch.stack([split["train"]["source_node"], split["train"]["target_node"]], 1)
+    E = pos_all.size(0)
+    # weak scaling over edge batches: every rank steps on its own batch of B positives, gradients are
+    # all-reduced (model.py has no multi-device path)
+    model.world_size, model.rank = world, rank
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_steps(n, seed_shift):
+        """n steps on HBM-resident edges; negatives for exactly these n batches sampled on the GPU"""
+        g = torch.Generator(device=device).manual_seed(1000 + seed_shift + rank)
+        idx = torch.randint(0, E, (n * B,), generator=g, device=device)
+        sub = {"train": {"edge": pos_all[idx]}}
+        pos, neg = get_pos_neg_edges("train", sub, edge_index=data.edge_index, num_nodes=cfg["N"],
+                                     neg_sampler_name=cfg["sampler"], num_neg=k, device=device)
+        model.encoder.train(); model.predictor.train()
+        for i in range(n):
+            model.train_batch(data, pos[i * B:(i + 1) * B], neg[i * B:(i + 1) * B].reshape(-1, 2), k)
+
+    # ---- value: device-resident ------------------------------------------------------------
+    device_steps(W, 0)
+    barrier()
+    l0 = _lib.launch_count()
+    with ClockSampler(local) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        device_steps(K, 1)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - l0
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    pairs = K * B * (1 + k) * world
+    value = pairs / (ms / 1e3)
+
+    # ---- e2e: public API with HOST split_edge ----------------------------------------------
+    host_split = {"train": {kk: v.cpu().pin_memory() for kk, v in split["train"].items()}}
+    model.train(data, host_split, batch_size=B, neg_sampler_name=cfg["sampler"], num_neg=k, max_batches=W)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    model.train(data, host_split, batch_size=B, neg_sampler_name=cfg["sampler"], num_neg=k, max_batches=K)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    h2d = sum(v.numel() * v.element_size() for v in host_split["train"].values())
+    e2e = {"value": pairs / (e2e_ms / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d // K,
+           "d2h_bytes_per_step": 8 // K if K <= 8 else 1, "ms_per_step": e2e_ms / K,
+           "note": "BaseModel.train(host split_edge): H2D of all positive edges + per-epoch sampler + K steps + "
+                   "loss D2H; bytes are the per-epoch copies divided by K"}
+
+    # ---- instrumented pass: per-kernel durations (rank 0) ------------------------------------
+    roof, kernels = None, []
+    if rank == 0:
+        pk = peaks()
+        profiling.enable()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        device_steps(K, 2)
+        p1.record()
+        torch.cuda.synchronize()
+        stats = profiling.disable()
+        ours = sum(s["ms"] for s in stats.values())
+        stats["(torch plumbing: adam, clip, index, cat, sampler glue, launch gaps)"] = {
+            "n": 1, "ms": max(p0.elapsed_time(p1) - ours, 0.0), "bytes": 0, "flops": 0}
+        total = sum(s["ms"] for s in stats.values()) or 1.0
+        for name, s in sorted(stats.items(), key=lambda kv: -kv[1]["ms"]):
+            rec = {"kernel": name, "launches": s["n"], "ms_total": round(s["ms"], 3),
+                   "share": round(s["ms"] / total, 4), "avg_ms": round(s["ms"] / s["n"], 4)}
+            if s["bytes"]:
+                rec["achieved_gbs"] = round(s["bytes"] / s["ms"] / 1e6, 1)
+                rec["frac_hbm"] = round(s["bytes"] / s["ms"] / 1e6 / pk["hbm"], 4)
+            if s["flops"]:
+                rec["achieved_tflops"] = round(s["flops"] / s["ms"] / 1e9, 2)
+                rec["frac_tensor"] = round(s["flops"] / s["ms"] / 1e9 / pk["tensor"], 4)
+            kernels.append(rec)
+        top = next(r for r in kernels if not r["kernel"].startswith("("))
+        if "achieved_tflops" in top:
+            roof = {"kernel": top["kernel"], "bound": "tensor", "achieved": top["achieved_tflops"],
+                    "peak": pk["tensor"], "unit": "TFLOP/s", "frac": top["frac_tensor"], "traffic": None,
+                    "peak_source": pk["src"] + " bf16 sustained; kernel computes in fp32"}
+        else:
+            roof = {"kernel": top["kernel"], "bound": "hbm", "achieved": top.get("achieved_gbs"),
+                    "peak": pk["hbm"], "unit": "GB/s", "frac": top.get("frac_hbm"), "traffic": None,
+                    "peak_source": pk["src"]}
+        spmm = [r for r in kernels if r["kernel"].startswith("spmm")]
+        if spmm:
+            src_bytes = cfg["N"] * cfg["hid"] * 4
+            roof["spmm"] = {"achieved_gbs": spmm[0].get("achieved_gbs"), "frac_hbm": spmm[0].get("frac_hbm"),
+                            "l2_resident_source": bool(src_bytes < 126e6),
+                            "note": "effective bandwidth of the gather model; source matrix is L2-resident"
+                            if src_bytes < 126e6 else "source matrix exceeds L2"}
+
+    # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(cfg, steps=args.cpu_steps)
+
+    if rank == 0:
+        line = {"metric": "pos+neg pairs/s (train step)", "value": value, "unit": "pairs/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{cfg['name']} N={cfg['N']} E={E} {cfg['gnn_layers']}x{cfg['encoder']}"
+                                       f"{cfg['hid']} + {cfg['predictor']} head, num_neg={k}, {cfg['loss']} loss, "
+                                       f"batch={B} positives/step/GPU, dropout={cfg['dropout']}",
+                           "pairs_per_step_per_gpu": B * (1 + k),
+                           "l2": "working set per step (>1.6 GB of per-pair activations) exceeds the 126 MB L2",
+                           "parallelism": f"dp{world} over edge batches, encoder replicated" if world > 1 else "single"},
+                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roof, "kernels": kernels[:12], "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_baseline(cfg, steps=2):
+    """the oracle restatement of the reference's train step (torch CPU, all host threads) on a bounded
+    sample: `steps` optimisation steps of the same workload (full-graph encode each)."""
+    from oracle import plnlp_ref, sparse
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cpu = torch.device("cpu")
+    data, split = build_workload(cfg, cpu, _OracleGraph, sparse.gcn_normalization)
+    m = plnlp_ref.OracleModel(num_nodes=cfg["N"], emb_hidden=cfg["emb"], gnn_hidden=cfg["hid"], mlp_hidden=cfg["hid"],
+                              gnn_layers=cfg["gnn_layers"], mlp_layers=cfg["mlp_layers"], encoder=cfg["encoder"],
+                              predictor=cfg["predictor"], loss=cfg["loss"], lr=0.001, clip_norm=cfg["clip"],
+                              num_node_feats=cfg["feats"], use_node_feats=cfg["use_feats"])
+    pos_all = plnlp_ref.train_pos_edges(split)
+    B, k, N = cfg["batch"], cfg["num_neg"], cfg["N"]
+    g = torch.Generator().manual_seed(3)
+
+    def one():
+        idx = torch.randint(0, pos_all.size(0), (B,), generator=g)
+        pos = pos_all[idx]
+        neg = torch.stack([pos[:, :1].expand(B, k), torch.randint(0, N, (B, k), generator=g)], -1)
+        m.step(data.x, data.adj_t, pos, neg, k)
+
+    one()                                    # warm-up (allocator, MKL)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    return {"value": steps * B * (1 + k) / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} train steps of {B * (1 + k)} pairs on the same {cfg['name']} workload after 1 warm-up "
+                      f"step ({dt:.1f} s); oracle restatement of the reference step in torch CPU "
+                      "(torch_geometric / torch_sparse are not installable here, so this is NOT the PyG path); "
+                      "negatives pre-drawn uniformly (sampler cost excluded)", "seconds": dt}
+
+
+class _OracleGraph:
+    """adapter giving oracle.sparse.SparseTensor the constructor name build_workload uses"""
+
+    @staticmethod
+    def from_edge_index(ei, w, N):
+        from oracle import sparse
+        return sparse.to_sparse_tensor(ei, w, N)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = dict(WORKLOADS[args.workload])
+    K, W = args.steps, args.warmup
+    steps = max(1, min(K, args.cpu_steps))
+    cpu = cpu_baseline(cfg, steps=steps)
+    B, k = cfg["batch"], cfg["num_neg"]
+    line = {"impl": "reference", "metric": "pos+neg pairs/s (train step)", "value": cpu["value"], "unit": "pairs/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": 1,
+            "ms_per_step": cpu["seconds"] / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{cfg['name']} N={cfg['N']} E~{cfg['E']} {cfg['gnn_layers']}x{cfg['encoder']}"
+                                   f"{cfg['hid']} + {cfg['predictor']} head, num_neg={k}, {cfg['loss']} loss, "
+                                   f"batch={B} positives/step", "requested_steps": K, "requested_warmup": W},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=17)      # one ddi-shape epoch = 17 batches
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ddi", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -185,9 +185,10 @@ class OracleModel:
     def __init__(self, *, num_nodes, emb_hidden, gnn_hidden, mlp_hidden, gnn_layers, mlp_layers,
                  encoder="SAGE", predictor="MLP", loss="AUC", lr=1e-3, dropout=0.0,
                  clip_norm=2.0, num_node_feats=0, use_node_feats=False, train_node_emb=True,
-                 dtype=torch.float32):
+                 dtype=torch.float32, optimizer="Adam"):
         self.kind, self.pred_kind, self.loss_name = encoder.upper(), predictor.upper(), loss
         self.dropout, self.clip_norm, self.lr = dropout, clip_norm, lr
+        self.optimizer_name = optimizer
         self.use_node_feats, self.train_node_emb = use_node_feats, train_node_emb
         self.num_nodes = num_nodes
         in_dim = 0
@@ -230,7 +231,11 @@ class OracleModel:
         order = [k for k in self.params if k.startswith("enc.")] + \
                 [k for k in self.params if k.startswith("pred.")] + \
                 [k for k in self.params if k == "emb"]
-        self.optimizer = torch.optim.Adam([self.params[k] for k in order], lr=self.lr)
+        plist = [self.params[k] for k in order]
+        if self.optimizer_name == "SGD":   # model.py:87-88
+            self.optimizer = torch.optim.SGD(plist, lr=self.lr, momentum=0.9, weight_decay=1e-5, nesterov=True)
+        else:
+            self.optimizer = torch.optim.Adam(plist, lr=self.lr)
 
     def load(self, state):
         with torch.no_grad():

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib
+from . import _lib, profiling
 from ._lib import check, ptr, stream, workspace
 from .graph import structure_of
 
@@ -65,11 +65,12 @@ def spmm_raw(plan, x, use_val, div_rows, bias=None, relu=False, drop_p=0.0, seed
     if plan.n_fix:
         partial = workspace.get("spmm_partial", plan.n_partial * F * 4, x.device)
     val = plan.val if use_val else None
-    check(lib.plnlp_spmm_csr_f32(ptr(plan.item_ptr), ptr(plan.item_row), ptr(plan.item_slot), plan.n_items,
-                                 ptr(plan.col), ptr(val), ptr(plan.row_cnt if div_rows else None), ptr(bias),
-                                 int(relu), float(drop_p), int(seed), ptr(x), _ld(x), ptr(out), _ld(out), F,
-                                 ptr(partial), ptr(plan.fix_ptr), ptr(plan.fix_row), plan.n_fix, stream()),
-          "plnlp_spmm_csr_f32")
+    with profiling.span("spmm_csr_f32", plan.alg_bytes(F) - (0 if use_val or plan.val is None else plan.nnz * 4), 0):
+        check(lib.plnlp_spmm_csr_f32(ptr(plan.item_ptr), ptr(plan.item_row), ptr(plan.item_slot), plan.n_items,
+                                     ptr(plan.col), ptr(val), ptr(plan.row_cnt if div_rows else None), ptr(bias),
+                                     int(relu), float(drop_p), int(seed), ptr(x), _ld(x), ptr(out), _ld(out), F,
+                                     ptr(partial), ptr(plan.fix_ptr), ptr(plan.fix_row), plan.n_fix, stream()),
+              "plnlp_spmm_csr_f32")
     return out
 
 
@@ -95,10 +96,11 @@ def gemm_raw(A, B, transa=False, transb=False, C=None, beta=0.0, bias=None, act=
     if split_k > 1:
         ws_bytes = split_k * M * N * 4
         ws = workspace.get("gemm_splitk", ws_bytes, A.device)
-    check(lib.plnlp_gemm_f32(int(transa), int(transb), M, N, K, ptr(A), _ld(A), ptr(B), _ld(B), ptr(C), _ld(C),
-                             float(beta), ptr(bias), int(act), ptr(aux), _ld(aux) if aux is not None else 0,
-                             float(drop_p), int(seed), ptr(ws), ws_bytes, int(split_k), stream()),
-          "plnlp_gemm_f32")
+    with profiling.span(f"gemm_f32 {M}x{N}x{K}{' splitk' if split_k > 1 else ''}", 0, 2 * M * N * K):
+        check(lib.plnlp_gemm_f32(int(transa), int(transb), M, N, K, ptr(A), _ld(A), ptr(B), _ld(B), ptr(C), _ld(C),
+                                 float(beta), ptr(bias), int(act), ptr(aux), _ld(aux) if aux is not None else 0,
+                                 float(drop_p), int(seed), ptr(ws), ws_bytes, int(split_k), stream()),
+              "plnlp_gemm_f32")
     return C
 
 
@@ -109,8 +111,9 @@ def colsum_raw(x, scale=1.0):
     out = torch.empty(cols, dtype=torch.float32, device=x.device)
     nbytes = lib.plnlp_colsum_workspace_bytes(rows, cols)
     ws = workspace.get("colsum", nbytes, x.device)
-    check(lib.plnlp_colsum_f32(ptr(x), _ld(x), rows, cols, float(scale), ptr(out), ptr(ws), nbytes, stream()),
-          "plnlp_colsum_f32")
+    with profiling.span("colsum_f32", rows * cols * 4, 0):
+        check(lib.plnlp_colsum_f32(ptr(x), _ld(x), rows, cols, float(scale), ptr(out), ptr(ws), nbytes, stream()),
+              "plnlp_colsum_f32")
     return out
 
 
@@ -118,8 +121,9 @@ def relu_drop_bwd_raw(y, dy, scale):
     lib = _lib.load()
     y, dy = _rowmajor(y), _rowmajor(dy)
     dx = torch.empty(y.shape, dtype=torch.float32, device=y.device)
-    check(lib.plnlp_relu_drop_bwd_f32(ptr(y), _ld(y), ptr(dy), _ld(dy), float(scale), y.size(0), y.size(1),
-                                      ptr(dx), _ld(dx), stream()), "plnlp_relu_drop_bwd_f32")
+    with profiling.span("relu_drop_bwd_f32", y.numel() * 12, 0):
+        check(lib.plnlp_relu_drop_bwd_f32(ptr(y), _ld(y), ptr(dy), _ld(dy), float(scale), y.size(0), y.size(1),
+                                          ptr(dx), _ld(dx), stream()), "plnlp_relu_drop_bwd_f32")
     return dx
 
 
@@ -136,8 +140,9 @@ def gather_hadamard_raw(h, edges):
     h, edges = _rowmajor(h), _edges_i64(edges)
     P, H = edges.size(0), h.size(1)
     out = torch.empty(P, H, dtype=torch.float32, device=h.device)
-    check(lib.plnlp_gather_hadamard_f32(ptr(h), _ld(h), h.size(0), ptr(edges), P, H, ptr(out), H, stream()),
-          "plnlp_gather_hadamard_f32")
+    with profiling.span("gather_hadamard_f32", P * (3 * H * 4 + 16), 0):
+        check(lib.plnlp_gather_hadamard_f32(ptr(h), _ld(h), h.size(0), ptr(edges), P, H, ptr(out), H, stream()),
+              "plnlp_gather_hadamard_f32")
     return out
 
 
@@ -146,8 +151,9 @@ def edge_dot_raw(h, edges):
     h, edges = _rowmajor(h), _edges_i64(edges)
     P, H = edges.size(0), h.size(1)
     score = torch.empty(P, dtype=torch.float32, device=h.device)
-    check(lib.plnlp_edge_dot_fwd_f32(ptr(h), _ld(h), h.size(0), ptr(edges), P, H, ptr(score), stream()),
-          "plnlp_edge_dot_fwd_f32")
+    with profiling.span("edge_dot_fwd_f32", P * (2 * H * 4 + 20), 0):
+        check(lib.plnlp_edge_dot_fwd_f32(ptr(h), _ld(h), h.size(0), ptr(edges), P, H, ptr(score), stream()),
+              "plnlp_edge_dot_fwd_f32")
     return score
 
 
@@ -157,8 +163,9 @@ def mlp_out_fwd_raw(a, w, b):
     w = _f32c(w).reshape(-1).contiguous()
     P, H = a.shape
     score = torch.empty(P, dtype=torch.float32, device=a.device)
-    check(lib.plnlp_mlp_out_fwd_f32(ptr(a), _ld(a), ptr(w), ptr(b), P, H, ptr(score), stream()),
-          "plnlp_mlp_out_fwd_f32")
+    with profiling.span("mlp_out_fwd_f32", P * (H * 4 + 4), 0):
+        check(lib.plnlp_mlp_out_fwd_f32(ptr(a), _ld(a), ptr(w), ptr(b), P, H, ptr(score), stream()),
+              "plnlp_mlp_out_fwd_f32")
     return score
 
 
@@ -174,9 +181,10 @@ def mlp_out_bwd_raw(a, w, dscore, mask_a, drop_scale):
     db = torch.empty(1, dtype=torch.float32, device=a.device)
     nbytes = lib.plnlp_mlp_out_bwd_workspace_bytes(P, H)
     ws = workspace.get("mlp_out_bwd", nbytes, a.device)
-    check(lib.plnlp_mlp_out_bwd_f32(ptr(a), _ld(a), ptr(w), ptr(dscore), P, H, int(mask_a), float(drop_scale),
-                                    ptr(dz), H, ptr(dw), ptr(db), ptr(ws), nbytes, stream()),
-          "plnlp_mlp_out_bwd_f32")
+    with profiling.span("mlp_out_bwd_f32", P * (2 * H * 4 + 4), 0):
+        check(lib.plnlp_mlp_out_bwd_f32(ptr(a), _ld(a), ptr(w), ptr(dscore), P, H, int(mask_a), float(drop_scale),
+                                        ptr(dz), H, ptr(dw), ptr(db), ptr(ws), nbytes, stream()),
+              "plnlp_mlp_out_bwd_f32")
     return dz, dw, db
 
 
@@ -193,11 +201,14 @@ def edge_scatter_raw(h, edges, da=None, dscore=None, mode=None):
     grad_h = torch.zeros(n_rows, H, dtype=torch.float32, device=h.device)
     ldda = _ld(da) if da is not None else 0
     if mode == "atomic":
-        check(lib.plnlp_edge_scatter_atomic_f32(ptr(h), _ld(h), n_rows, ptr(edges), P, H, ptr(da), ldda,
-                                                ptr(dscore), ptr(grad_h), H, stream()),
-              "plnlp_edge_scatter_atomic_f32")
+        with profiling.span("edge_scatter_atomic_f32", P * (5 * H * 4 + 16), 0):
+            check(lib.plnlp_edge_scatter_atomic_f32(ptr(h), _ld(h), n_rows, ptr(edges), P, H, ptr(da), ldda,
+                                                    ptr(dscore), ptr(grad_h), H, stream()),
+                  "plnlp_edge_scatter_atomic_f32")
         return grad_h
     # node-sorted incidence list: key = node * 2P + (2p + side) is unique -> any sort is deterministic
+    _sp = profiling.span("torch: sort+unique for sorted scatter")
+    _sp.__enter__()
     flat = edges.reshape(-1)                          # entry id t = 2p + side  <->  flat[t]
     flat = torch.where(flat < 0, flat + n_rows, flat)
     key = flat * (2 * P) + torch.arange(2 * P, device=edges.device)
@@ -207,9 +218,11 @@ def edge_scatter_raw(h, edges, da=None, dscore=None, mode=None):
     seg_node, counts = torch.unique_consecutive(node, return_counts=True)
     seg_ptr = torch.zeros(seg_node.numel() + 1, dtype=torch.int64, device=edges.device)
     seg_ptr[1:] = torch.cumsum(counts, 0)
-    check(lib.plnlp_edge_scatter_sorted_f32(ptr(h), _ld(h), n_rows, ptr(edges), P, H, ptr(da), ldda, ptr(dscore),
-                                            ptr(seg_ptr), ptr(seg_node), seg_node.numel(), ptr(entry),
-                                            ptr(grad_h), H, stream()), "plnlp_edge_scatter_sorted_f32")
+    _sp.__exit__()
+    with profiling.span("edge_scatter_sorted_f32", P * (5 * H * 4 + 32), 0):
+        check(lib.plnlp_edge_scatter_sorted_f32(ptr(h), _ld(h), n_rows, ptr(edges), P, H, ptr(da), ldda, ptr(dscore),
+                                                ptr(seg_ptr), ptr(seg_node), seg_node.numel(), ptr(entry),
+                                                ptr(grad_h), H, stream()), "plnlp_edge_scatter_sorted_f32")
     return grad_h
 
 
@@ -228,8 +241,9 @@ def pair_loss_raw(kind, pos, neg, num_neg, weight=None):
     dneg = torch.empty(B * num_neg, dtype=torch.float32, device=pos.device)
     nbytes = lib.plnlp_pair_loss_workspace_bytes(B)
     ws = workspace.get("pair_loss", nbytes, pos.device)
-    check(lib.plnlp_pair_loss_f32(int(kind), ptr(pos), ptr(neg), ptr(weight), B, int(num_neg), ptr(loss), ptr(dpos),
-                                  ptr(dneg), ptr(ws), nbytes, stream()), "plnlp_pair_loss_f32")
+    with profiling.span("pair_loss_f32", (B + B * num_neg) * 8, 0):
+        check(lib.plnlp_pair_loss_f32(int(kind), ptr(pos), ptr(neg), ptr(weight), B, int(num_neg), ptr(loss), ptr(dpos),
+                                      ptr(dneg), ptr(ws), nbytes, stream()), "plnlp_pair_loss_f32")
     return loss, dpos, dneg
 
 

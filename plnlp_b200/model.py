@@ -124,6 +124,8 @@ class BaseModel(object):
                                     head=head, params=self.predictor.flat_params(), drop_p=p,
                                     seed=_ops.new_seed() if p > 0 else 0)
         loss.backward()
+        if getattr(self, 'world_size', 1) > 1:
+            self._allreduce_grads()
         if self.clip_norm >= 0:
             torch.nn.utils.clip_grad_norm_(self.encoder.parameters(), self.clip_norm)
             pp = list(self.predictor.parameters())
@@ -131,6 +133,19 @@ class BaseModel(object):
                 torch.nn.utils.clip_grad_norm_(pp, self.clip_norm)
         self.optimizer.step()
         return loss.detach()
+
+    def _allreduce_grads(self):
+        """data-parallel edge batches (no counterpart in the reference): every rank
+        scored its own batch against a replicated encoder; the loss is a SUM over pairs, so summing
+        the gradients over ranks gives the gradient of the global batch.  One flat NCCL all-reduce."""
+        import torch.distributed as dist
+        grads = [p.grad for p in self.para_list if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat)
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
 
     def train(self, data, split_edge, batch_size, neg_sampler_name, num_neg, perms=None, neg_edges=None,
               max_batches=None):

@@ -181,7 +181,8 @@ class _RecordingLoader:
 
 
 def golden_train(tag, *, encoder, predictor, loss, num_neg, sampler, gnn_layers, mlp_layers,
-                 emb, hid, feats, use_feats, weighted, clip, directed_sym=False, epochs=2):
+                 emb, hid, feats, use_feats, weighted, clip, directed_sym=False, epochs=2,
+                 optimizer="Adam", lr=0.01):
     torch.manual_seed(100)
     random.seed(100)
     N, B = 64, 96
@@ -211,10 +212,10 @@ def golden_train(tag, *, encoder, predictor, loss, num_neg, sampler, gnn_layers,
             split[sp] = {"edge": torch.randint(0, N, (40, 2)), "edge_neg": torch.randint(0, N, (120, 2))}
 
     model = ref_model.BaseModel(
-        lr=0.01, dropout=0.0, grad_clip_norm=clip, gnn_num_layers=gnn_layers, mlp_num_layers=mlp_layers,
+        lr=lr, dropout=0.0, grad_clip_norm=clip, gnn_num_layers=gnn_layers, mlp_num_layers=mlp_layers,
         emb_hidden_channels=emb, gnn_hidden_channels=hid, mlp_hidden_channels=hid, num_nodes=N,
         num_node_feats=feats, gnn_encoder_name=encoder, predictor_name=predictor, loss_func=loss,
-        optimizer_name="Adam", device=torch.device("cpu"), use_node_feats=use_feats, train_node_emb=True)
+        optimizer_name=optimizer, device=torch.device("cpu"), use_node_feats=use_feats, train_node_emb=True)
     model.param_init()
     init = {"encoder": sd(model.encoder), "predictor": sd(model.predictor), "emb": model.emb.weight.detach().clone()}
 
@@ -254,7 +255,7 @@ def golden_train(tag, *, encoder, predictor, loss, num_neg, sampler, gnn_layers,
     rowptr, colv, val = adj.csr()
     return {"tag": tag, "cfg": dict(encoder=encoder, predictor=predictor, loss=loss, num_neg=num_neg,
                                     sampler=sampler, gnn_layers=gnn_layers, mlp_layers=mlp_layers, emb=emb,
-                                    hid=hid, feats=feats, use_feats=use_feats, clip=clip, lr=0.01,
+                                    hid=hid, feats=feats, use_feats=use_feats, clip=clip, lr=lr, optimizer=optimizer,
                                     batch_size=B, num_nodes=N, metric=metric),
             "edge_index": data.edge_index, "adj_rowptr": rowptr, "adj_col": colv, "adj_val": val,
             "x": data.x, "split": split, "init": init, "final": final, "negs": negs, "perms": perms,
@@ -280,6 +281,14 @@ def main():
         golden_train("hinge_like", encoder="SAGE", predictor="MLP", loss="HingeAUC", num_neg=2, sampler="local",
                      gnn_layers=2, mlp_layers=3, emb=10, hid=18, feats=0, use_feats=False, weighted=False,
                      clip=-1.0),
+        # SGD (model.py:87-88): the update is linear in the gradient, so the whole trajectory is
+        # well conditioned and can be compared element by element
+        golden_train("sgd_like", encoder="SAGE", predictor="MLP", loss="AUC", num_neg=3, sampler="local",
+                     gnn_layers=2, mlp_layers=2, emb=16, hid=16, feats=0, use_feats=False, weighted=False,
+                     clip=2.0, optimizer="SGD", lr=1e-4, epochs=3),
+        golden_train("sgd_gcn_like", encoder="GCN", predictor="DOT", loss="HingeAUC", num_neg=2, sampler="local",
+                     gnn_layers=2, mlp_layers=2, emb=6, hid=20, feats=9, use_feats=True, weighted=False,
+                     clip=1.0, directed_sym=True, optimizer="SGD", lr=1e-4, epochs=3),
     ]
     torch.save({r["tag"]: r for r in runs}, os.path.join(HERE, "train_runs.pt"))
     for f in sorted(os.listdir(HERE)):

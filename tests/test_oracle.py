@@ -179,14 +179,16 @@ def test_edges_and_eval_match_reference(golden_dir):
     assert plnlp_ref.evaluate_mrr(m["pv"], m["nv"], m["pt"], m["nt"]) == m["res"]
 
 
-@pytest.mark.parametrize("tag", ["ddi_like", "collab_like", "citation_like", "hinge_like"])
+@pytest.mark.parametrize("tag", ["ddi_like", "collab_like", "citation_like", "hinge_like", "sgd_like",
+                                 "sgd_gcn_like"])
 def test_train_replay_matches_reference(golden_dir, tag):
     R = torch.load(os.path.join(golden_dir, "train_runs.pt"))[tag]
     cfg = R["cfg"]
     m = plnlp_ref.OracleModel(num_nodes=cfg["num_nodes"], emb_hidden=cfg["emb"], gnn_hidden=cfg["hid"],
                               mlp_hidden=cfg["hid"], gnn_layers=cfg["gnn_layers"], mlp_layers=cfg["mlp_layers"],
                               encoder=cfg["encoder"], predictor=cfg["predictor"], loss=cfg["loss"], lr=cfg["lr"],
-                              clip_norm=cfg["clip"], num_node_feats=cfg["feats"], use_node_feats=cfg["use_feats"])
+                              clip_norm=cfg["clip"], num_node_feats=cfg["feats"], use_node_feats=cfg["use_feats"],
+                              optimizer=cfg.get("optimizer", "Adam"))
     st = map_encoder_state(R["init"]["encoder"])
     st.update(map_predictor_state(R["init"]["predictor"]))
     st["emb"] = R["init"]["emb"]
