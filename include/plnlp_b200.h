@@ -93,6 +93,17 @@ int plnlp_gemm_f32(int transa, int transb, int64_t M, int64_t N, int64_t K,
                    const float* aux, int64_t ldaux, float drop_p, uint64_t seed,
                    float* workspace, int64_t workspace_bytes, int split_k, void* stream);
 
+/* Same contract on the 5th-generation tensor cores: tcgen05.mma kind::tf32, operands staged in
+ * shared memory, fp32 accumulator in TMEM (csrc/gemm_tcgen05.cu).
+ *   passes = 3: error-compensated 3xTF32 (A = Ah + Al, B = Bh + Bl; Ah.Bh + Ah.Bl + Al.Bh), ~1e-6
+ *               relative to the fp32 result -- the parity path;
+ *   passes = 1: plain TF32 (~1e-3 relative) -- the stated fast path. */
+int plnlp_gemm_tf32(int passes, int transa, int transb, int64_t M, int64_t N, int64_t K,
+                    const float* A, int64_t lda, const float* B, int64_t ldb,
+                    float* C, int64_t ldc, float beta, const float* bias, int act,
+                    const float* aux, int64_t ldaux, float drop_p, uint64_t seed,
+                    float* workspace, int64_t workspace_bytes, int split_k, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Edge scoring (replaces h[edge[0]], h[edge[1]] advanced indexing + MLPPredictor /
  * DotPredictor, model.py:152-156,180 and layer.py:80-87,174-176).

@@ -5,6 +5,8 @@ CUDA stream.  Nothing falls back to eager PyTorch arithmetic: CPU tensors raise.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib, profiling
@@ -17,6 +19,10 @@ LOSS_KINDS = {"AUC": 0, "HingeAUC": 1, "WeightedHingeAUC": 2}
 # which scatter kernel backs the endpoint-gather backward: "sorted" (deterministic, default)
 # or "atomic" (red.global.add, order non-deterministic)
 SCATTER_MODE = "sorted"
+
+# dense-layer backend: "tf32x3" = tcgen05 tensor cores with error-compensated 3xTF32 (fp32 parity,
+# default), "tf32" = plain TF32 tensor cores (fast path, ~1e-3 relative), "ffma" = exact fp32 CUDA cores
+GEMM_BACKEND = os.environ.get("PLNLP_GEMM", "ffma")
 
 
 def _f32c(t):
@@ -75,7 +81,7 @@ def spmm_raw(plan, x, use_val, div_rows, bias=None, relu=False, drop_p=0.0, seed
 
 
 def gemm_raw(A, B, transa=False, transb=False, C=None, beta=0.0, bias=None, act=ACT_NONE, aux=None,
-             drop_p=0.0, seed=0, split_k=None):
+             drop_p=0.0, seed=0, split_k=None, backend=None):
     """C = act(op(A) @ op(B) + beta*C + bias); A, B row-major with leading dimensions."""
     lib = _lib.load()
     A, B = _rowmajor(A), _rowmajor(B)
@@ -86,8 +92,12 @@ def gemm_raw(A, B, transa=False, transb=False, C=None, beta=0.0, bias=None, act=
     if C is None:
         C = torch.empty(M, N, dtype=torch.float32, device=A.device)
         beta = 0.0
+    backend = backend or GEMM_BACKEND
+    if backend != "ffma" and (K < 32 or M * N < 128 * 128):
+        backend = "ffma"                      # too small to fill one tensor-core tile
+    bn = 128 if backend == "ffma" or N <= 128 else 256
     if split_k is None:
-        tiles = ((M + 127) // 128) * ((N + 127) // 128)
+        tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
         split_k = 1
         if tiles < 148 and K >= 2048:
             split_k = int(min(max(1, (2 * 148) // tiles), K // 512, 64))
@@ -96,11 +106,15 @@ def gemm_raw(A, B, transa=False, transb=False, C=None, beta=0.0, bias=None, act=
     if split_k > 1:
         ws_bytes = split_k * M * N * 4
         ws = workspace.get("gemm_splitk", ws_bytes, A.device)
-    with profiling.span(f"gemm_f32 {M}x{N}x{K}{' splitk' if split_k > 1 else ''}", 0, 2 * M * N * K):
-        check(lib.plnlp_gemm_f32(int(transa), int(transb), M, N, K, ptr(A), _ld(A), ptr(B), _ld(B), ptr(C), _ld(C),
-                                 float(beta), ptr(bias), int(act), ptr(aux), _ld(aux) if aux is not None else 0,
-                                 float(drop_p), int(seed), ptr(ws), ws_bytes, int(split_k), stream()),
-              "plnlp_gemm_f32")
+    tail = (int(transa), int(transb), M, N, K, ptr(A), _ld(A), ptr(B), _ld(B), ptr(C), _ld(C),
+            float(beta), ptr(bias), int(act), ptr(aux), _ld(aux) if aux is not None else 0,
+            float(drop_p), int(seed), ptr(ws), ws_bytes, int(split_k), stream())
+    name = {"ffma": "gemm_f32", "tf32x3": "gemm_tf32x3", "tf32": "gemm_tf32"}[backend]
+    with profiling.span(f"{name} {M}x{N}x{K}{' splitk' if split_k > 1 else ''}", 0, 2 * M * N * K):
+        if backend == "ffma":
+            check(lib.plnlp_gemm_f32(*tail), "plnlp_gemm_f32")
+        else:
+            check(lib.plnlp_gemm_tf32(3 if backend == "tf32x3" else 1, *tail), "plnlp_gemm_tf32")
     return C
 
 

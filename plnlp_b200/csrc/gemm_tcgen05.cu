@@ -1,0 +1,393 @@
+// Tensor-core GEMM for sm_100a: tcgen05.mma kind::tf32, operands staged in shared memory in the
+// canonical no-swizzle core-matrix layout, fp32 accumulator in TMEM, fused epilogue.
+//
+// Replaces torch.nn.Linear -> cuBLAS sgemm at /root/reference/plnlp/layer.py:20,23,82-86 and its two
+// backward GEMMs on the tensor pipe while keeping fp32 parity:
+//
+//   passes = 3 ("3xTF32", error-compensated):  A = Ah + Al, B = Bh + Bl with Ah = rn_tf32(A),
+//            Al = A - Ah (exact in fp32);  A.B ~= Ah.Bh + Ah.Bl + Al.Bh, all accumulated in fp32 in
+//            TMEM.  The dropped Al.Bl term is 2^-22 relative: results agree with the FFMA kernel to
+//            ~1e-6 relative, inside the 1e-5 parity bar.
+//   passes = 1: plain TF32 (~1e-3 relative), the stated fast path.
+//
+// CTA = 128 x BN output tile, 9 warps: warps 0-7 load A/B tiles from global memory (any of the four
+// transpose combinations), split them into hi/lo parts and write the UMMA layout; warp 8 allocates
+// TMEM and its elected lane issues the MMAs; full/empty mbarriers form a STAGES-deep ring
+// (loaders -> MMA via fence.proxy.async + arrive, MMA -> loaders via tcgen05.commit).  After the last
+// k-slab the same 8 warps read the accumulator (tcgen05.ld 32x32b) and apply the epilogue
+// (split-k partial store, or beta*C + bias -> relu -> dropout / relu-grad mask).
+//
+// Shared-memory operand layouts (BK = 32 fp32 = 128 B of K per slab, 8-row x 16-byte core matrices):
+//   K-major  tile [R rows][32 k]: byte(r, k) = (k/4)*LBO + (r/8)*128 + (r%8)*16 + (k%4)*4,
+//            LBO = R*16 + 16 (the +16 skews successive k-chunks by one 16-byte bank group so a
+//            quarter-warp writing the 8 chunks of one row is conflict-free); SBO = 128.
+//   MN-major tile [32 k][R cols]: byte(r, k) = (k/8)*LBO + (r/4)*SBO + (k%8)*16 + (r%4)*4,
+//            SBO = 144 (128 + 16 skew), LBO = (R/4)*144.
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace plnlp {
+
+namespace {
+
+constexpr int TBM = 128;           // CTA tile rows  (UMMA M)
+constexpr int TBK = 32;            // k-slab
+constexpr int LOADERS = 256;       // threads of warps 0-7
+constexpr int NTHREADS = 288;
+
+struct TcGemmParams {
+    int64_t M, N, K;
+    const float* A; int64_t lda;
+    const float* B; int64_t ldb;
+    float* C; int64_t ldc;
+    float beta;
+    const float* bias;
+    int act;
+    const float* aux; int64_t ldaux;
+    float drop_p; uint64_t seed;
+    float* ws;
+    int split_k;
+    int64_t k_per_split;
+    int passes;                    // 1 or 3
+};
+
+__host__ __device__ constexpr int tile_bytes(int rows, bool mn_major) {
+    return mn_major ? rows * 144 : 8 * (rows * 16 + 16);
+}
+__host__ __device__ constexpr int slot_bytes(int rows) {  // either layout fits
+    return tile_bytes(rows, true) > tile_bytes(rows, false) ? tile_bytes(rows, true) : tile_bytes(rows, false);
+}
+
+// one 16-byte chunk of an operand tile -> shared memory (hi and, when SPLIT, lo parts)
+template <bool SPLIT>
+__device__ __forceinline__ void put_chunk(uint8_t* hi, uint8_t* lo, int off, const float (&v)[4]) {
+    float h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        h[e] = tc::to_tf32(v[e]);
+        l[e] = v[e] - h[e];
+    }
+    *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+    if (SPLIT) *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+}
+
+// Global -> registers for this thread's chunks of one operand slab.
+//  MN = false (K-major source: element (r, k) at src[r*ld + k]); chunk c: kq = c%8, r = c/8
+//  MN = true  (MN-major source: element (r, k) at src[k*ld + r]); chunk c: rg = c%(R/4), k = c/(R/4)
+template <int R, bool MN, bool VEC>
+__device__ __forceinline__ void fetch_tile(const float* __restrict__ src, int64_t ld, int64_t r0, int64_t rows,
+                                           int64_t k0, int64_t kend, int tid, float (&reg)[R / 32][4]) {
+#pragma unroll
+    for (int i = 0; i < R / 32; ++i) {
+        const int c = tid + LOADERS * i;
+        int64_t r, k;
+        const float* p;
+        if (!MN) {
+            r = r0 + (c >> 3);
+            k = k0 + (c & 7) * 4;
+            p = src + r * ld + k;
+            if (VEC) {
+                if (r < rows && k < kend) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+                    reg[i][0] = t.x; reg[i][1] = t.y; reg[i][2] = t.z; reg[i][3] = t.w;
+                } else {
+                    reg[i][0] = reg[i][1] = reg[i][2] = reg[i][3] = 0.0f;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) reg[i][e] = (r < rows && k + e < kend) ? __ldg(p + e) : 0.0f;
+            }
+        } else {
+            r = r0 + (c % (R / 4)) * 4;
+            k = k0 + c / (R / 4);
+            p = src + k * ld + r;
+            if (VEC) {
+                if (k < kend && r < rows) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+                    reg[i][0] = t.x; reg[i][1] = t.y; reg[i][2] = t.z; reg[i][3] = t.w;
+                } else {
+                    reg[i][0] = reg[i][1] = reg[i][2] = reg[i][3] = 0.0f;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) reg[i][e] = (k < kend && r + e < rows) ? __ldg(p + e) : 0.0f;
+            }
+        }
+    }
+}
+
+template <int R, bool MN, bool SPLIT>
+__device__ __forceinline__ void stash_tile(uint8_t* hi, uint8_t* lo, int tid, const float (&reg)[R / 32][4]) {
+#pragma unroll
+    for (int i = 0; i < R / 32; ++i) {
+        const int c = tid + LOADERS * i;
+        int off;
+        if (!MN) {
+            const int kq = c & 7, r = c >> 3;
+            off = kq * (R * 16 + 16) + (r >> 3) * 128 + (r & 7) * 16;
+        } else {
+            const int rg = c % (R / 4), k = c / (R / 4);
+            off = (k >> 3) * ((R / 4) * 144) + rg * 144 + (k & 7) * 16;
+        }
+        put_chunk<SPLIT>(hi, lo, off, reg[i]);
+    }
+}
+
+__device__ __forceinline__ float tc_epilogue_one(const TcGemmParams& p, int64_t r, int64_t c, float v) {
+    if (p.beta != 0.0f) v += p.beta * p.C[r * p.ldc + c];
+    if (p.bias) v += __ldg(p.bias + c);
+    if (p.act == PLNLP_ACT_RELU) {
+        v = fmaxf(v, 0.0f);
+        if (p.drop_p > 0.0f)
+            v = dropout_keep(p.seed, static_cast<uint64_t>(r) * p.N + c, p.drop_p) ? v / (1.0f - p.drop_p) : 0.0f;
+    } else if (p.act == PLNLP_ACT_RELU_GRAD) {
+        v = (__ldg(p.aux + r * p.ldaux + c) > 0.0f) ? v / (1.0f - p.drop_p) : 0.0f;
+    }
+    return v;
+}
+
+// BN: CTA tile columns (UMMA N, TMEM columns); AMN/BMN: operand is MN-major in global memory
+// (A: transa = 1, B: transb = 0); VA/VB: 16-byte global loads legal; SPLIT: 3xTF32.
+template <int BN, bool AMN, bool BMN, bool VA, bool VB, bool SPLIT>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tcgen05_kernel(const TcGemmParams p) {
+    constexpr int STAGES = SPLIT ? 2 : 4;
+    constexpr int A_SLOT = slot_bytes(TBM), B_SLOT = slot_bytes(BN);
+    constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_SLOT + B_SLOT);
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+    __shared__ uint32_t tmem_holder;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t m0 = static_cast<int64_t>(blockIdx.y) * TBM, n0 = static_cast<int64_t>(blockIdx.x) * BN;
+    const int64_t kbeg = static_cast<int64_t>(blockIdx.z) * p.k_per_split;
+    const int64_t kend = min(p.K, kbeg + p.k_per_split);
+    const int n_iter = static_cast<int>((kend - kbeg + TBK - 1) / TBK);
+    // columns actually multiplied: N remainder rounded up to the UMMA granularity (16)
+    const int64_t n_rem = ((p.N - n0 + 15) / 16) * 16;
+    const int n_mma = n_rem < BN ? static_cast<int>(n_rem) : BN;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(&full_bar[s], LOADERS);
+            tc::mbar_init(&empty_bar[s], 1);
+        }
+        tc::mbar_init(&accum_bar, 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 8) tc::tmem_alloc<BN>(&tmem_holder);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_d = tmem_holder;
+
+    auto stage_ptr = [&](int s, int which) -> uint8_t* {  // which: 0 A.hi, 1 B.hi, 2 A.lo, 3 B.lo
+        uint8_t* base = smem + s * STAGE_BYTES;
+        return base + (which & 1 ? A_SLOT : 0) + (which & 2 ? (A_SLOT + B_SLOT) : 0);
+    };
+
+    if (warp < 8) {
+        // ============================ loaders ============================
+        float ra[TBM / 32][4], rb[BN / 32][4];
+        if (n_iter > 0) {
+            fetch_tile<TBM, AMN, VA>(p.A, p.lda, m0, p.M, kbeg, kend, tid, ra);
+            fetch_tile<BN, BMN, VB>(p.B, p.ldb, n0, p.N, kbeg, kend, tid, rb);
+        }
+        for (int it = 0; it < n_iter; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            tc::mbar_wait(&empty_bar[s], ph ^ 1);         // slot free (first round passes immediately)
+            stash_tile<TBM, AMN, SPLIT>(stage_ptr(s, 0), stage_ptr(s, 2), tid, ra);
+            stash_tile<BN, BMN, SPLIT>(stage_ptr(s, 1), stage_ptr(s, 3), tid, rb);
+            if (it + 1 < n_iter) {                        // next slab's global loads fly during the MMAs
+                const int64_t k0 = kbeg + static_cast<int64_t>(it + 1) * TBK;
+                fetch_tile<TBM, AMN, VA>(p.A, p.lda, m0, p.M, k0, kend, tid, ra);
+                fetch_tile<BN, BMN, VB>(p.B, p.ldb, n0, p.N, k0, kend, tid, rb);
+            }
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(&full_bar[s]);
+        }
+    } else {
+        // ============================ MMA issuer ============================
+        const uint32_t idesc = tc::make_idesc_tf32(TBM, n_mma, AMN ? 1 : 0, BMN ? 1 : 0);
+        constexpr uint32_t A_LBO = AMN ? (TBM / 4) * 144 : (TBM * 16 + 16), A_SBO = AMN ? 144 : 128;
+        constexpr uint32_t B_LBO = BMN ? (BN / 4) * 144 : (BN * 16 + 16), B_SBO = BMN ? 144 : 128;
+        // one UMMA consumes K = 8 (32 bytes): K-major -> two 16-byte k-chunks (2*LBO apart per step);
+        // MN-major -> one group of 8 k rows (LBO apart per step)
+        constexpr uint32_t A_STEP = AMN ? A_LBO : 2 * A_LBO, B_STEP = BMN ? B_LBO : 2 * B_LBO;
+        for (int it = 0; it < n_iter; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            tc::mbar_wait(&full_bar[s], ph);
+            tc::fence_after_sync();
+            if (lane == 0) {
+                const uint32_t a_hi = tc::smem_u32(stage_ptr(s, 0)), b_hi = tc::smem_u32(stage_ptr(s, 1));
+                const uint32_t a_lo = tc::smem_u32(stage_ptr(s, 2)), b_lo = tc::smem_u32(stage_ptr(s, 3));
+#pragma unroll
+                for (int j = 0; j < TBK / 8; ++j) {
+                    const uint64_t dah = tc::make_smem_desc(a_hi + j * A_STEP, A_LBO, A_SBO);
+                    const uint64_t dbh = tc::make_smem_desc(b_hi + j * B_STEP, B_LBO, B_SBO);
+                    tc::mma_tf32_ss(tmem_d, dah, dbh, idesc, (it | j) != 0);
+                    if (SPLIT) {
+                        const uint64_t dal = tc::make_smem_desc(a_lo + j * A_STEP, A_LBO, A_SBO);
+                        const uint64_t dbl = tc::make_smem_desc(b_lo + j * B_STEP, B_LBO, B_SBO);
+                        tc::mma_tf32_ss(tmem_d, dah, dbl, idesc, 1u);
+                        tc::mma_tf32_ss(tmem_d, dal, dbh, idesc, 1u);
+                    }
+                }
+                tc::mma_commit(&empty_bar[s]);                       // frees the slot when these finish
+                if (it == n_iter - 1) tc::mma_commit(&accum_bar);    // accumulator complete
+            }
+            __syncwarp();
+        }
+    }
+
+    // ============================ epilogue (warps 0-7) ============================
+    if (warp < 8) {
+        if (n_iter > 0) {
+            tc::mbar_wait(&accum_bar, 0);
+            tc::fence_after_sync();
+        }
+        const int q = warp & 3, half = warp >> 2;
+        const int64_t r = m0 + q * 32 + lane;
+        const bool split = p.split_k > 1;
+        float* wsz = split ? p.ws + static_cast<int64_t>(blockIdx.z) * p.M * p.N : nullptr;
+        for (int cb = half * (BN / 2); cb < (half + 1) * (BN / 2); cb += 32) {
+            if (cb >= n_mma) break;                                   // warp-uniform
+            float v[32];
+            if (n_iter > 0) {
+                tc::tmem_ld_32x32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(cb), v);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = 0.0f;
+            }
+            if (r < p.M) {
+                const int64_t c0 = n0 + cb;
+                if (split) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (c0 + e < p.N) wsz[r * p.N + c0 + e] = v[e];
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (c0 + e < p.N) v[e] = tc_epilogue_one(p, r, c0 + e, v[e]);
+                    float* dst = p.C + r * p.ldc + c0;
+                    if ((p.ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(p.C) % 16 == 0) && c0 + 31 < p.N) {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4)
+                            *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            if (c0 + e < p.N) dst[e] = v[e];
+                    }
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tc::tmem_dealloc<BN>(tmem_d);
+}
+
+__global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const TcGemmParams p) {
+    const int64_t total = p.M * p.N;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float v = 0.0f;
+        for (int z = 0; z < p.split_k; ++z) v += p.ws[static_cast<int64_t>(z) * total + i];
+        const int64_t r = i / p.N, c = i % p.N;
+        p.C[r * p.ldc + c] = tc_epilogue_one(p, r, c, v);
+    }
+}
+
+template <int BN, bool AMN, bool BMN, bool VA, bool VB, bool SPLIT>
+int launch_one(const TcGemmParams& p, dim3 grid, cudaStream_t st) {
+    constexpr int STAGES = SPLIT ? 2 : 4;
+    constexpr int bytes = STAGES * (SPLIT ? 2 : 1) * (slot_bytes(TBM) + slot_bytes(BN));
+    auto kern = gemm_tcgen05_kernel<BN, AMN, BMN, VA, VB, SPLIT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        configured = true;
+    }
+    kern<<<grid, NTHREADS, bytes, st>>>(p);
+    return 0;
+}
+
+template <int BN, bool AMN, bool BMN>
+int launch_vec(const TcGemmParams& p, bool va, bool vb, dim3 grid, cudaStream_t st) {
+    // the unaligned (scalar-load) path is only instantiated for the exact 3-pass variant to bound
+    // compile time; plain-TF32 requests with unaligned operands use it too
+    const bool split = p.passes == 3;
+    if (va && vb) {
+        return split ? launch_one<BN, AMN, BMN, true, true, true>(p, grid, st)
+                     : launch_one<BN, AMN, BMN, true, true, false>(p, grid, st);
+    }
+    if (va) return launch_one<BN, AMN, BMN, true, false, true>(p, grid, st);
+    if (vb) return launch_one<BN, AMN, BMN, false, true, true>(p, grid, st);
+    return launch_one<BN, AMN, BMN, false, false, true>(p, grid, st);
+}
+
+template <int BN>
+int launch_major(const TcGemmParams& p, bool amn, bool bmn, bool va, bool vb, dim3 grid, cudaStream_t st) {
+    if (!amn && !bmn) return launch_vec<BN, false, false>(p, va, vb, grid, st);
+    if (!amn && bmn) return launch_vec<BN, false, true>(p, va, vb, grid, st);
+    if (amn && !bmn) return launch_vec<BN, true, false>(p, va, vb, grid, st);
+    return launch_vec<BN, true, true>(p, va, vb, grid, st);
+}
+
+}  // namespace
+}  // namespace plnlp
+
+extern "C" int plnlp_gemm_tf32(int passes, int transa, int transb, int64_t M, int64_t N, int64_t K, const float* A,
+                               int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, float beta,
+                               const float* bias, int act, const float* aux, int64_t ldaux, float drop_p,
+                               uint64_t seed, float* workspace, int64_t workspace_bytes, int split_k,
+                               void* stream) {
+    using namespace plnlp;
+    PLNLP_REQUIRE(passes == 1 || passes == 3, PLNLP_E_UNSUPPORTED);
+    PLNLP_REQUIRE(M >= 0 && N >= 0 && K >= 0, PLNLP_E_SIZE);
+    if (M == 0 || N == 0) return 0;
+    PLNLP_REQUIRE(A && B && C, PLNLP_E_NULL);
+    PLNLP_REQUIRE(lda >= (transa ? M : K) && ldb >= (transb ? K : N) && ldc >= N, PLNLP_E_SIZE);
+    PLNLP_REQUIRE(act >= 0 && act <= 2 && drop_p >= 0.0f && drop_p < 1.0f, PLNLP_E_SIZE);
+    if (act == PLNLP_ACT_RELU_GRAD) PLNLP_REQUIRE(aux && ldaux >= N, PLNLP_E_NULL);
+    if (split_k < 1 || K == 0) split_k = 1;
+    TcGemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
+    p.beta = beta; p.bias = bias; p.act = act; p.aux = aux; p.ldaux = ldaux; p.drop_p = drop_p; p.seed = seed;
+    p.passes = passes;
+    int64_t kper = ceil_div(ceil_div(K, split_k), TBK) * TBK;
+    if (kper == 0) kper = TBK;
+    p.k_per_split = kper;
+    p.split_k = split_k = static_cast<int>(K == 0 ? 1 : ceil_div(K, kper));
+    p.ws = workspace;
+    if (split_k > 1) {
+        PLNLP_REQUIRE(workspace, PLNLP_E_NULL);
+        PLNLP_REQUIRE(workspace_bytes >= static_cast<int64_t>(split_k) * M * N * 4, PLNLP_E_WORKSPACE);
+    }
+    const bool amn = transa != 0, bmn = transb == 0;
+    const bool va = aligned(A, 16) && (lda % 4 == 0) && ((transa ? M : K) % 4 == 0);
+    const bool vb = aligned(B, 16) && (ldb % 4 == 0) && ((transb ? K : N) % 4 == 0);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    if (N > 128) {
+        const dim3 grid(static_cast<unsigned>(ceil_div(N, 256)), static_cast<unsigned>(ceil_div(M, TBM)),
+                        static_cast<unsigned>(split_k));
+        rc = launch_major<256>(p, amn, bmn, va, vb, grid, st);
+    } else {
+        const dim3 grid(static_cast<unsigned>(ceil_div(N, 128)), static_cast<unsigned>(ceil_div(M, TBM)),
+                        static_cast<unsigned>(split_k));
+        rc = launch_major<128>(p, amn, bmn, va, vb, grid, st);
+    }
+    if (rc != 0) return rc;
+    PLNLP_LAUNCH_CHECK();
+    if (split_k > 1) {
+        const int64_t total = M * N;
+        const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div(total, 256), 148 * 8));
+        tc_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p);
+        PLNLP_LAUNCH_CHECK();
+    }
+    return 0;
+}

@@ -369,3 +369,47 @@ def test_eval_glue_against_reference_golden(ops, golden_dir):
     c = G["citation_style"]
     pos, neg = get_pos_neg_edges("valid", c["split"], device=torch.device("cuda"))
     assert torch.equal(pos.cpu(), c["pos"]) and torch.equal(neg.cpu(), c["neg"])
+
+
+# ------------------------------------------------------------------ tensor-core GEMM (tcgen05)
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 256, 64), (256, 512, 512), (4267, 512, 512),
+                                   (300, 200, 178), (129, 257, 50), (512, 512, 4100), (1000, 72, 96)])
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])
+def test_gemm_tf32x3_layouts(ops, M, N, K, ta, tb):
+    """3xTF32 on tcgen05 must sit inside the fp32 parity bar for every operand layout"""
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    A = torch.randn((K, M) if ta else (M, K), generator=g)
+    B = torch.randn((N, K) if tb else (K, N), generator=g)
+    got = ops.gemm_raw(A.cuda(), B.cuda(), transa=ta, transb=tb, backend="tf32x3").cpu()
+    want = ((A.t() if ta else A).double() @ (B.t() if tb else B).double())
+    assert rel_err(got, want) < TOL, rel_err(got, want)
+
+
+def test_gemm_tf32_plain_and_epilogues(ops):
+    g = torch.Generator().manual_seed(4)
+    A, W = torch.randn(1000, 512, generator=g), torch.randn(384, 512, generator=g)
+    bias, C0 = torch.randn(384, generator=g), torch.randn(1000, 384, generator=g)
+    want = A.double() @ W.double().t()
+    fast = ops.gemm_raw(A.cuda(), W.cuda(), transb=True, backend="tf32").cpu()
+    assert 1e-5 < rel_err(fast, want) < 5e-3                   # really TF32, stated separately
+    # bias + beta + relu epilogue, and the relu-grad epilogue
+    C = C0.clone().cuda()
+    ops.gemm_raw(A.cuda(), W.cuda(), transb=True, C=C, beta=1.0, bias=bias.cuda(), act=ops.ACT_RELU,
+                 backend="tf32x3")
+    ref = torch.relu(want + C0.double() + bias.double())
+    assert rel_err(C.cpu(), ref) < TOL
+    aux = torch.randn(1000, 384, generator=g)
+    G = ops.gemm_raw(A.cuda(), W.cuda(), transb=True, act=ops.ACT_RELU_GRAD, aux=aux.cuda(), backend="tf32x3")
+    assert rel_err(G.cpu(), want * (aux > 0)) < TOL
+    # dropout epilogue uses the same Philox stream as the FFMA kernel
+    d1 = ops.gemm_raw(A.cuda(), W.cuda(), transb=True, act=ops.ACT_RELU, drop_p=0.3, seed=99, backend="tf32x3")
+    d2 = ops.gemm_raw(A.cuda(), W.cuda(), transb=True, act=ops.ACT_RELU, drop_p=0.3, seed=99, backend="ffma")
+    assert torch.equal(d1 == 0, d2 == 0) and rel_err(d1, d2) < TOL
+
+
+def test_gemm_tf32x3_splitk(ops):
+    g = torch.Generator().manual_seed(5)
+    A, B = torch.randn(30000, 512, generator=g), torch.randn(30000, 512, generator=g)
+    outs = [ops.gemm_raw(A.cuda(), B.cuda(), transa=True, split_k=9, backend="tf32x3").cpu() for _ in range(2)]
+    assert torch.equal(outs[0], outs[1])
+    assert rel_err(outs[0], A.double().t() @ B.double()) < TOL

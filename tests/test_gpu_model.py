@@ -161,15 +161,20 @@ def _check_update(name, got, init, final, lr, steps, adam):
     scale = max(float(d_ref.abs().max()), 1e-30)
     err = (d_got - d_ref).abs()
     if not adam:
-        assert float(err.max()) <= 2e-4 * scale, f"{name}: update err {float(err.max()):.3e} vs scale {scale:.3e}"
+        # 1e-7 absolute floor: parameters whose exact update is 0 (bias under sum(dscore) == 0)
+        assert float(err.max()) <= 2e-4 * scale + 1e-7, \
+            f"{name}: update err {float(err.max()):.3e} vs scale {scale:.3e}"
         return
-    # Adam divides by sqrt(v): an element whose gradient is pure rounding noise (e.g. biases under an
-    # AUC-family loss, where sum(d loss/d score) == 0 exactly) moves by +-lr per step in an arbitrary
-    # direction IN THE REFERENCE TOO.  Require the bulk of every tensor to follow the reference and bound
-    # every element by the largest drift Adam can produce.
+    # Adam divides by sqrt(v): an element whose gradient is pure rounding noise moves by +-lr per step
+    # in an arbitrary direction IN THE REFERENCE TOO.  The predictor biases are exactly that under an
+    # AUC-family loss (sum(d loss/d score) == 0, so d loss/d bias is a sum that cancels to rounding
+    # noise): for them only the largest drift Adam can produce is bounded.  Every other tensor must
+    # follow the reference in bulk as well.
+    assert float(err.max()) <= 2.0 * lr * steps + 1e-6, f"{name}: drift {float(err.max()):.3e}"
+    if name.startswith("lins.") and name.endswith(".bias"):
+        return
     frac_ok = float((err <= 2e-3 * scale).double().mean())
     assert frac_ok >= 0.8, f"{name}: only {frac_ok:.2f} of the elements follow the reference update"
-    assert float(err.max()) <= 2.0 * lr * steps + 1e-6, f"{name}: drift {float(err.max()):.3e}"
 
 
 @pytest.mark.parametrize("tag", ["ddi_like", "collab_like", "citation_like", "hinge_like", "sgd_like",

@@ -77,7 +77,7 @@ def bench_gemm(M, N, K, ta=False, tb=True, **kw):
     B = torch.randn((N, K) if tb else (K, N), device=DEV)
     ms = timeit(lambda: _ops.gemm_raw(A, B, transa=ta, transb=tb, **kw))
     fl = 2.0 * M * N * K
-    print(f"[gemm] M={M} N={N} K={K} ta={int(ta)} tb={int(tb)}: {ms:.3f} ms -> {fl/ms/1e9:.1f} TFLOP/s", flush=True)
+    print(f"[gemm {kw.get('backend', 'ffma')}] M={M} N={N} K={K} ta={int(ta)} tb={int(tb)}: {ms:.3f} ms -> {fl/ms/1e9:.1f} TFLOP/s", flush=True)
     return ms
 
 
@@ -88,10 +88,11 @@ def ddi():
     bench_spmm("ddi", adj, H, "mean", None)
     bench_spmm("ddi(L2 flushed)", adj, H, "mean", flush)
     P = B * (1 + k)
-    bench_gemm(N, H, H)
-    bench_gemm(P, H, H)                       # predictor layer 1 fwd
-    bench_gemm(P, H, H, tb=False)             # dA0 = dZ1 @ W1
-    bench_gemm(H, H, P, ta=True, tb=False)    # dW1 = dZ1^T @ A0 (split-k)
+    for be in (["ffma"] if "noffma" not in sys.argv else []) + ["tf32x3", "tf32"]:
+        bench_gemm(N, H, H, backend=be)
+        bench_gemm(P, H, H, backend=be)                       # predictor layer 1 fwd
+        bench_gemm(P, H, H, tb=False, backend=be)             # dA0 = dZ1 @ W1
+        bench_gemm(H, H, P, ta=True, tb=False, backend=be)    # dW1 = dZ1^T @ A0 (split-k)
     h = torch.randn(N, H, device=DEV)
     edges = torch.randint(0, N, (P, 2), device=DEV)
     ms = timeit(lambda: _ops.gather_hadamard_raw(h, edges))
