@@ -17,12 +17,17 @@
 // k-slab the same 8 warps read the accumulator (tcgen05.ld 32x32b) and apply the epilogue
 // (split-k partial store, or beta*C + bias -> relu -> dropout / relu-grad mask).
 //
-// Shared-memory operand layouts (BK = 32 fp32 = 128 B of K per slab, 8-row x 16-byte core matrices):
-//   K-major  tile [R rows][32 k]: byte(r, k) = (k/4)*LBO + (r/8)*128 + (r%8)*16 + (k%4)*4,
-//            LBO = R*16 + 16 (the +16 skews successive k-chunks by one 16-byte bank group so a
-//            quarter-warp writing the 8 chunks of one row is conflict-free); SBO = 128.
-//   MN-major tile [32 k][R cols]: byte(r, k) = (k/8)*LBO + (r/4)*SBO + (k%8)*16 + (r%4)*4,
-//            SBO = 144 (128 + 16 skew), LBO = (R/4)*144.
+// Shared-memory operand layout: BOTH operands are staged K-major, whatever their layout in global
+// memory (MN-major tf32 operands need the special 128B_BASE32B swizzle on this hardware; transposing in
+// the loader keeps one well-understood layout).  Tile [R rows][32 k] (BK = 32 fp32 = 128 B of K per
+// slab), made of 8-row x 16-byte core matrices:
+//     byte(r, k) = (k/4)*LBO + (r/8)*SBO + (r%8)*16 + (k%4)*4,   SBO = 144, LBO = 18*R + 16
+//   SBO = 128 + 16 and LBO = odd multiple of 16 skew successive row-groups / k-chunks by one 16-byte bank
+//   group, so both store patterns below are bank-conflict free:
+//     K-contiguous source : a quarter-warp writes the 8 k-chunks of one row      (16-byte stores)
+//     MN-contiguous source: a thread loads a 4(k) x 4(mn) block with four 16-byte loads, transposes it
+//                           in registers and writes four 16-byte chunks (rows r..r+3 of one k-chunk);
+//                           a quarter-warp covers 8 consecutive 4-row groups.
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -51,12 +56,9 @@ struct TcGemmParams {
     int passes;                    // 1 or 3
 };
 
-__host__ __device__ constexpr int tile_bytes(int rows, bool mn_major) {
-    return mn_major ? rows * 144 : 8 * (rows * 16 + 16);
-}
-__host__ __device__ constexpr int slot_bytes(int rows) {  // either layout fits
-    return tile_bytes(rows, true) > tile_bytes(rows, false) ? tile_bytes(rows, true) : tile_bytes(rows, false);
-}
+__host__ __device__ constexpr int tile_lbo(int rows) { return 18 * rows + 16; }
+constexpr int TILE_SBO = 144;
+__host__ __device__ constexpr int slot_bytes(int rows) { return 8 * tile_lbo(rows); }
 
 // one 16-byte chunk of an operand tile -> shared memory (hi and, when SPLIT, lo parts)
 template <bool SPLIT>
@@ -71,21 +73,21 @@ __device__ __forceinline__ void put_chunk(uint8_t* hi, uint8_t* lo, int off, con
     if (SPLIT) *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
 }
 
-// Global -> registers for this thread's chunks of one operand slab.
-//  MN = false (K-major source: element (r, k) at src[r*ld + k]); chunk c: kq = c%8, r = c/8
-//  MN = true  (MN-major source: element (r, k) at src[k*ld + r]); chunk c: rg = c%(R/4), k = c/(R/4)
+// Global -> registers for this thread's share of one operand slab (R rows x 32 k).
+//  MN = false (K-contiguous source, element (r, k) at src[r*ld + k]):
+//       chunk c = tid + 256*i: kq = c%8, r = c/8; reg[i] = 4 consecutive k of row r
+//  MN = true  (MN-contiguous source, element (r, k) at src[k*ld + r]):
+//       block b = tid + 256*i: rg = b%(R/4), kq = b/(R/4); reg[4*i + j] = rows rg*4..+3 at k = kq*4 + j
 template <int R, bool MN, bool VEC>
 __device__ __forceinline__ void fetch_tile(const float* __restrict__ src, int64_t ld, int64_t r0, int64_t rows,
                                            int64_t k0, int64_t kend, int tid, float (&reg)[R / 32][4]) {
+    if (!MN) {
 #pragma unroll
-    for (int i = 0; i < R / 32; ++i) {
-        const int c = tid + LOADERS * i;
-        int64_t r, k;
-        const float* p;
-        if (!MN) {
-            r = r0 + (c >> 3);
-            k = k0 + (c & 7) * 4;
-            p = src + r * ld + k;
+        for (int i = 0; i < R / 32; ++i) {
+            const int c = tid + LOADERS * i;
+            const int64_t r = r0 + (c >> 3);
+            const int64_t k = k0 + (c & 7) * 4;
+            const float* p = src + r * ld + k;
             if (VEC) {
                 if (r < rows && k < kend) {
                     const float4 t = __ldg(reinterpret_cast<const float4*>(p));
@@ -97,20 +99,29 @@ __device__ __forceinline__ void fetch_tile(const float* __restrict__ src, int64_
 #pragma unroll
                 for (int e = 0; e < 4; ++e) reg[i][e] = (r < rows && k + e < kend) ? __ldg(p + e) : 0.0f;
             }
-        } else {
-            r = r0 + (c % (R / 4)) * 4;
-            k = k0 + c / (R / 4);
-            p = src + k * ld + r;
-            if (VEC) {
-                if (k < kend && r < rows) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
-                    reg[i][0] = t.x; reg[i][1] = t.y; reg[i][2] = t.z; reg[i][3] = t.w;
-                } else {
-                    reg[i][0] = reg[i][1] = reg[i][2] = reg[i][3] = 0.0f;
-                }
-            } else {
+        }
+    } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) reg[i][e] = (k < kend && r + e < rows) ? __ldg(p + e) : 0.0f;
+        for (int i = 0; i < R / 128; ++i) {
+            const int b = tid + LOADERS * i;
+            const int64_t r = r0 + (b % (R / 4)) * 4;
+            const int64_t kb = k0 + (b / (R / 4)) * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t k = kb + j;
+                const float* p = src + k * ld + r;
+                float (&d)[4] = reg[4 * i + j];
+                if (VEC) {
+                    if (k < kend && r < rows) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+                        d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+                    } else {
+                        d[0] = d[1] = d[2] = d[3] = 0.0f;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) d[e] = (k < kend && r + e < rows) ? __ldg(p + e) : 0.0f;
+                }
             }
         }
     }
@@ -118,18 +129,25 @@ __device__ __forceinline__ void fetch_tile(const float* __restrict__ src, int64_
 
 template <int R, bool MN, bool SPLIT>
 __device__ __forceinline__ void stash_tile(uint8_t* hi, uint8_t* lo, int tid, const float (&reg)[R / 32][4]) {
+    if (!MN) {
 #pragma unroll
-    for (int i = 0; i < R / 32; ++i) {
-        const int c = tid + LOADERS * i;
-        int off;
-        if (!MN) {
+        for (int i = 0; i < R / 32; ++i) {
+            const int c = tid + LOADERS * i;
             const int kq = c & 7, r = c >> 3;
-            off = kq * (R * 16 + 16) + (r >> 3) * 128 + (r & 7) * 16;
-        } else {
-            const int rg = c % (R / 4), k = c / (R / 4);
-            off = (k >> 3) * ((R / 4) * 144) + rg * 144 + (k & 7) * 16;
+            put_chunk<SPLIT>(hi, lo, kq * tile_lbo(R) + (r >> 3) * TILE_SBO + (r & 7) * 16, reg[i]);
         }
-        put_chunk<SPLIT>(hi, lo, off, reg[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < R / 128; ++i) {
+            const int b = tid + LOADERS * i;
+            const int rg = b % (R / 4), kq = b / (R / 4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {          // row r = rg*4 + e gets (k%4 = 0..3) from the 4 loads
+                const int r = rg * 4 + e;
+                const float v[4] = {reg[4 * i + 0][e], reg[4 * i + 1][e], reg[4 * i + 2][e], reg[4 * i + 3][e]};
+                put_chunk<SPLIT>(hi, lo, kq * tile_lbo(R) + (r >> 3) * TILE_SBO + (r & 7) * 16, v);
+            }
+        }
     }
 }
 
@@ -208,12 +226,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tcgen05_kernel(const TcGemmP
         }
     } else {
         // ============================ MMA issuer ============================
-        const uint32_t idesc = tc::make_idesc_tf32(TBM, n_mma, AMN ? 1 : 0, BMN ? 1 : 0);
-        constexpr uint32_t A_LBO = AMN ? (TBM / 4) * 144 : (TBM * 16 + 16), A_SBO = AMN ? 144 : 128;
-        constexpr uint32_t B_LBO = BMN ? (BN / 4) * 144 : (BN * 16 + 16), B_SBO = BMN ? 144 : 128;
-        // one UMMA consumes K = 8 (32 bytes): K-major -> two 16-byte k-chunks (2*LBO apart per step);
-        // MN-major -> one group of 8 k rows (LBO apart per step)
-        constexpr uint32_t A_STEP = AMN ? A_LBO : 2 * A_LBO, B_STEP = BMN ? B_LBO : 2 * B_LBO;
+        const uint32_t idesc = tc::make_idesc_tf32(TBM, n_mma, 0, 0);      // both operands K-major in smem
+        constexpr uint32_t A_LBO = tile_lbo(TBM), B_LBO = tile_lbo(BN), A_SBO = TILE_SBO, B_SBO = TILE_SBO;
+        // one UMMA consumes K = 8 (32 bytes) = two 16-byte k-chunks, i.e. 2*LBO per step
+        constexpr uint32_t A_STEP = 2 * A_LBO, B_STEP = 2 * B_LBO;
         for (int it = 0; it < n_iter; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
@@ -304,6 +320,7 @@ template <int BN, bool AMN, bool BMN, bool VA, bool VB, bool SPLIT>
 int launch_one(const TcGemmParams& p, dim3 grid, cudaStream_t st) {
     constexpr int STAGES = SPLIT ? 2 : 4;
     constexpr int bytes = STAGES * (SPLIT ? 2 : 1) * (slot_bytes(TBM) + slot_bytes(BN));
+    static_assert(bytes <= 227 * 1024, "shared memory budget");
     auto kern = gemm_tcgen05_kernel<BN, AMN, BMN, VA, VB, SPLIT>;
     static bool configured = false;
     if (!configured) {
