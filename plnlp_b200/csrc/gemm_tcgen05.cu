@@ -6,25 +6,30 @@
 //
 //   passes = 3 ("3xTF32", error-compensated):  A = Ah + Al, B = Bh + Bl with Ah = rn_tf32(A),
 //            Al = A - Ah (exact in fp32);  A.B ~= Ah.Bh + Ah.Bl + Al.Bh, all accumulated in fp32 in
-//            TMEM.  The dropped Al.Bl term is 2^-22 relative: results agree with the FFMA kernel to
-//            ~1e-6 relative, inside the 1e-5 parity bar.
+//            TMEM.  The dropped Al.Bl term is 2^-22 relative.  The tensor core accumulates with
+//            round-toward-zero, so the error grows linearly with the number of accumulation steps
+//            (K/8): callers keep K per accumulator <= 1024 (split-k, partials reduced with RN adds on
+//            the CUDA cores) which keeps the result within ~4e-6 relative -- inside the 1e-5 bar.
 //   passes = 1: plain TF32 (~1e-3 relative), the stated fast path.
 //
-// CTA = 128 x BN output tile, 9 warps: warps 0-7 load A/B tiles from global memory (any of the four
+// CTA = 128 x BN output tile, 9 warps: warps 0-7 load A/B slabs from global memory (any of the four
 // transpose combinations), split them into hi/lo parts and write the UMMA layout; warp 8 allocates
 // TMEM and its elected lane issues the MMAs; full/empty mbarriers form a STAGES-deep ring
-// (loaders -> MMA via fence.proxy.async + arrive, MMA -> loaders via tcgen05.commit).  After the last
-// k-slab the same 8 warps read the accumulator (tcgen05.ld 32x32b) and apply the epilogue
-// (split-k partial store, or beta*C + bias -> relu -> dropout / relu-grad mask).
+// (loaders -> MMA via fence.proxy.async + arrive, MMA -> loaders via tcgen05.commit).  Global loads
+// run two slabs ahead of the shared-memory stores (two register buffers).  The shared-memory footprint
+// is held to ~165 KB on purpose: the global loads travel through L1, and with a full 227 KB carve-out
+// the ~7 KB of L1 left throttles the loads in flight (measured: 4x slower).  After the last k-slab the
+// same 8 warps read the accumulator (tcgen05.ld 32x32b) and apply the epilogue (split-k partial store,
+// or beta*C + bias -> relu -> dropout / relu-grad mask).
 //
 // Shared-memory operand layout: BOTH operands are staged K-major, whatever their layout in global
 // memory (MN-major tf32 operands need the special 128B_BASE32B swizzle on this hardware; transposing in
-// the loader keeps one well-understood layout).  Tile [R rows][32 k] (BK = 32 fp32 = 128 B of K per
-// slab), made of 8-row x 16-byte core matrices:
-//     byte(r, k) = (k/4)*LBO + (r/8)*SBO + (r%8)*16 + (k%4)*4,   SBO = 144, LBO = 18*R + 16
-//   SBO = 128 + 16 and LBO = odd multiple of 16 skew successive row-groups / k-chunks by one 16-byte bank
-//   group, so both store patterns below are bank-conflict free:
-//     K-contiguous source : a quarter-warp writes the 8 k-chunks of one row      (16-byte stores)
+// the loader keeps one well-understood layout).  Slab tile [R rows][16 k] (64 B of K per row), made of
+// 8-row x 16-byte core matrices:
+//     byte(r, k) = (k/4)*LBO + (r/8)*SBO + (r%8)*16 + (k%4)*4,   SBO = 144, LBO = 18*R + 32
+//   SBO = 128 + 16 and LBO = 2 (mod 8) x 16 bytes skew successive row-groups / k-chunks by one / two 16-byte bank
+//   groups, so both store patterns below are bank-conflict free:
+//     K-contiguous source : a quarter-warp writes the k-chunks of two rows           (16-byte stores)
 //     MN-contiguous source: a thread loads a 4(k) x 4(mn) block with four 16-byte loads, transposes it
 //                           in registers and writes four 16-byte chunks (rows r..r+3 of one k-chunk);
 //                           a quarter-warp covers 8 consecutive 4-row groups.
@@ -36,7 +41,8 @@ namespace plnlp {
 namespace {
 
 constexpr int TBM = 128;           // CTA tile rows  (UMMA M)
-constexpr int TBK = 32;            // k-slab
+constexpr int TBK = 16;            // k-slab (fp32 elements)
+constexpr int KQ = TBK / 4;        // 16-byte k-chunks per row per slab
 constexpr int LOADERS = 256;       // threads of warps 0-7
 constexpr int NTHREADS = 288;
 
@@ -56,9 +62,13 @@ struct TcGemmParams {
     int passes;                    // 1 or 3
 };
 
-__host__ __device__ constexpr int tile_lbo(int rows) { return 18 * rows + 16; }
+__host__ __device__ constexpr int tile_lbo(int rows) { return 18 * rows + 32; }
 constexpr int TILE_SBO = 144;
-__host__ __device__ constexpr int slot_bytes(int rows) { return 8 * tile_lbo(rows); }
+__host__ __device__ constexpr int slot_bytes(int rows) { return KQ * tile_lbo(rows); }
+// 16-byte register chunks a loader thread holds for one operand slab
+__host__ __device__ constexpr int nreg(int rows, bool mn) {
+    return mn ? 4 * (((rows / 4) * KQ + LOADERS - 1) / LOADERS) : (rows * KQ) / LOADERS;
+}
 
 // one 16-byte chunk of an operand tile -> shared memory (hi and, when SPLIT, lo parts)
 template <bool SPLIT>
@@ -73,73 +83,68 @@ __device__ __forceinline__ void put_chunk(uint8_t* hi, uint8_t* lo, int off, con
     if (SPLIT) *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
 }
 
-// Global -> registers for this thread's share of one operand slab (R rows x 32 k).
-//  MN = false (K-contiguous source, element (r, k) at src[r*ld + k]):
-//       chunk c = tid + 256*i: kq = c%8, r = c/8; reg[i] = 4 consecutive k of row r
-//  MN = true  (MN-contiguous source, element (r, k) at src[k*ld + r]):
-//       block b = tid + 256*i: rg = b%(R/4), kq = b/(R/4); reg[4*i + j] = rows rg*4..+3 at k = kq*4 + j
-template <int R, bool MN, bool VEC>
-__device__ __forceinline__ void fetch_tile(const float* __restrict__ src, int64_t ld, int64_t r0, int64_t rows,
-                                           int64_t k0, int64_t kend, int tid, float (&reg)[R / 32][4]) {
-    if (!MN) {
-#pragma unroll
-        for (int i = 0; i < R / 32; ++i) {
-            const int c = tid + LOADERS * i;
-            const int64_t r = r0 + (c >> 3);
-            const int64_t k = k0 + (c & 7) * 4;
-            const float* p = src + r * ld + k;
-            if (VEC) {
-                if (r < rows && k < kend) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
-                    reg[i][0] = t.x; reg[i][1] = t.y; reg[i][2] = t.z; reg[i][3] = t.w;
-                } else {
-                    reg[i][0] = reg[i][1] = reg[i][2] = reg[i][3] = 0.0f;
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) reg[i][e] = (r < rows && k + e < kend) ? __ldg(p + e) : 0.0f;
-            }
+template <bool VEC>
+__device__ __forceinline__ void load4(const float* p, bool ok, int64_t lim, float (&d)[4]) {
+    // ok: the whole chunk is addressable (VEC) / lim: number of valid leading elements (scalar path)
+    if (VEC) {
+        if (ok) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+            d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+        } else {
+            d[0] = d[1] = d[2] = d[3] = 0.0f;
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < R / 128; ++i) {
+        for (int e = 0; e < 4; ++e) d[e] = (ok && e < lim) ? __ldg(p + e) : 0.0f;
+    }
+}
+
+// Global -> registers for this thread's share of one operand slab (R rows x TBK k).
+//  MN = false (K-contiguous source, element (r, k) at src[r*ld + k]):
+//       chunk c = tid + 256*i: kq = c % KQ, r = c / KQ; reg[i] = 4 consecutive k of row r
+//  MN = true  (MN-contiguous source, element (r, k) at src[k*ld + r]):
+//       block b = tid + 256*i: rg = b % (R/4), kq = b / (R/4); reg[4*i + j] = rows rg*4..+3 at k = kq*4 + j
+template <int R, bool MN, bool VEC>
+__device__ __forceinline__ void fetch_tile(const float* __restrict__ src, int64_t ld, int64_t r0, int64_t rows,
+                                           int64_t k0, int64_t kend, int tid, float (&reg)[nreg(R, MN)][4]) {
+    if (!MN) {
+#pragma unroll
+        for (int i = 0; i < nreg(R, false); ++i) {
+            const int c = tid + LOADERS * i;
+            const int64_t r = r0 + c / KQ;
+            const int64_t k = k0 + (c % KQ) * 4;
+            load4<VEC>(src + r * ld + k, r < rows && k < kend, kend - k, reg[i]);
+        }
+    } else {
+        constexpr int BLOCKS = (R / 4) * KQ;
+#pragma unroll
+        for (int i = 0; i < nreg(R, true) / 4; ++i) {
             const int b = tid + LOADERS * i;
             const int64_t r = r0 + (b % (R / 4)) * 4;
             const int64_t kb = k0 + (b / (R / 4)) * 4;
+            const bool live = (BLOCKS % LOADERS == 0) || b < BLOCKS;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int64_t k = kb + j;
-                const float* p = src + k * ld + r;
-                float (&d)[4] = reg[4 * i + j];
-                if (VEC) {
-                    if (k < kend && r < rows) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
-                        d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
-                    } else {
-                        d[0] = d[1] = d[2] = d[3] = 0.0f;
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) d[e] = (k < kend && r + e < rows) ? __ldg(p + e) : 0.0f;
-                }
-            }
+            for (int j = 0; j < 4; ++j)
+                load4<VEC>(src + (kb + j) * ld + r, live && (kb + j) < kend && r < rows, rows - r, reg[4 * i + j]);
         }
     }
 }
 
 template <int R, bool MN, bool SPLIT>
-__device__ __forceinline__ void stash_tile(uint8_t* hi, uint8_t* lo, int tid, const float (&reg)[R / 32][4]) {
+__device__ __forceinline__ void stash_tile(uint8_t* hi, uint8_t* lo, int tid, const float (&reg)[nreg(R, MN)][4]) {
     if (!MN) {
 #pragma unroll
-        for (int i = 0; i < R / 32; ++i) {
+        for (int i = 0; i < nreg(R, false); ++i) {
             const int c = tid + LOADERS * i;
-            const int kq = c & 7, r = c >> 3;
+            const int kq = c % KQ, r = c / KQ;
             put_chunk<SPLIT>(hi, lo, kq * tile_lbo(R) + (r >> 3) * TILE_SBO + (r & 7) * 16, reg[i]);
         }
     } else {
+        constexpr int BLOCKS = (R / 4) * KQ;
 #pragma unroll
-        for (int i = 0; i < R / 128; ++i) {
+        for (int i = 0; i < nreg(R, true) / 4; ++i) {
             const int b = tid + LOADERS * i;
+            if ((BLOCKS % LOADERS != 0) && b >= BLOCKS) continue;
             const int rg = b % (R / 4), kq = b / (R / 4);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {          // row r = rg*4 + e gets (k%4 = 0..3) from the 4 loads
@@ -164,11 +169,16 @@ __device__ __forceinline__ float tc_epilogue_one(const TcGemmParams& p, int64_t 
     return v;
 }
 
-// BN: CTA tile columns (UMMA N, TMEM columns); AMN/BMN: operand is MN-major in global memory
+template <bool SPLIT>
+struct Cfg {
+    static constexpr int STAGES = SPLIT ? 3 : 6;
+};
+
+// BN: CTA tile columns (UMMA N, TMEM columns); AMN/BMN: operand is MN-contiguous in global memory
 // (A: transa = 1, B: transb = 0); VA/VB: 16-byte global loads legal; SPLIT: 3xTF32.
 template <int BN, bool AMN, bool BMN, bool VA, bool VB, bool SPLIT>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tcgen05_kernel(const TcGemmParams p) {
-    constexpr int STAGES = SPLIT ? 2 : 4;
+    constexpr int STAGES = Cfg<SPLIT>::STAGES;
     constexpr int A_SLOT = slot_bytes(TBM), B_SLOT = slot_bytes(BN);
     constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_SLOT + B_SLOT);
     extern __shared__ __align__(128) uint8_t smem[];
@@ -205,24 +215,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tcgen05_kernel(const TcGemmP
 
     if (warp < 8) {
         // ============================ loaders ============================
-        float ra[TBM / 32][4], rb[BN / 32][4];
-        if (n_iter > 0) {
-            fetch_tile<TBM, AMN, VA>(p.A, p.lda, m0, p.M, kbeg, kend, tid, ra);
-            fetch_tile<BN, BMN, VB>(p.B, p.ldb, n0, p.N, kbeg, kend, tid, rb);
-        }
-        for (int it = 0; it < n_iter; ++it) {
+        float ra[2][nreg(TBM, AMN)][4], rb[2][nreg(BN, BMN)][4];
+        auto fetch = [&](int it, float (&a)[nreg(TBM, AMN)][4], float (&b)[nreg(BN, BMN)][4]) {
+            if (it < n_iter) {
+                const int64_t k0 = kbeg + static_cast<int64_t>(it) * TBK;
+                fetch_tile<TBM, AMN, VA>(p.A, p.lda, m0, p.M, k0, kend, tid, a);
+                fetch_tile<BN, BMN, VB>(p.B, p.ldb, n0, p.N, k0, kend, tid, b);
+            }
+        };
+        auto publish = [&](int it, const float (&a)[nreg(TBM, AMN)][4], const float (&b)[nreg(BN, BMN)][4]) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
             tc::mbar_wait(&empty_bar[s], ph ^ 1);         // slot free (first round passes immediately)
-            stash_tile<TBM, AMN, SPLIT>(stage_ptr(s, 0), stage_ptr(s, 2), tid, ra);
-            stash_tile<BN, BMN, SPLIT>(stage_ptr(s, 1), stage_ptr(s, 3), tid, rb);
-            if (it + 1 < n_iter) {                        // next slab's global loads fly during the MMAs
-                const int64_t k0 = kbeg + static_cast<int64_t>(it + 1) * TBK;
-                fetch_tile<TBM, AMN, VA>(p.A, p.lda, m0, p.M, k0, kend, tid, ra);
-                fetch_tile<BN, BMN, VB>(p.B, p.ldb, n0, p.N, k0, kend, tid, rb);
-            }
+            stash_tile<TBM, AMN, SPLIT>(stage_ptr(s, 0), stage_ptr(s, 2), tid, a);
+            stash_tile<BN, BMN, SPLIT>(stage_ptr(s, 1), stage_ptr(s, 3), tid, b);
+        };
+        fetch(0, ra[0], rb[0]);
+        fetch(1, ra[1], rb[1]);
+        for (int it = 0; it < n_iter; it += 2) {
+            publish(it, ra[0], rb[0]);
+            fetch(it + 2, ra[0], rb[0]);                  // two slabs ahead of the stores
             tc::fence_proxy_async_smem();
-            tc::mbar_arrive(&full_bar[s]);
+            tc::mbar_arrive(&full_bar[it % STAGES]);
+            if (it + 1 < n_iter) {
+                publish(it + 1, ra[1], rb[1]);
+                fetch(it + 3, ra[1], rb[1]);
+                tc::fence_proxy_async_smem();
+                tc::mbar_arrive(&full_bar[(it + 1) % STAGES]);
+            }
         }
     } else {
         // ============================ MMA issuer ============================
@@ -279,9 +299,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tcgen05_kernel(const TcGemmP
             if (r < p.M) {
                 const int64_t c0 = n0 + cb;
                 if (split) {
+                    float* dst = wsz + r * p.N + c0;
+                    if ((p.N % 4 == 0) && c0 + 31 < p.N) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                        if (c0 + e < p.N) wsz[r * p.N + c0 + e] = v[e];
+                        for (int e = 0; e < 32; e += 4)
+                            *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            if (c0 + e < p.N) dst[e] = v[e];
+                    }
                 } else {
 #pragma unroll
                     for (int e = 0; e < 32; ++e)
@@ -318,9 +345,8 @@ __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const TcGemmParam
 
 template <int BN, bool AMN, bool BMN, bool VA, bool VB, bool SPLIT>
 int launch_one(const TcGemmParams& p, dim3 grid, cudaStream_t st) {
-    constexpr int STAGES = SPLIT ? 2 : 4;
-    constexpr int bytes = STAGES * (SPLIT ? 2 : 1) * (slot_bytes(TBM) + slot_bytes(BN));
-    static_assert(bytes <= 227 * 1024, "shared memory budget");
+    constexpr int bytes = Cfg<SPLIT>::STAGES * (SPLIT ? 2 : 1) * (slot_bytes(TBM) + slot_bytes(BN));
+    static_assert(bytes <= 180 * 1024, "keep >= 48 KB of the 228 KB carve-out for L1 (loads in flight)");
     auto kern = gemm_tcgen05_kernel<BN, AMN, BMN, VA, VB, SPLIT>;
     static bool configured = false;
     if (!configured) {
@@ -383,6 +409,7 @@ extern "C" int plnlp_gemm_tf32(int passes, int transa, int transb, int64_t M, in
     if (split_k > 1) {
         PLNLP_REQUIRE(workspace, PLNLP_E_NULL);
         PLNLP_REQUIRE(workspace_bytes >= static_cast<int64_t>(split_k) * M * N * 4, PLNLP_E_WORKSPACE);
+        PLNLP_REQUIRE(aligned(workspace, 16), PLNLP_E_ALIGN);
     }
     const bool amn = transa != 0, bmn = transb == 0;
     const bool va = aligned(A, 16) && (lda % 4 == 0) && ((transa ? M : K) % 4 == 0);
