@@ -101,10 +101,10 @@ def gemm_raw(A, B, transa=False, transb=False, C=None, beta=0.0, bias=None, act=
         split_k = 1
         if tiles < 148 and K >= 2048:
             split_k = int(min(max(1, (2 * 148) // tiles), K // 512, 64))
-        if backend == "tf32x3":
-            # the tensor core accumulates with round-toward-zero: keep K per accumulator <= 1024 and
-            # let the split-k reduction (RN adds on the CUDA cores) combine the partials
-            split_k = max(split_k, (K + 1023) // 1024)
+    if backend == "tf32x3":
+        # the tensor core accumulates with round-toward-zero: keep K per accumulator <= 1024 and
+        # let the split-k reduction (RN adds on the CUDA cores) combine the partials
+        split_k = max(split_k, (K + 1023) // 1024)
     ws = None
     ws_bytes = 0
     if split_k > 1:

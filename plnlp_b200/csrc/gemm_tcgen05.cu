@@ -232,16 +232,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tcgen05_kernel(const TcGemmP
         };
         fetch(0, ra[0], rb[0]);
         fetch(1, ra[1], rb[1]);
+        // NOTE the order: the proxy fence waits for every memory operation the thread has in flight,
+        // including global loads, so it must come BEFORE the next prefetch is issued (measured: with
+        // the prefetch first every slab paid a full global-load latency).
         for (int it = 0; it < n_iter; it += 2) {
             publish(it, ra[0], rb[0]);
-            fetch(it + 2, ra[0], rb[0]);                  // two slabs ahead of the stores
             tc::fence_proxy_async_smem();
             tc::mbar_arrive(&full_bar[it % STAGES]);
+            fetch(it + 2, ra[0], rb[0]);                  // two slabs ahead of the stores
             if (it + 1 < n_iter) {
                 publish(it + 1, ra[1], rb[1]);
-                fetch(it + 3, ra[1], rb[1]);
                 tc::fence_proxy_async_smem();
                 tc::mbar_arrive(&full_bar[(it + 1) % STAGES]);
+                fetch(it + 3, ra[1], rb[1]);
             }
         }
     } else {
