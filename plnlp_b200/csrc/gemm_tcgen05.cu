@@ -83,78 +83,104 @@ __device__ __forceinline__ void put_chunk(uint8_t* hi, uint8_t* lo, int off, con
     if (SPLIT) *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
 }
 
-template <bool VEC>
-__device__ __forceinline__ void load4(const float* p, bool ok, int64_t lim, float (&d)[4]) {
-    // ok: the whole chunk is addressable (VEC) / lim: number of valid leading elements (scalar path)
-    if (VEC) {
-        if (ok) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(p));
-            d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
-        } else {
-            d[0] = d[1] = d[2] = d[3] = 0.0f;
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) d[e] = (ok && e < lim) ? __ldg(p + e) : 0.0f;
-    }
-}
-
-// Global -> registers for this thread's share of one operand slab (R rows x TBK k).
+// Per-thread view of one operand's slabs.  Everything that does not change from slab to slab (row
+// pointers, row validity, shared-memory offsets) is computed once; per slab the loader only bumps the
+// pointers -- the loader warps are instruction-issue bound, every hoisted instruction counts.
 //  MN = false (K-contiguous source, element (r, k) at src[r*ld + k]):
 //       chunk c = tid + 256*i: kq = c % KQ, r = c / KQ; reg[i] = 4 consecutive k of row r
 //  MN = true  (MN-contiguous source, element (r, k) at src[k*ld + r]):
 //       block b = tid + 256*i: rg = b % (R/4), kq = b / (R/4); reg[4*i + j] = rows rg*4..+3 at k = kq*4 + j
 template <int R, bool MN, bool VEC>
-__device__ __forceinline__ void fetch_tile(const float* __restrict__ src, int64_t ld, int64_t r0, int64_t rows,
-                                           int64_t k0, int64_t kend, int tid, float (&reg)[nreg(R, MN)][4]) {
-    if (!MN) {
+struct Loader {
+    static constexpr int NR = nreg(R, MN);
+    static constexpr int NP = MN ? NR / 4 : NR;
+    const float* ptr[NP];
+    int soff[NP];       // byte offset of the chunk (MN: of row rg*4, rows +1..+3 follow at +16 B)
+    int kq4[NP];        // first k of the chunk inside the slab
+    int nrow[NP];       // MN scalar path: valid rows of the block (<= 4); otherwise 0/1 row validity
+    int64_t step;       // elements between consecutive slabs
+
+    __device__ __forceinline__ void init(const float* src, int64_t ld, int64_t r0, int64_t rows, int64_t kbeg,
+                                         int tid) {
 #pragma unroll
-        for (int i = 0; i < nreg(R, false); ++i) {
+        for (int i = 0; i < NP; ++i) {
             const int c = tid + LOADERS * i;
-            const int64_t r = r0 + c / KQ;
-            const int64_t k = k0 + (c % KQ) * 4;
-            load4<VEC>(src + r * ld + k, r < rows && k < kend, kend - k, reg[i]);
+            if (!MN) {
+                const int kq = c % KQ, r = c / KQ;
+                kq4[i] = kq * 4;
+                nrow[i] = (r0 + r) < rows ? 1 : 0;
+                soff[i] = kq * tile_lbo(R) + (r >> 3) * TILE_SBO + (r & 7) * 16;
+                ptr[i] = src + (r0 + r) * ld + kbeg + kq * 4;
+            } else {
+                const int rg = c % (R / 4), kq = c / (R / 4);
+                const bool live = c < (R / 4) * KQ;
+                const int64_t left = rows - (r0 + rg * 4);
+                kq4[i] = kq * 4;
+                nrow[i] = !live ? 0 : (left >= 4 ? 4 : (left > 0 ? static_cast<int>(left) : 0));
+                soff[i] = kq * tile_lbo(R) + ((rg * 4) >> 3) * TILE_SBO + ((rg * 4) & 7) * 16;
+                ptr[i] = src + (kbeg + kq * 4) * ld + r0 + rg * 4;
+            }
         }
-    } else {
-        constexpr int BLOCKS = (R / 4) * KQ;
+        step = MN ? ld * TBK : TBK;
+    }
+
+    // kleft = kend - k0 of the slab being fetched (<= 0: nothing left, zero fill)
+    __device__ __forceinline__ void fetch(int kleft, float (&reg)[NR][4]) {
 #pragma unroll
-        for (int i = 0; i < nreg(R, true) / 4; ++i) {
-            const int b = tid + LOADERS * i;
-            const int64_t r = r0 + (b % (R / 4)) * 4;
-            const int64_t kb = k0 + (b / (R / 4)) * 4;
-            const bool live = (BLOCKS % LOADERS == 0) || b < BLOCKS;
+        for (int i = 0; i < NP; ++i) {
+            if (!MN) {
+                const int lim = kleft - kq4[i];
+                if (VEC) {
+                    if (nrow[i] && lim > 0) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(ptr[i]));
+                        reg[i][0] = t.x; reg[i][1] = t.y; reg[i][2] = t.z; reg[i][3] = t.w;
+                    } else {
+                        reg[i][0] = reg[i][1] = reg[i][2] = reg[i][3] = 0.0f;
+                    }
+                } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                load4<VEC>(src + (kb + j) * ld + r, live && (kb + j) < kend && r < rows, rows - r, reg[4 * i + j]);
+                    for (int e = 0; e < 4; ++e) reg[i][e] = (nrow[i] && e < lim) ? __ldg(ptr[i] + e) : 0.0f;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float* q = ptr[i] + j * (step / TBK);
+                    float (&d)[4] = reg[4 * i + j];
+                    const bool kok = (kq4[i] + j) < kleft;
+                    if (VEC) {
+                        if (kok && nrow[i]) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(q));
+                            d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+                        } else {
+                            d[0] = d[1] = d[2] = d[3] = 0.0f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) d[e] = (kok && e < nrow[i]) ? __ldg(q + e) : 0.0f;
+                    }
+                }
+            }
+            ptr[i] += step;
         }
     }
-}
 
-template <int R, bool MN, bool SPLIT>
-__device__ __forceinline__ void stash_tile(uint8_t* hi, uint8_t* lo, int tid, const float (&reg)[nreg(R, MN)][4]) {
-    if (!MN) {
+    template <bool SPLIT>
+    __device__ __forceinline__ void stash(uint8_t* hi, uint8_t* lo, const float (&reg)[NR][4]) const {
 #pragma unroll
-        for (int i = 0; i < nreg(R, false); ++i) {
-            const int c = tid + LOADERS * i;
-            const int kq = c % KQ, r = c / KQ;
-            put_chunk<SPLIT>(hi, lo, kq * tile_lbo(R) + (r >> 3) * TILE_SBO + (r & 7) * 16, reg[i]);
-        }
-    } else {
-        constexpr int BLOCKS = (R / 4) * KQ;
+        for (int i = 0; i < NP; ++i) {
+            if (!MN) {
+                put_chunk<SPLIT>(hi, lo, soff[i], reg[i]);
+            } else {
+                if ((((R / 4) * KQ) % LOADERS != 0) && (threadIdx.x + LOADERS * i >= (R / 4) * KQ)) continue;
 #pragma unroll
-        for (int i = 0; i < nreg(R, true) / 4; ++i) {
-            const int b = tid + LOADERS * i;
-            if ((BLOCKS % LOADERS != 0) && b >= BLOCKS) continue;
-            const int rg = b % (R / 4), kq = b / (R / 4);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {          // row r = rg*4 + e gets (k%4 = 0..3) from the 4 loads
-                const int r = rg * 4 + e;
-                const float v[4] = {reg[4 * i + 0][e], reg[4 * i + 1][e], reg[4 * i + 2][e], reg[4 * i + 3][e]};
-                put_chunk<SPLIT>(hi, lo, kq * tile_lbo(R) + (r >> 3) * TILE_SBO + (r & 7) * 16, v);
+                for (int e = 0; e < 4; ++e) {      // row rg*4 + e gets (k%4 = 0..3) from the 4 loads
+                    const float v[4] = {reg[4 * i + 0][e], reg[4 * i + 1][e], reg[4 * i + 2][e], reg[4 * i + 3][e]};
+                    put_chunk<SPLIT>(hi, lo, soff[i] + e * 16, v);
+                }
             }
         }
     }
-}
+};
 
 __device__ __forceinline__ float tc_epilogue_one(const TcGemmParams& p, int64_t r, int64_t c, float v) {
     if (p.beta != 0.0f) v += p.beta * p.C[r * p.ldc + c];
@@ -216,19 +242,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tcgen05_kernel(const TcGemmP
     if (warp < 8) {
         // ============================ loaders ============================
         float ra[2][nreg(TBM, AMN)][4], rb[2][nreg(BN, BMN)][4];
+        Loader<TBM, AMN, VA> la;
+        Loader<BN, BMN, VB> lb;
+        la.init(p.A, p.lda, m0, p.M, kbeg, tid);
+        lb.init(p.B, p.ldb, n0, p.N, kbeg, tid);
+        const int ktot = static_cast<int>(kend - kbeg);
         auto fetch = [&](int it, float (&a)[nreg(TBM, AMN)][4], float (&b)[nreg(BN, BMN)][4]) {
-            if (it < n_iter) {
-                const int64_t k0 = kbeg + static_cast<int64_t>(it) * TBK;
-                fetch_tile<TBM, AMN, VA>(p.A, p.lda, m0, p.M, k0, kend, tid, a);
-                fetch_tile<BN, BMN, VB>(p.B, p.ldb, n0, p.N, k0, kend, tid, b);
+            if (it < n_iter) {                            // called with it = 0, 1, 2, ... in order
+                la.fetch(ktot - it * TBK, a);
+                lb.fetch(ktot - it * TBK, b);
             }
         };
         auto publish = [&](int it, const float (&a)[nreg(TBM, AMN)][4], const float (&b)[nreg(BN, BMN)][4]) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
             tc::mbar_wait(&empty_bar[s], ph ^ 1);         // slot free (first round passes immediately)
-            stash_tile<TBM, AMN, SPLIT>(stage_ptr(s, 0), stage_ptr(s, 2), tid, a);
-            stash_tile<BN, BMN, SPLIT>(stage_ptr(s, 1), stage_ptr(s, 3), tid, b);
+            la.template stash<SPLIT>(stage_ptr(s, 0), stage_ptr(s, 2), a);
+            lb.template stash<SPLIT>(stage_ptr(s, 1), stage_ptr(s, 3), b);
         };
         fetch(0, ra[0], rb[0]);
         fetch(1, ra[1], rb[1]);
@@ -289,6 +319,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tcgen05_kernel(const TcGemmP
         const int q = warp & 3, half = warp >> 2;
         const int64_t r = m0 + q * 32 + lane;
         const bool split = p.split_k > 1;
+        const bool plain = p.beta == 0.0f && p.bias == nullptr && p.act == PLNLP_ACT_NONE;
         float* wsz = split ? p.ws + static_cast<int64_t>(blockIdx.z) * p.M * p.N : nullptr;
         for (int cb = half * (BN / 2); cb < (half + 1) * (BN / 2); cb += 32) {
             if (cb >= n_mma) break;                                   // warp-uniform
@@ -313,9 +344,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tcgen05_kernel(const TcGemmP
                             if (c0 + e < p.N) dst[e] = v[e];
                     }
                 } else {
+                    if (!plain) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                        if (c0 + e < p.N) v[e] = tc_epilogue_one(p, r, c0 + e, v[e]);
+                        for (int e = 0; e < 32; ++e)
+                            if (c0 + e < p.N) v[e] = tc_epilogue_one(p, r, c0 + e, v[e]);
+                    }
                     float* dst = p.C + r * p.ldc + c0;
                     if ((p.ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(p.C) % 16 == 0) && c0 + 31 < p.N) {
 #pragma unroll
