@@ -9,7 +9,7 @@ import os
 
 import torch
 
-from . import _lib, profiling
+from . import _lib, parallel, profiling
 from ._lib import check, ptr, stream, workspace
 from .graph import structure_of
 
@@ -22,7 +22,7 @@ SCATTER_MODE = "sorted"
 
 # dense-layer backend: "tf32x3" = tcgen05 tensor cores with error-compensated 3xTF32 (fp32 parity,
 # default), "tf32" = plain TF32 tensor cores (fast path, ~1e-3 relative), "ffma" = exact fp32 CUDA cores
-GEMM_BACKEND = os.environ.get("PLNLP_GEMM", "ffma")
+GEMM_BACKEND = os.environ.get("PLNLP_GEMM", "tf32x3")
 
 
 def _f32c(t):
@@ -302,6 +302,8 @@ class SpMM(torch.autograd.Function):
 def spmm(adj, x, reduce="sum", bias=None, relu=False, drop_p=0.0, seed=0):
     if reduce == "add":
         reduce = "sum"
+    if isinstance(adj, parallel.ShardedAdj):      # row-partitioned encoder (citation2-shape)
+        return parallel.pspmm(adj, x, reduce, bias=bias, relu=relu, drop_p=drop_p, seed=seed)
     if reduce not in ("sum", "mean"):
         raise NotImplementedError(f"reduce={reduce!r}")
     return SpMM.apply(x, bias, adj, reduce, bool(relu), float(drop_p), int(seed))

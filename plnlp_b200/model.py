@@ -138,14 +138,8 @@ class BaseModel(object):
         """data-parallel edge batches (no counterpart in the reference): every rank
         scored its own batch against a replicated encoder; the loss is a SUM over pairs, so summing
         the gradients over ranks gives the gradient of the global batch.  One flat NCCL all-reduce."""
-        import torch.distributed as dist
-        grads = [p.grad for p in self.para_list if p.grad is not None]
-        flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat)
-        off = 0
-        for g in grads:
-            g.copy_(flat[off:off + g.numel()].view_as(g))
-            off += g.numel()
+        from . import parallel
+        parallel.allreduce_grads(self.para_list)
 
     def train(self, data, split_edge, batch_size, neg_sampler_name, num_neg, perms=None, neg_edges=None,
               max_batches=None):

@@ -1,0 +1,97 @@
+"""CPU tests (-m "not gpu") of the multi-GPU plumbing with torch.distributed gloo, world_size 2:
+row partition bookkeeping, the all-gather / reduce-scatter autograd pair, the partitioned SpMM
+(with the oracle as the injected local operator -- the CUDA kernel is exercised under gpurun) and
+the flat gradient all-reduce.  Parity target: the single-process result."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import sparse
+from plnlp_b200 import parallel
+from tests.helpers import rand_graph, rel_err
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _oracle_graph(rowptr, col, val, sizes):
+    return sparse.SparseTensor(rowptr=rowptr, col=col, value=val, sparse_sizes=sizes, is_sorted=True)
+
+
+def _local_op(adj, x, reduce, **kw):
+    return sparse.matmul(adj, x, reduce)
+
+
+def _worker(rank, world_size, port, N, F, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        torch.manual_seed(0)
+        ei, w = rand_graph(N, 400, seed=3, weighted=True, hub=True)
+        full = sparse.to_sparse_tensor(ei, w, N)
+        x = torch.randn(N, F)
+        gout = torch.randn(N, F)
+        lo, hi = parallel.row_block(N, rank, world_size)
+        blk = parallel.block_size(N, world_size)
+        sadj = parallel.shard_graph(full, rank, world_size, _oracle_graph)
+        assert sadj.local.size(0) == blk and sadj.local.size(1) == blk * world_size
+        # index work: local rows are the global rows, bit for bit
+        rp, col, val = full.csr()
+        lrp, lcol, lval = sadj.local.csr()
+        assert torch.equal(lcol, col[rp[lo]:rp[hi]]) and torch.equal(lval, val[rp[lo]:rp[hi]])
+        assert torch.equal(lrp[: hi - lo + 1], rp[lo:hi + 1] - rp[lo])
+        out = {}
+        for reduce in ("sum", "mean"):
+            xl = x[lo:hi].clone().requires_grad_(True)
+            adj_r = sadj if reduce == "sum" else parallel.ShardedAdj(
+                _oracle_graph(lrp, lcol, None, sadj.local.sparse_sizes()), N, rank, world_size)
+            y = parallel.pspmm(adj_r, xl, reduce, local_op=_local_op)
+            assert y.shape == (blk, F)
+            g = torch.zeros(blk, F)
+            g[: hi - lo] = gout[lo:hi]
+            y.backward(g)
+            out[reduce] = (y.detach()[: hi - lo], xl.grad.clone())
+        # flat gradient all-reduce
+        p1, p2 = torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(5))
+        p1.grad = torch.full((3, 2), float(rank + 1))
+        p2.grad = torch.arange(5.0) * (rank + 1)
+        parallel.allreduce_grads([p1, p2])
+        assert torch.equal(p1.grad, torch.full((3, 2), 3.0)) and torch.equal(p2.grad, torch.arange(5.0) * 3)
+        ret[rank] = {k: (v[0], v[1], lo, hi) for k, v in out.items()}
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_partition_bookkeeping():
+    assert parallel.block_size(10, 4) == 3
+    assert [parallel.row_block(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert parallel.row_block(2, 3, 4) == (2, 2)                 # empty tail block
+    blocks = [parallel.row_block(2927963, r, 8) for r in range(8)]
+    assert blocks[0][0] == 0 and blocks[-1][1] == 2927963
+    assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+
+
+def test_partitioned_spmm_matches_single_process_gloo_ws2():
+    N, F, ws = 37, 6, 2                                          # odd N: last block is padded
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(ws, port, N, F, ret), nprocs=ws, join=True)
+    ei, w = rand_graph(N, 400, seed=3, weighted=True, hub=True)
+    torch.manual_seed(0)
+    x = torch.randn(N, F)
+    gout = torch.randn(N, F)
+    for reduce in ("sum", "mean"):
+        full = sparse.to_sparse_tensor(ei, w if reduce == "sum" else None, N)
+        xr = x.clone().requires_grad_(True)
+        y = sparse.matmul(full, xr, reduce)
+        y.backward(gout)
+        for r in range(ws):
+            yl, gl, lo, hi = ret[r][reduce]
+            assert rel_err(yl, y.detach()[lo:hi]) < 1e-6
+            assert rel_err(gl, xr.grad[lo:hi]) < 1e-5             # summation order differs across ranks
