@@ -117,35 +117,55 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
+    """one streaming `nvidia-smi -lms 20` process started before the warm-up; `mark()` brackets the
+    timed region and only the samples that arrived inside it are summarised."""
+
     def __init__(self, index=0):
-        self.index, self.rows, self._stop = index, [], threading.Event()
-        self._t = threading.Thread(target=self._run, daemon=True)
+        self.index, self.rows, self.t0, self.t1 = index, [], None, None
+        self._proc, self._t = None, None
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        for line in self._proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.strip().split(",")]))
 
-    def __enter__(self):
-        self._t.start()
+    def start(self):
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                           "--format=csv,noheader,nounits", "-lms", "20"],
+                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        except Exception:
+            self._proc = None
         return self
 
-    def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+    def mark(self, begin):
+        if begin:
+            self.t0 = time.perf_counter()
+        else:
+            self.t1 = time.perf_counter()
+
+    def stop(self):
+        if self._proc is not None:
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=5)
+            except Exception:
+                self._proc.kill()
 
     def summary(self):
-        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= t <= self.t1]
+        note = "inside the timed region"
+        if not inside:       # region shorter than the sampling period: fall back to the nearest samples
+            inside = [r for t, r in self.rows if self.t0 is not None and t >= self.t0 - 0.5][:5]
+            note = "nearest to the timed region"
+        ok = [r for r in inside if len(r) >= 7]
+        sm = sorted(float(r[0]) for r in ok if r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in ok if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower() == "active"})
+        reasons = sorted({n for r in ok for n, v in zip(names, r[3:7]) if v.lower() == "active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(ok), "sampling": note}
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -194,15 +214,18 @@ def run_ours(args):
             model.train_batch(data, pos[i * B:(i + 1) * B], neg[i * B:(i + 1) * B].reshape(-1, 2), k)
 
     # ---- value: device-resident ------------------------------------------------------------
+    clk = ClockSampler(local).start()
     device_steps(W, 0)
     barrier()
     l0 = _lib.launch_count()
-    with ClockSampler(local) as clk:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        device_steps(K, 1)
-        e1.record()
-        barrier()
+    clk.mark(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    device_steps(K, 1)
+    e1.record()
+    barrier()
+    clk.mark(False)
+    clk.stop()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - l0
     t = torch.tensor([ms], dtype=torch.float64, device=device)

@@ -134,7 +134,9 @@ int plnlp_mlp_out_bwd_f32(const float* a, int64_t lda, const float* w, const flo
  *   grad_h[src_p] += g[p] * h[dst_p];   grad_h[dst_p] += g[p] * h[src_p]
  * _atomic: red.global.add (order non-deterministic).  _sorted: one warp per node segment of
  * the node-sorted incidence list (entry = 2*p + side), fixed summation order; grad_h rows of
- * listed nodes are OVERWRITTEN, the caller zero-fills grad_h first. */
+ * listed nodes are OVERWRITTEN.  seg_node == NULL: segment i is node i (n_seg <= n_rows, empty
+ * segments write a zero row, so with n_seg == n_rows no zero fill is needed); otherwise the
+ * caller zero-fills grad_h first. */
 int plnlp_edge_scatter_atomic_f32(const float* h, int64_t ldh, int64_t n_rows, const int64_t* edges, int64_t P, int64_t H,
                                   const float* da, int64_t ldda, const float* dscore, float* grad_h,
                                   int64_t ldg, void* stream);

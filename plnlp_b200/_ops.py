@@ -216,30 +216,31 @@ def edge_scatter_raw(h, edges, da=None, dscore=None, mode=None):
         da = _rowmajor(da)
     if dscore is not None:
         dscore = _f32c(dscore).contiguous()
-    grad_h = torch.zeros(n_rows, H, dtype=torch.float32, device=h.device)
     ldda = _ld(da) if da is not None else 0
     if mode == "atomic":
+        grad_h = torch.zeros(n_rows, H, dtype=torch.float32, device=h.device)
         with profiling.span("edge_scatter_atomic_f32", P * (5 * H * 4 + 16), 0):
             check(lib.plnlp_edge_scatter_atomic_f32(ptr(h), _ld(h), n_rows, ptr(edges), P, H, ptr(da), ldda,
                                                     ptr(dscore), ptr(grad_h), H, stream()),
                   "plnlp_edge_scatter_atomic_f32")
         return grad_h
-    # node-sorted incidence list: key = node * 2P + (2p + side) is unique -> any sort is deterministic
-    _sp = profiling.span("torch: sort+unique for sorted scatter")
+    # node-sorted incidence list (a CSR over ALL nodes): a STABLE sort of the endpoint ids orders the
+    # entries t = 2p + side by node and, inside a node, by t -> fixed summation order.  One segment per
+    # node (empty ones included, they write their zero row), so there is no data-dependent size and no
+    # host synchronisation, and grad_h needs no separate zero fill.
+    _sp = profiling.span("torch: stable sort + bincount for sorted scatter")
     _sp.__enter__()
     flat = edges.reshape(-1)                          # entry id t = 2p + side  <->  flat[t]
     flat = torch.where(flat < 0, flat + n_rows, flat)
-    key = flat * (2 * P) + torch.arange(2 * P, device=edges.device)
-    skey, _ = torch.sort(key)
-    entry = skey % (2 * P)
-    node = torch.div(skey, 2 * P, rounding_mode="floor")
-    seg_node, counts = torch.unique_consecutive(node, return_counts=True)
-    seg_ptr = torch.zeros(seg_node.numel() + 1, dtype=torch.int64, device=edges.device)
-    seg_ptr[1:] = torch.cumsum(counts, 0)
+    key = flat.to(torch.int32) if n_rows < 2 ** 31 else flat
+    _, entry = torch.sort(key, stable=True)
+    seg_ptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=edges.device)
+    seg_ptr[1:] = torch.cumsum(torch.bincount(flat, minlength=n_rows), 0)
     _sp.__exit__()
+    grad_h = torch.empty(n_rows, H, dtype=torch.float32, device=h.device)
     with profiling.span("edge_scatter_sorted_f32", P * (5 * H * 4 + 32), 0):
         check(lib.plnlp_edge_scatter_sorted_f32(ptr(h), _ld(h), n_rows, ptr(edges), P, H, ptr(da), ldda, ptr(dscore),
-                                                ptr(seg_ptr), ptr(seg_node), seg_node.numel(), ptr(entry),
+                                                ptr(seg_ptr), None, n_rows, ptr(entry),
                                                 ptr(grad_h), H, stream()), "plnlp_edge_scatter_sorted_f32")
     return grad_h
 

@@ -195,32 +195,63 @@ __global__ void __launch_bounds__(256) edge_scatter_sorted_kernel(const float* _
                                                                   const int64_t* __restrict__ seg_node, int64_t n_seg,
                                                                   const int64_t* __restrict__ entry,
                                                                   float* __restrict__ grad_h, int64_t ldg) {
+    // seg_node == NULL: segment sg IS node sg (one segment per node, empty ones write a zero row).
+    // The (entry, pair, partner) triples are fetched 32 at a time, one per lane, and broadcast by
+    // shuffle; each lane owns U feature vectors so every gathered row is read exactly once.
+    constexpr int U = 4;
     const int lane = threadIdx.x & 31;
     const int64_t sg = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (sg >= n_seg) return;
     const int64_t t0 = __ldg(seg_ptr + sg), t1 = __ldg(seg_ptr + sg + 1);
-    const int64_t node = wrap_index(__ldg(seg_node + sg), n_rows);
-    for (int f = lane * VEC; f < H; f += 32 * VEC) {
-        float acc[VEC];
+    const int64_t node = seg_node ? wrap_index(__ldg(seg_node + sg), n_rows) : sg;
+    for (int f0 = 0; f0 < H; f0 += 32 * VEC * U) {
+        float acc[U][VEC];
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) acc[e] = 0.0f;
-        for (int64_t t = t0; t < t1; ++t) {
-            const int64_t ent = __ldg(entry + t);
-            const int64_t p = ent >> 1;
-            const int64_t partner = wrap_index(__ldg(edges + 2 * p + ((ent & 1) ^ 1)), n_rows);
-            float g[VEC], b[VEC];
-            if (da) {
-                load_vec<VEC>(g, da + p * ldda + f);
-            } else {
-                const float gs = __ldg(dscore + p);
+        for (int u = 0; u < U; ++u)
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) g[e] = gs;
+            for (int e = 0; e < VEC; ++e) acc[u][e] = 0.0f;
+        for (int64_t base = t0; base < t1; base += 32) {
+            const int n = (t1 - base) < 32 ? static_cast<int>(t1 - base) : 32;
+            int64_t p = 0, partner = 0;
+            float gs = 0.0f;
+            if (lane < n) {
+                const int64_t ent = __ldg(entry + base + lane);
+                p = ent >> 1;
+                partner = wrap_index(__ldg(edges + 2 * p + ((ent & 1) ^ 1)), n_rows);
+                if (!da) gs = __ldg(dscore + p);
             }
-            load_vec<VEC>(b, h + partner * ldh + f);
+            for (int j = 0; j < n; ++j) {
+                const int64_t pj = __shfl_sync(0xffffffffu, p, j);
+                const int64_t qj = __shfl_sync(0xffffffffu, partner, j);
+                const float gj = __shfl_sync(0xffffffffu, gs, j);
+                float g[U][VEC], b[U][VEC];
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) acc[e] = fmaf(g[e], b[e], acc[e]);
+                for (int u = 0; u < U; ++u) {
+                    const int f = f0 + (u * 32 + lane) * VEC;
+                    if (f < H) {
+                        if (da) {
+                            load_vec<VEC>(g[u], da + pj * ldda + f);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) g[u][e] = gj;
+                        }
+                        load_vec<VEC>(b[u], h + qj * ldh + f);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) g[u][e] = b[u][e] = 0.0f;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) acc[u][e] = fmaf(g[u][e], b[u][e], acc[u][e]);
+            }
         }
-        store_vec<VEC>(grad_h + node * ldg + f, acc);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int f = f0 + (u * 32 + lane) * VEC;
+            if (f < H) store_vec<VEC>(grad_h + node * ldg + f, acc[u]);
+        }
     }
 }
 
@@ -338,8 +369,9 @@ extern "C" int plnlp_edge_scatter_sorted_f32(const float* h, int64_t ldh, int64_
                                              int64_t n_seg, const int64_t* entry, float* grad_h, int64_t ldg,
                                              void* stream) {
     PLNLP_REQUIRE(P >= 0 && H > 0 && n_rows > 0 && n_seg >= 0, PLNLP_E_SIZE);
-    if (P == 0 || n_seg == 0) return 0;
-    PLNLP_REQUIRE(h && edges && grad_h && (da || dscore) && seg_ptr && seg_node && entry, PLNLP_E_NULL);
+    if (n_seg == 0) return 0;
+    PLNLP_REQUIRE(h && edges && grad_h && (da || dscore) && seg_ptr && entry, PLNLP_E_NULL);
+    PLNLP_REQUIRE(seg_node || n_seg <= n_rows, PLNLP_E_SIZE);
     PLNLP_REQUIRE(ldh >= H && ldg >= H && (!da || ldda >= H), PLNLP_E_SIZE);
     const int vec = pick_vec(H, {ldh, ldg, da ? ldda : 4}, {h, grad_h, da});
     const unsigned grid = static_cast<unsigned>(ceil_div(n_seg, 8));

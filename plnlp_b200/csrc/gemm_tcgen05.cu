@@ -345,9 +345,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tcgen05_kernel(const TcGemmP
                     }
                 } else {
                     if (!plain) {
+                        const bool fast_relu = p.act == PLNLP_ACT_RELU && p.beta == 0.0f && (p.N % 4 == 0) &&
+                                               c0 + 31 < p.N;
+                        if (fast_relu) {
+                            // bias -> relu -> dropout with ONE Philox block per 4 consecutive columns
+                            // (element r*N + c uses word c%4 of block (r*N + c)/4: same stream as
+                            // dropout_keep, a quarter of the hashing)
+                            const float scale = 1.0f / (1.0f - p.drop_p);
 #pragma unroll
-                        for (int e = 0; e < 32; ++e)
-                            if (c0 + e < p.N) v[e] = tc_epilogue_one(p, r, c0 + e, v[e]);
+                            for (int e = 0; e < 32; e += 4) {
+                                bool keep[4] = {true, true, true, true};
+                                if (p.drop_p > 0.0f)
+                                    dropout_keep4(p.seed, static_cast<uint64_t>(r) * p.N + (c0 + e), p.drop_p, keep);
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    float x = v[e + t] + (p.bias ? __ldg(p.bias + c0 + e + t) : 0.0f);
+                                    x = fmaxf(x, 0.0f);
+                                    v[e + t] = p.drop_p > 0.0f ? (keep[t] ? x / (1.0f - p.drop_p) : 0.0f) : x;
+                                }
+                            }
+                            (void)scale;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e)
+                                if (c0 + e < p.N) v[e] = tc_epilogue_one(p, r, c0 + e, v[e]);
+                        }
                     }
                     float* dst = p.C + r * p.ldc + c0;
                     if ((p.ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(p.C) % 16 == 0) && c0 + 31 < p.N) {
