@@ -137,3 +137,17 @@ if __name__ == "__main__":
         citation2()
     if "citation2_small" in which:
         citation2(0.25)
+
+
+def gemm_epilogues():
+    """isolate the epilogue cost of the predictor forward GEMM"""
+    P, H = 262144, 512
+    A, W, b = torch.randn(P, H, device=DEV), torch.randn(H, H, device=DEV), torch.randn(H, device=DEV)
+    for name, kw in (("plain", {}), ("bias", dict(bias=b)), ("bias+relu", dict(bias=b, act=1)),
+                     ("bias+relu+drop", dict(bias=b, act=1, drop_p=0.3, seed=7))):
+        ms = timeit(lambda: _ops.gemm_raw(A, W, transb=True, backend="tf32x3", **kw))
+        print(f"[gemm tf32x3 epilogue {name}] {ms:.3f} ms -> {2.0*P*H*H/ms/1e9:.1f} TFLOP/s", flush=True)
+
+
+if __name__ == "__main__" and "epi" in sys.argv:
+    gemm_epilogues()
