@@ -37,9 +37,9 @@ __device__ __forceinline__ float epilogue_one(const GemmParams& p, int64_t r, in
     if (p.act == PLNLP_ACT_RELU) {
         v = fmaxf(v, 0.0f);
         if (p.drop_p > 0.0f)
-            v = dropout_keep(p.seed, static_cast<uint64_t>(r) * p.N + c, p.drop_p) ? v / (1.0f - p.drop_p) : 0.0f;
+            v = dropout_keep(p.seed, static_cast<uint64_t>(r) * p.N + c, p.drop_p) ? v * (1.0f / (1.0f - p.drop_p)) : 0.0f;
     } else if (p.act == PLNLP_ACT_RELU_GRAD) {
-        v = (__ldg(p.aux + r * p.ldaux + c) > 0.0f) ? v / (1.0f - p.drop_p) : 0.0f;
+        v = (__ldg(p.aux + r * p.ldaux + c) > 0.0f) ? v * (1.0f / (1.0f - p.drop_p)) : 0.0f;
     }
     return v;
 }

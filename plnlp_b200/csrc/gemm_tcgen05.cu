@@ -188,22 +188,22 @@ __device__ __forceinline__ float tc_epilogue_one(const TcGemmParams& p, int64_t 
     if (p.act == PLNLP_ACT_RELU) {
         v = fmaxf(v, 0.0f);
         if (p.drop_p > 0.0f)
-            v = dropout_keep(p.seed, static_cast<uint64_t>(r) * p.N + c, p.drop_p) ? v / (1.0f - p.drop_p) : 0.0f;
+            v = dropout_keep(p.seed, static_cast<uint64_t>(r) * p.N + c, p.drop_p) ? v * (1.0f / (1.0f - p.drop_p)) : 0.0f;
     } else if (p.act == PLNLP_ACT_RELU_GRAD) {
-        v = (__ldg(p.aux + r * p.ldaux + c) > 0.0f) ? v / (1.0f - p.drop_p) : 0.0f;
+        v = (__ldg(p.aux + r * p.ldaux + c) > 0.0f) ? v * (1.0f / (1.0f - p.drop_p)) : 0.0f;
     }
     return v;
 }
 
 template <bool SPLIT>
 struct Cfg {
-    static constexpr int STAGES = SPLIT ? 3 : 6;
+    static constexpr int STAGES = SPLIT ? 2 : 4;      // 2 CTAs per SM share the 227 KB
 };
 
 // BN: CTA tile columns (UMMA N, TMEM columns); AMN/BMN: operand is MN-contiguous in global memory
 // (A: transa = 1, B: transb = 0); VA/VB: 16-byte global loads legal; SPLIT: 3xTF32.
 template <int BN, bool AMN, bool BMN, bool VA, bool VB, bool SPLIT>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_tcgen05_kernel(const TcGemmParams p) {
+__global__ void __launch_bounds__(NTHREADS, 2) gemm_tcgen05_kernel(const TcGemmParams p) {
     constexpr int STAGES = Cfg<SPLIT>::STAGES;
     constexpr int A_SLOT = slot_bytes(TBM), B_SLOT = slot_bytes(BN);
     constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_SLOT + B_SLOT);
@@ -320,6 +320,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tcgen05_kernel(const TcGemmP
         const int64_t r = m0 + q * 32 + lane;
         const bool split = p.split_k > 1;
         const bool plain = p.beta == 0.0f && p.bias == nullptr && p.act == PLNLP_ACT_NONE;
+        const float keep_scale = 1.0f / (1.0f - p.drop_p);
+        const bool vec_epi = (p.N % 4 == 0) && (p.ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(p.C) % 16 == 0) &&
+                             (!p.bias || reinterpret_cast<uintptr_t>(p.bias) % 16 == 0) &&
+                             (!p.aux || ((p.ldaux % 4 == 0) && reinterpret_cast<uintptr_t>(p.aux) % 16 == 0));
         float* wsz = split ? p.ws + static_cast<int64_t>(blockIdx.z) * p.M * p.N : nullptr;
         for (int cb = half * (BN / 2); cb < (half + 1) * (BN / 2); cb += 32) {
             if (cb >= n_mma) break;                                   // warp-uniform
@@ -345,26 +349,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tcgen05_kernel(const TcGemmP
                     }
                 } else {
                     if (!plain) {
-                        const bool fast_relu = p.act == PLNLP_ACT_RELU && p.beta == 0.0f && (p.N % 4 == 0) &&
-                                               c0 + 31 < p.N;
-                        if (fast_relu) {
-                            // bias -> relu -> dropout with ONE Philox block per 4 consecutive columns
-                            // (element r*N + c uses word c%4 of block (r*N + c)/4: same stream as
-                            // dropout_keep, a quarter of the hashing)
-                            const float scale = 1.0f / (1.0f - p.drop_p);
+                        if (vec_epi && c0 + 31 < p.N) {
+                            // 4 columns at a time: 16-byte loads of C / bias / aux, one Philox block per
+                            // group (element r*N + c uses word c%4 of block (r*N + c)/4 -- the same
+                            // stream as dropout_keep, a quarter of the hashing)
+                            const float* crow = p.C + r * p.ldc + c0;
+                            const float* arow = p.aux ? p.aux + r * p.ldaux + c0 : nullptr;
+                            const uint64_t ebase = static_cast<uint64_t>(r) * p.N + c0;
 #pragma unroll
                             for (int e = 0; e < 32; e += 4) {
-                                bool keep[4] = {true, true, true, true};
-                                if (p.drop_p > 0.0f)
-                                    dropout_keep4(p.seed, static_cast<uint64_t>(r) * p.N + (c0 + e), p.drop_p, keep);
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    float x = v[e + t] + (p.bias ? __ldg(p.bias + c0 + e + t) : 0.0f);
-                                    x = fmaxf(x, 0.0f);
-                                    v[e + t] = p.drop_p > 0.0f ? (keep[t] ? x / (1.0f - p.drop_p) : 0.0f) : x;
+                                float x[4] = {v[e], v[e + 1], v[e + 2], v[e + 3]};
+                                if (p.beta != 0.0f) {
+                                    const float4 c4 = *reinterpret_cast<const float4*>(crow + e);
+                                    x[0] += p.beta * c4.x; x[1] += p.beta * c4.y;
+                                    x[2] += p.beta * c4.z; x[3] += p.beta * c4.w;
                                 }
+                                if (p.bias) {
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + e));
+                                    x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w;
+                                }
+                                if (p.act == PLNLP_ACT_RELU) {
+                                    bool keep[4] = {true, true, true, true};
+                                    if (p.drop_p > 0.0f) dropout_keep4(p.seed, ebase + e, p.drop_p, keep);
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t) x[t] = keep[t] ? fmaxf(x[t], 0.0f) * keep_scale : 0.0f;
+                                } else if (p.act == PLNLP_ACT_RELU_GRAD) {
+                                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(arow + e));
+                                    x[0] = a4.x > 0.0f ? x[0] * keep_scale : 0.0f;
+                                    x[1] = a4.y > 0.0f ? x[1] * keep_scale : 0.0f;
+                                    x[2] = a4.z > 0.0f ? x[2] * keep_scale : 0.0f;
+                                    x[3] = a4.w > 0.0f ? x[3] * keep_scale : 0.0f;
+                                }
+                                v[e] = x[0]; v[e + 1] = x[1]; v[e + 2] = x[2]; v[e + 3] = x[3];
                             }
-                            (void)scale;
                         } else {
 #pragma unroll
                             for (int e = 0; e < 32; ++e)
@@ -404,7 +421,7 @@ __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const TcGemmParam
 template <int BN, bool AMN, bool BMN, bool VA, bool VB, bool SPLIT>
 int launch_one(const TcGemmParams& p, dim3 grid, cudaStream_t st) {
     constexpr int bytes = Cfg<SPLIT>::STAGES * (SPLIT ? 2 : 1) * (slot_bytes(TBM) + slot_bytes(BN));
-    static_assert(bytes <= 180 * 1024, "keep >= 48 KB of the 228 KB carve-out for L1 (loads in flight)");
+    static_assert(bytes <= 113 * 1024, "two CTAs per SM: epilogue of one overlaps the main loop of the other");
     auto kern = gemm_tcgen05_kernel<BN, AMN, BMN, VA, VB, SPLIT>;
     static bool configured = false;
     if (!configured) {
