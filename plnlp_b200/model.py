@@ -71,6 +71,8 @@ class BaseModel(object):
         else:
             self.optimizer = torch.optim.Adam(trainable, lr=lr, fused=True)
         self.last_epoch_stats = {}
+        # multi-GPU state, set by the launcher (bench.py / tests): see plnlp_b200/parallel.py
+        self.world_size, self.rank, self.partitioned = 1, 0, False
 
     # ------------------------------------------------------------------
     def param_init(self):
@@ -117,6 +119,11 @@ class BaseModel(object):
         Returns the batch loss as a 0-d device tensor (no host sync)."""
         self.optimizer.zero_grad(set_to_none=True)
         h = self.encoder(self.input_parts(data), data.adj_t)
+        if self.partitioned:
+            # row-partitioned encoder (SURVEY 8e): h is this rank's row block; scoring needs arbitrary
+            # endpoints -> all-gather once per step (backward: reduce-scatter of grad_h)
+            from . import parallel
+            h = parallel.gather_rows(h)
         head = 'DOT' if isinstance(self.predictor, DotPredictor) else 'MLP'
         p = self.predictor.dropout if (head == 'MLP' and self.predictor.training) else 0.0
         loss = _ops.edge_score_loss(h, pos_edge, neg_edge, num_neg, self._loss_name(weight_margin is not None),
@@ -139,7 +146,13 @@ class BaseModel(object):
         scored its own batch against a replicated encoder; the loss is a SUM over pairs, so summing
         the gradients over ranks gives the gradient of the global batch.  One flat NCCL all-reduce."""
         from . import parallel
-        parallel.allreduce_grads(self.para_list)
+        params = self.para_list
+        if self.partitioned and self.emb is not None:
+            # embedding rows are owned by exactly one rank; their gradient arrived complete through
+            # the reduce-scatter of the gathers (owner computes) -> no all-reduce
+            own = {id(p) for p in self.emb.parameters()}
+            params = [p for p in params if id(p) not in own]
+        parallel.allreduce_grads(params)
 
     def train(self, data, split_edge, batch_size, neg_sampler_name, num_neg, perms=None, neg_edges=None,
               max_batches=None):
@@ -148,6 +161,13 @@ class BaseModel(object):
         ``max_batches`` stops early (bench time-boxing)."""
         self.encoder.train()
         self.predictor.train()
+        if self.world_size > 1 and neg_edges is None:
+            # data-parallel edge batches: rank r trains on edges r, r+R, r+2R, ... (equal counts on every
+            # rank so the per-step collectives line up)
+            tr = split_edge['train']
+            n_each = next(iter(tr.values())).size(0) // self.world_size
+            tr = {k: v[self.rank::self.world_size][:n_each] for k, v in tr.items()}
+            split_edge = dict(split_edge, train=tr)
         if neg_edges is None:
             pos_train_edge, neg_train_edge = get_pos_neg_edges(
                 'train', split_edge, edge_index=data.edge_index, num_nodes=self.num_nodes,
