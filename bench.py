@@ -272,15 +272,17 @@ def run_ours(args):
                    "loss D2H; bytes are the per-epoch copies divided by K"}
 
     # ---- instrumented pass: per-kernel durations (rank 0) ------------------------------------
+    # every rank runs the pass (its steps contain collectives); only rank 0 records events
     roof, kernels = None, []
     if rank == 0:
-        pk = peaks()
         profiling.enable()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record()
-        device_steps(K, 2)
-        p1.record()
-        torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    device_steps(K, 2)
+    p1.record()
+    barrier()
+    if rank == 0:
+        pk = peaks()
         stats = profiling.disable()
         ours = sum(s["ms"] for s in stats.values())
         stats["(torch plumbing: adam, clip, index, cat, sampler glue, launch gaps)"] = {

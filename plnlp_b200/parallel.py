@@ -47,7 +47,9 @@ def allreduce_grads(params, group=None):
     if not grads:
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, group=group)
+    from . import profiling
+    with profiling.span("nccl all_reduce (grads)", flat.numel() * 4, 0):
+        dist.all_reduce(flat, group=group)
     off = 0
     for g in grads:
         g.copy_(flat[off:off + g.numel()].view_as(g))
@@ -62,7 +64,10 @@ def _reduce_scatter_rows(full, blk, group=None):
         dist.all_reduce(full, group=group)
         out.copy_(full[rank * blk:(rank + 1) * blk])
     else:
-        dist.reduce_scatter_tensor(out, full.contiguous(), group=group)
+        from . import profiling
+        # bytes RECEIVED per rank: (R-1)/R of the full matrix (SURVEY 8d all-gather model)
+        with profiling.span("nccl reduce_scatter (rows)", (ws - 1) * out.numel() * 4, 0):
+            dist.reduce_scatter_tensor(out, full.contiguous(), group=group)
     return out
 
 
@@ -75,7 +80,9 @@ class GatherRows(torch.autograd.Function):
         _, ws = world()
         ctx.group, ctx.blk = group, x_local.size(0)
         full = torch.empty(ws * x_local.size(0), x_local.size(1), dtype=x_local.dtype, device=x_local.device)
-        dist.all_gather_into_tensor(full, x_local.contiguous(), group=group)
+        from . import profiling
+        with profiling.span("nccl all_gather (rows)", (ws - 1) * x_local.numel() * 4, 0):
+            dist.all_gather_into_tensor(full, x_local.contiguous(), group=group)
         return full
 
     @staticmethod
