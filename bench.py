@@ -253,23 +253,32 @@ def run_ours(args):
     value = pairs / (ms / 1e3)
 
     # ---- e2e: public API with HOST split_edge ----------------------------------------------
-    host_split = {"train": {kk: v.cpu().pin_memory() for kk, v in split["train"].items()}}
-    model.train(data, host_split, batch_size=B, neg_sampler_name=cfg["sampler"], num_neg=k, max_batches=W)
+    # the "epoch" handed to train() holds exactly K (resp. W) full batches per rank, in pinned host memory
+    def host_epoch(n_steps, seed):
+        g = torch.Generator().manual_seed(seed)
+        idx = torch.randint(0, E, (n_steps * B * world,), generator=g)
+        return {"train": {kk: v.cpu()[idx].contiguous().pin_memory() for kk, v in split["train"].items()}}
+
+    warm_split, host_split = host_epoch(W, 11), host_epoch(K, 12)
+    model.train(data, warm_split, batch_size=B, neg_sampler_name=cfg["sampler"], num_neg=k)
+    model.train(data, host_split, batch_size=B, neg_sampler_name=cfg["sampler"], num_neg=k)   # allocator warm-up
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    model.train(data, host_split, batch_size=B, neg_sampler_name=cfg["sampler"], num_neg=k, max_batches=K)
+    model.train(data, host_split, batch_size=B, neg_sampler_name=cfg["sampler"], num_neg=k)
     e1.record()
     barrier()
+    assert model.last_epoch_stats == {"batches": K, "examples": K * B}, model.last_epoch_stats
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    h2d = sum(v.numel() * v.element_size() for v in host_split["train"].values())
+    h2d = sum(v.numel() * v.element_size() for v in host_split["train"].values()) // world
     e2e = {"value": pairs / (e2e_ms / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d // K,
-           "d2h_bytes_per_step": 8 // K if K <= 8 else 1, "ms_per_step": e2e_ms / K,
-           "note": "BaseModel.train(host split_edge): H2D of all positive edges + per-epoch sampler + K steps + "
-                   "loss D2H; bytes are the per-epoch copies divided by K"}
+           "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms / K,
+           "note": "one BaseModel.train(data, split_edge) call whose split_edge (pinned HOST tensors) holds exactly "
+                   "K full batches per rank: H2D of the positive edges, GPU negative sampling, K optimisation "
+                   "steps, D2H of the epoch loss (one 8-byte read per call, not per step)"}
 
     # ---- instrumented pass: per-kernel durations (rank 0) ------------------------------------
     # every rank runs the pass (its steps contain collectives); only rank 0 records events
@@ -335,7 +344,7 @@ def run_ours(args):
                                            f"dp{world} over edge batches, encoder replicated, flat grad all-reduce")},
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roof, "kernels": kernels[:12], "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -402,7 +411,16 @@ def run_reference(args):
                                    f"batch={B} positives/step", "requested_steps": K, "requested_warmup": W},
             "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_OUT = None
+
+
+def emit(line):
+    out = _OUT if _OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -415,6 +433,12 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: keep a private handle to the real stdout and point fd 1
+    # at stderr so that library banners (e.g. "NCCL version ...") cannot pollute it
+    global _OUT
+    _OUT = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -83,6 +83,20 @@ __device__ __forceinline__ void put_chunk(uint8_t* hi, uint8_t* lo, int off, con
     if (SPLIT) *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
 }
 
+// operand tiles are streamed once per CTA: read-only path, do not allocate in L1 (the L1 / shared-memory
+// SRAM bandwidth is the bottleneck of this kernel)
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+    float4 r;
+#ifdef PLNLP_GEMM_LDG_ALLOCATE
+    r = __ldg(reinterpret_cast<const float4*>(p));
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+#endif
+    return r;
+}
+
 // Per-thread view of one operand's slabs.  Everything that does not change from slab to slab (row
 // pointers, row validity, shared-memory offsets) is computed once; per slab the loader only bumps the
 // pointers -- the loader warps are instruction-issue bound, every hoisted instruction counts.
@@ -132,7 +146,7 @@ struct Loader {
                 const int lim = kleft - kq4[i];
                 if (VEC) {
                     if (nrow[i] && lim > 0) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(ptr[i]));
+                        const float4 t = ld_stream4(ptr[i]);
                         reg[i][0] = t.x; reg[i][1] = t.y; reg[i][2] = t.z; reg[i][3] = t.w;
                     } else {
                         reg[i][0] = reg[i][1] = reg[i][2] = reg[i][3] = 0.0f;
@@ -149,7 +163,7 @@ struct Loader {
                     const bool kok = (kq4[i] + j) < kleft;
                     if (VEC) {
                         if (kok && nrow[i]) {
-                            const float4 t = __ldg(reinterpret_cast<const float4*>(q));
+                            const float4 t = ld_stream4(q);
                             d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
                         } else {
                             d[0] = d[1] = d[2] = d[3] = 0.0f;

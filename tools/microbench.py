@@ -151,3 +151,40 @@ def gemm_epilogues():
 
 if __name__ == "__main__" and "epi" in sys.argv:
     gemm_epilogues()
+
+
+def collab_dot():
+    """BASELINE config 3 shape: DOT head over a 241 MB h (does not fit L2): fused gather+dot forward and
+    the sorted-scatter backward against the gather roofline (fwd 2*H*4+12 B/pair, bwd +4*H*4)."""
+    N, H, P = 235868, 256, 131072
+    h = torch.randn(N, H, device=DEV)
+    edges = torch.randint(0, N, (P, 2), device=DEV)
+    ds = torch.randn(P, device=DEV)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=DEV)
+    ms = timeit(lambda: _ops.edge_dot_raw(h, edges), flush=flush)
+    by = P * (2 * H * 4 + 12)
+    print(f"[edge_dot fwd collab-shape] {ms:.4f} ms -> {by/ms/1e6:.0f} GB/s ({by/ms/1e6/HBM*100:.0f}% of HBM)")
+    for mode in ("sorted", "atomic"):
+        ms = timeit(lambda: _ops.edge_scatter_raw(h, edges, dscore=ds, mode=mode), flush=flush)
+        by = P * (4 * H * 4 + 20) + N * H * 4
+        print(f"[edge_dot bwd {mode} collab-shape] {ms:.4f} ms -> {by/ms/1e6:.0f} GB/s ({by/ms/1e6/HBM*100:.0f}% of HBM; "
+              f"includes the N*H*4 dense grad_h write)")
+
+
+def sweep():
+    """BASELINE config 5 (subset): power-law graphs, source matrix >= 4x L2, fp32 SpMM forward"""
+    for E, N in ((10_000_000, 2_000_000), (50_000_000, 4_000_000)):
+        ei = powerlaw_graph(N, E, 5)
+        adj = CSRGraph.from_edge_index(ei, None, N)
+        for F in (64, 128, 256, 512):
+            if N * F * 4 > 12e9:
+                continue
+            bench_spmm(f"powerlaw E={E//1_000_000}M N={N//1_000_000}M", adj, F, "sum", None)
+        del adj
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__" and "collab" in sys.argv:
+    collab_dot()
+if __name__ == "__main__" and "sweep" in sys.argv:
+    sweep()
