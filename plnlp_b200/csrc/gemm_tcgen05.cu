@@ -83,11 +83,11 @@ __device__ __forceinline__ void put_chunk(uint8_t* hi, uint8_t* lo, int off, con
     if (SPLIT) *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
 }
 
-// operand tiles are streamed once per CTA: read-only path, do not allocate in L1 (the L1 / shared-memory
-// SRAM bandwidth is the bottleneck of this kernel)
+// operand tile loads: plain read-only path.  (L1::no_allocate was measured 6 % SLOWER on B200 for this
+// kernel -- 0.94 vs 0.88 ms at 262144x512x512 -- so it is kept only behind a macro.)
 __device__ __forceinline__ float4 ld_stream4(const float* p) {
     float4 r;
-#ifdef PLNLP_GEMM_LDG_ALLOCATE
+#ifndef PLNLP_GEMM_LDG_NO_ALLOCATE
     r = __ldg(reinterpret_cast<const float4*>(p));
 #else
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
