@@ -104,6 +104,14 @@ int plnlp_gemm_tf32(int passes, int transa, int transb, int64_t M, int64_t N, in
                     const float* aux, int64_t ldaux, float drop_p, uint64_t seed,
                     float* workspace, int64_t workspace_bytes, int split_k, void* stream);
 
+/* Same again with CTA pairs (tcgen05.mma.cta_group::2, csrc/gemm_tcgen05_2cta.cu): two SMs share one
+ * 256 x 256 tile, each staging half of the B operand. */
+int plnlp_gemm_tf32_2cta(int passes, int transa, int transb, int64_t M, int64_t N, int64_t K,
+                         const float* A, int64_t lda, const float* B, int64_t ldb,
+                         float* C, int64_t ldc, float beta, const float* bias, int act,
+                         const float* aux, int64_t ldaux, float drop_p, uint64_t seed,
+                         float* workspace, int64_t workspace_bytes, int split_k, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Edge scoring (replaces h[edge[0]], h[edge[1]] advanced indexing + MLPPredictor /
  * DotPredictor, model.py:152-156,180 and layer.py:80-87,174-176).

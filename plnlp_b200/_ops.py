@@ -95,13 +95,13 @@ def gemm_raw(A, B, transa=False, transb=False, C=None, beta=0.0, bias=None, act=
     backend = backend or GEMM_BACKEND
     if backend != "ffma" and (K < 32 or M * N < 128 * 128):
         backend = "ffma"                      # too small to fill one tensor-core tile
-    bn = 128 if backend == "ffma" or N <= 128 else 256
+    bn = 128 if backend == "ffma" or (N <= 128 and not backend.endswith("c2")) else 256
     if split_k is None:
         tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
         split_k = 1
         if tiles < 148 and K >= 2048:
             split_k = int(min(max(1, (2 * 148) // tiles), K // 512, 64))
-    if backend == "tf32x3":
+    if backend in ("tf32x3", "tf32x3c2"):
         # the tensor core accumulates with round-toward-zero: keep K per accumulator <= 1024 and
         # let the split-k reduction (RN adds on the CUDA cores) combine the partials
         split_k = max(split_k, (K + 1023) // 1024)
@@ -113,10 +113,13 @@ def gemm_raw(A, B, transa=False, transb=False, C=None, beta=0.0, bias=None, act=
     tail = (int(transa), int(transb), M, N, K, ptr(A), _ld(A), ptr(B), _ld(B), ptr(C), _ld(C),
             float(beta), ptr(bias), int(act), ptr(aux), _ld(aux) if aux is not None else 0,
             float(drop_p), int(seed), ptr(ws), ws_bytes, int(split_k), stream())
-    name = {"ffma": "gemm_f32", "tf32x3": "gemm_tf32x3", "tf32": "gemm_tf32"}[backend]
+    name = {"ffma": "gemm_f32", "tf32x3": "gemm_tf32x3", "tf32": "gemm_tf32", "tf32x3c2": "gemm_tf32x3_2cta",
+            "tf32c2": "gemm_tf32_2cta"}[backend]
     with profiling.span(f"{name} {M}x{N}x{K}{' splitk' if split_k > 1 else ''}", 0, 2 * M * N * K):
         if backend == "ffma":
             check(lib.plnlp_gemm_f32(*tail), "plnlp_gemm_f32")
+        elif backend.endswith("c2"):
+            check(lib.plnlp_gemm_tf32_2cta(3 if backend == "tf32x3c2" else 1, *tail), "plnlp_gemm_tf32_2cta")
         else:
             check(lib.plnlp_gemm_tf32(3 if backend == "tf32x3" else 1, *tail), "plnlp_gemm_tf32")
     return C

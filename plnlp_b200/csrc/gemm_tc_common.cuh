@@ -1,0 +1,280 @@
+// Shared pieces of the tcgen05 TF32 GEMM kernels (gemm_tcgen05.cu: one CTA per tile, cta_group::1;
+// gemm_tcgen05_2cta.cu: CTA pairs, cta_group::2): parameters, the K-major shared-memory tile layout, the
+// loader that splits fp32 operands into tf32 hi/lo parts, and the scalar epilogue.  See gemm_tcgen05.cu
+// for the layout description.
+#pragma once
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace plnlp {
+namespace tcgemm {
+
+
+constexpr int TBM = 128;           // CTA tile rows  (UMMA M)
+constexpr int TBK = 16;            // k-slab (fp32 elements)
+constexpr int KQ = TBK / 4;        // 16-byte k-chunks per row per slab
+constexpr int LOADERS = 256;       // threads of warps 0-7
+constexpr int NTHREADS = 288;
+
+struct TcGemmParams {
+    int64_t M, N, K;
+    const float* A; int64_t lda;
+    const float* B; int64_t ldb;
+    float* C; int64_t ldc;
+    float beta;
+    const float* bias;
+    int act;
+    const float* aux; int64_t ldaux;
+    float drop_p; uint64_t seed;
+    float* ws;
+    int split_k;
+    int64_t k_per_split;
+    int passes;                    // 1 or 3
+};
+
+__host__ __device__ constexpr int tile_lbo(int rows) { return 18 * rows + 32; }
+constexpr int TILE_SBO = 144;
+__host__ __device__ constexpr int slot_bytes(int rows) { return KQ * tile_lbo(rows); }
+// 16-byte register chunks a loader thread holds for one operand slab
+__host__ __device__ constexpr int nreg(int rows, bool mn) {
+    return mn ? 4 * (((rows / 4) * KQ + LOADERS - 1) / LOADERS) : (rows * KQ) / LOADERS;
+}
+
+// one 16-byte chunk of an operand tile -> shared memory (hi and, when SPLIT, lo parts)
+template <bool SPLIT>
+__device__ __forceinline__ void put_chunk(uint8_t* hi, uint8_t* lo, int off, const float (&v)[4]) {
+    float h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        h[e] = tc::to_tf32(v[e]);
+        l[e] = v[e] - h[e];
+    }
+    *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+    if (SPLIT) *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+}
+
+// operand tile loads: plain read-only path.  (L1::no_allocate was measured 6 % SLOWER on B200 for this
+// kernel -- 0.94 vs 0.88 ms at 262144x512x512 -- so it is kept only behind a macro.)
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+    float4 r;
+#ifndef PLNLP_GEMM_LDG_NO_ALLOCATE
+    r = __ldg(reinterpret_cast<const float4*>(p));
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+#endif
+    return r;
+}
+
+// Per-thread view of one operand's slabs.  Everything that does not change from slab to slab (row
+// pointers, row validity, shared-memory offsets) is computed once; per slab the loader only bumps the
+// pointers -- the loader warps are instruction-issue bound, every hoisted instruction counts.
+//  MN = false (K-contiguous source, element (r, k) at src[r*ld + k]):
+//       chunk c = tid + 256*i: kq = c % KQ, r = c / KQ; reg[i] = 4 consecutive k of row r
+//  MN = true  (MN-contiguous source, element (r, k) at src[k*ld + r]):
+//       block b = tid + 256*i: rg = b % (R/4), kq = b / (R/4); reg[4*i + j] = rows rg*4..+3 at k = kq*4 + j
+template <int R, bool MN, bool VEC>
+struct Loader {
+    static constexpr int NR = nreg(R, MN);
+    static constexpr int NP = MN ? NR / 4 : NR;
+    const float* ptr[NP];
+    int soff[NP];       // byte offset of the chunk (MN: of row rg*4, rows +1..+3 follow at +16 B)
+    int kq4[NP];        // first k of the chunk inside the slab
+    int nrow[NP];       // MN scalar path: valid rows of the block (<= 4); otherwise 0/1 row validity
+    int64_t step;       // elements between consecutive slabs
+
+    __device__ __forceinline__ void init(const float* src, int64_t ld, int64_t r0, int64_t rows, int64_t kbeg,
+                                         int tid) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            const int c = tid + LOADERS * i;
+            if (!MN) {
+                const int kq = c % KQ, r = c / KQ;
+                kq4[i] = kq * 4;
+                nrow[i] = (r0 + r) < rows ? 1 : 0;
+                soff[i] = kq * tile_lbo(R) + (r >> 3) * TILE_SBO + (r & 7) * 16;
+                ptr[i] = src + (r0 + r) * ld + kbeg + kq * 4;
+            } else {
+                const int rg = c % (R / 4), kq = c / (R / 4);
+                const bool live = c < (R / 4) * KQ;
+                const int64_t left = rows - (r0 + rg * 4);
+                kq4[i] = kq * 4;
+                nrow[i] = !live ? 0 : (left >= 4 ? 4 : (left > 0 ? static_cast<int>(left) : 0));
+                soff[i] = kq * tile_lbo(R) + ((rg * 4) >> 3) * TILE_SBO + ((rg * 4) & 7) * 16;
+                ptr[i] = src + (kbeg + kq * 4) * ld + r0 + rg * 4;
+            }
+        }
+        step = MN ? ld * TBK : TBK;
+    }
+
+    // kleft = kend - k0 of the slab being fetched (<= 0: nothing left, zero fill)
+    __device__ __forceinline__ void fetch(int kleft, float (&reg)[NR][4]) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            if (!MN) {
+                const int lim = kleft - kq4[i];
+                if (VEC) {
+                    if (nrow[i] && lim > 0) {
+                        const float4 t = ld_stream4(ptr[i]);
+                        reg[i][0] = t.x; reg[i][1] = t.y; reg[i][2] = t.z; reg[i][3] = t.w;
+                    } else {
+                        reg[i][0] = reg[i][1] = reg[i][2] = reg[i][3] = 0.0f;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) reg[i][e] = (nrow[i] && e < lim) ? __ldg(ptr[i] + e) : 0.0f;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float* q = ptr[i] + j * (step / TBK);
+                    float (&d)[4] = reg[4 * i + j];
+                    const bool kok = (kq4[i] + j) < kleft;
+                    if (VEC) {
+                        if (kok && nrow[i]) {
+                            const float4 t = ld_stream4(q);
+                            d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+                        } else {
+                            d[0] = d[1] = d[2] = d[3] = 0.0f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) d[e] = (kok && e < nrow[i]) ? __ldg(q + e) : 0.0f;
+                    }
+                }
+            }
+            ptr[i] += step;
+        }
+    }
+
+    template <bool SPLIT>
+    __device__ __forceinline__ void stash(uint8_t* hi, uint8_t* lo, const float (&reg)[NR][4]) const {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            if (!MN) {
+                put_chunk<SPLIT>(hi, lo, soff[i], reg[i]);
+            } else {
+                if ((((R / 4) * KQ) % LOADERS != 0) && (threadIdx.x + LOADERS * i >= (R / 4) * KQ)) continue;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {      // row rg*4 + e gets (k%4 = 0..3) from the 4 loads
+                    const float v[4] = {reg[4 * i + 0][e], reg[4 * i + 1][e], reg[4 * i + 2][e], reg[4 * i + 3][e]};
+                    put_chunk<SPLIT>(hi, lo, soff[i] + e * 16, v);
+                }
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ float tc_epilogue_one(const TcGemmParams& p, int64_t r, int64_t c, float v) {
+    if (p.beta != 0.0f) v += p.beta * p.C[r * p.ldc + c];
+    if (p.bias) v += __ldg(p.bias + c);
+    if (p.act == PLNLP_ACT_RELU) {
+        v = fmaxf(v, 0.0f);
+        if (p.drop_p > 0.0f)
+            v = dropout_keep(p.seed, static_cast<uint64_t>(r) * p.N + c, p.drop_p) ? v * (1.0f / (1.0f - p.drop_p)) : 0.0f;
+    } else if (p.act == PLNLP_ACT_RELU_GRAD) {
+        v = (__ldg(p.aux + r * p.ldaux + c) > 0.0f) ? v * (1.0f / (1.0f - p.drop_p)) : 0.0f;
+    }
+    return v;
+}
+
+
+// Epilogue of one CTA tile, executed by warps 0-7 after the accumulator barrier: thread (warp q = w%4,
+// lane) owns accumulator row q*32 + lane; warps 0-3 / 4-7 take the two column halves.  Split-k partial
+// store, or beta*C + bias -> relu -> dropout / relu-grad mask.
+template <int BN>
+__device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t tmem_d, int64_t m0, int64_t n0,
+                                                 int n_mma, int n_iter, int warp, int lane) {
+    const int q = warp & 3, half = warp >> 2;
+    const int64_t r = m0 + q * 32 + lane;
+    const bool split = p.split_k > 1;
+    const bool plain = p.beta == 0.0f && p.bias == nullptr && p.act == PLNLP_ACT_NONE;
+    const float keep_scale = 1.0f / (1.0f - p.drop_p);
+    const bool vec_epi = (p.N % 4 == 0) && (p.ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(p.C) % 16 == 0) &&
+                         (!p.bias || reinterpret_cast<uintptr_t>(p.bias) % 16 == 0) &&
+                         (!p.aux || ((p.ldaux % 4 == 0) && reinterpret_cast<uintptr_t>(p.aux) % 16 == 0));
+    float* wsz = split ? p.ws + static_cast<int64_t>(blockIdx.z) * p.M * p.N : nullptr;
+    for (int cb = half * (BN / 2); cb < (half + 1) * (BN / 2); cb += 32) {
+        if (cb >= n_mma) break;                                   // warp-uniform
+        float v[32];
+        if (n_iter > 0) {
+            tc::tmem_ld_32x32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(cb), v);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = 0.0f;
+        }
+        if (r < p.M) {
+            const int64_t c0 = n0 + cb;
+            if (split) {
+                float* dst = wsz + r * p.N + c0;
+                if ((p.N % 4 == 0) && c0 + 31 < p.N) {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (c0 + e < p.N) dst[e] = v[e];
+                }
+            } else {
+                if (!plain) {
+                    if (vec_epi && c0 + 31 < p.N) {
+                        // 4 columns at a time: 16-byte loads of C / bias / aux, one Philox block per
+                        // group (element r*N + c uses word c%4 of block (r*N + c)/4 -- the same
+                        // stream as dropout_keep, a quarter of the hashing)
+                        const float* crow = p.C + r * p.ldc + c0;
+                        const float* arow = p.aux ? p.aux + r * p.ldaux + c0 : nullptr;
+                        const uint64_t ebase = static_cast<uint64_t>(r) * p.N + c0;
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            float x[4] = {v[e], v[e + 1], v[e + 2], v[e + 3]};
+                            if (p.beta != 0.0f) {
+                                const float4 c4 = *reinterpret_cast<const float4*>(crow + e);
+                                x[0] += p.beta * c4.x; x[1] += p.beta * c4.y;
+                                x[2] += p.beta * c4.z; x[3] += p.beta * c4.w;
+                            }
+                            if (p.bias) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + e));
+                                x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w;
+                            }
+                            if (p.act == PLNLP_ACT_RELU) {
+                                bool keep[4] = {true, true, true, true};
+                                if (p.drop_p > 0.0f) dropout_keep4(p.seed, ebase + e, p.drop_p, keep);
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) x[t] = keep[t] ? fmaxf(x[t], 0.0f) * keep_scale : 0.0f;
+                            } else if (p.act == PLNLP_ACT_RELU_GRAD) {
+                                const float4 a4 = __ldg(reinterpret_cast<const float4*>(arow + e));
+                                x[0] = a4.x > 0.0f ? x[0] * keep_scale : 0.0f;
+                                x[1] = a4.y > 0.0f ? x[1] * keep_scale : 0.0f;
+                                x[2] = a4.z > 0.0f ? x[2] * keep_scale : 0.0f;
+                                x[3] = a4.w > 0.0f ? x[3] * keep_scale : 0.0f;
+                            }
+                            v[e] = x[0]; v[e + 1] = x[1]; v[e + 2] = x[2]; v[e + 3] = x[3];
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            if (c0 + e < p.N) v[e] = tc_epilogue_one(p, r, c0 + e, v[e]);
+                    }
+                }
+                float* dst = p.C + r * p.ldc + c0;
+                if ((p.ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(p.C) % 16 == 0) && c0 + 31 < p.N) {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (c0 + e < p.N) dst[e] = v[e];
+                }
+            }
+        }
+    }
+}
+
+// split-k partial reduction + epilogue (defined in gemm_tcgen05.cu)
+int tc_splitk_reduce(const TcGemmParams& p, cudaStream_t st);
+
+}  // namespace tcgemm
+}  // namespace plnlp

@@ -1,0 +1,244 @@
+// Tensor-core GEMM for sm_100a with CTA PAIRS: tcgen05.mma.cta_group::2 kind::tf32.
+//
+// Same contract, operand layout, loader and epilogue as gemm_tcgen05.cu (see there); what changes is
+// who multiplies what.  A cluster of two CTAs (the two SMs of one TPC) computes one 256 x 256 output
+// tile: CTA r of the pair stages ITS 128 rows of A and ITS HALF (<= 128 rows) of the B tile; the leader
+// CTA (cluster rank 0) issues one M = 256 MMA per k-step that reads both CTAs' shared memory and
+// writes 128 accumulator rows into each CTA's TMEM.  Per unit of work every SM now reads / converts /
+// stores half as much of B -- the kernel is bound by the L1 / shared-memory SRAM bandwidth
+// (DESIGN.md), so this is where the time goes.
+//
+// Synchronisation per ring stage s (both CTAs run the same code):
+//   loaders (256 threads / CTA): wait empty[s] (local) -> st.shared tiles -> fence.proxy.async ->
+//                                arrive full[s] (local, count 256)
+//   CTA 1, warp 8 (relay)      : wait full[s] -> ONE remote arrive (release.cluster) on the leader's peer[s]
+//   CTA 0, warp 8 (MMA issuer) : wait full[s] and peer[s] (acquire.cluster) -> tcgen05.mma.cta_group::2 x
+//                                k-steps x passes -> tcgen05.commit multicast to empty[s] of BOTH CTAs
+//   last k-slab                : commit multicast to accum of both CTAs -> each CTA runs the epilogue for
+//                                its own 128 rows.
+#include "gemm_tc_common.cuh"
+
+namespace plnlp {
+
+namespace {
+
+using namespace tcgemm;
+
+constexpr int BN2 = 256;     // pair tile columns (UMMA N, TMEM columns per CTA)
+constexpr int BH2 = 128;     // B rows staged per CTA
+
+template <bool SPLIT>
+struct Cfg2 {
+    static constexpr int STAGES = SPLIT ? 3 : 6;      // 2 CTAs per SM share the 227 KB
+};
+
+template <bool AMN, bool BMN, bool VA, bool VB, bool SPLIT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 2)
+    gemm_tcgen05_2cta_kernel(const TcGemmParams p) {
+    constexpr int STAGES = Cfg2<SPLIT>::STAGES;
+    constexpr int A_SLOT = slot_bytes(TBM), B_SLOT = slot_bytes(BH2);
+    constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_SLOT + B_SLOT);
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES], peer_bar[STAGES], empty_bar[STAGES], accum_bar;
+    __shared__ uint32_t tmem_holder;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const int64_t m0 = static_cast<int64_t>(blockIdx.x >> 1) * (2 * TBM) + rank * TBM;
+    const int64_t n0 = static_cast<int64_t>(blockIdx.y) * BN2;
+    const int64_t kbeg = static_cast<int64_t>(blockIdx.z) * p.k_per_split;
+    const int64_t kend = min(p.K, kbeg + p.k_per_split);
+    const int n_iter = static_cast<int>((kend - kbeg + TBK - 1) / TBK);
+    const int64_t n_rem = ((p.N - n0 + 15) / 16) * 16;
+    const int n_mma = n_rem < BN2 ? static_cast<int>(n_rem) : BN2;     // multiple of 16
+    const int bhalf = n_mma / 2;                                       // B rows this CTA supplies
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(&full_bar[s], LOADERS);
+            tc::mbar_init(&peer_bar[s], 1);
+            tc::mbar_init(&empty_bar[s], 1);
+        }
+        tc::mbar_init(&accum_bar, 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 8) tc::tmem_alloc_2cta<BN2>(&tmem_holder);
+    tc::fence_before_sync();
+    tc::cluster_sync();              // barriers of BOTH CTAs are initialised before anyone signals them
+    tc::fence_after_sync();
+    const uint32_t tmem_d = tmem_holder;
+
+    auto stage_ptr = [&](int s, int which) -> uint8_t* {  // which: 0 A.hi, 1 B.hi, 2 A.lo, 3 B.lo
+        uint8_t* base = smem + s * STAGE_BYTES;
+        return base + (which & 1 ? A_SLOT : 0) + (which & 2 ? (A_SLOT + B_SLOT) : 0);
+    };
+
+    if (warp < 8) {
+        // ============================ loaders ============================
+        float ra[2][nreg(TBM, AMN)][4], rb[2][nreg(BH2, BMN)][4];
+        Loader<TBM, AMN, VA> la;
+        Loader<BH2, BMN, VB> lb;
+        const int64_t b0 = n0 + static_cast<int64_t>(rank) * bhalf;
+        const int64_t b_end = (b0 + bhalf) < p.N ? (b0 + bhalf) : p.N;   // rows past this CTA's half are zero
+        la.init(p.A, p.lda, m0, p.M, kbeg, tid);
+        lb.init(p.B, p.ldb, b0, b_end, kbeg, tid);
+        const int ktot = static_cast<int>(kend - kbeg);
+        auto fetch = [&](int it, float (&a)[nreg(TBM, AMN)][4], float (&b)[nreg(BH2, BMN)][4]) {
+            if (it < n_iter) {
+                la.fetch(ktot - it * TBK, a);
+                lb.fetch(ktot - it * TBK, b);
+            }
+        };
+        auto publish = [&](int it, const float (&a)[nreg(TBM, AMN)][4], const float (&b)[nreg(BH2, BMN)][4]) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            tc::mbar_wait(&empty_bar[s], ph ^ 1);
+            la.template stash<SPLIT>(stage_ptr(s, 0), stage_ptr(s, 2), a);
+            lb.template stash<SPLIT>(stage_ptr(s, 1), stage_ptr(s, 3), b);
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(&full_bar[s]);
+        };
+        fetch(0, ra[0], rb[0]);
+        fetch(1, ra[1], rb[1]);
+        for (int it = 0; it < n_iter; it += 2) {
+            publish(it, ra[0], rb[0]);
+            fetch(it + 2, ra[0], rb[0]);
+            if (it + 1 < n_iter) {
+                publish(it + 1, ra[1], rb[1]);
+                fetch(it + 3, ra[1], rb[1]);
+            }
+        }
+    } else if (rank == 0) {
+        // ============================ MMA issuer (leader CTA) ============================
+        const uint32_t idesc = tc::make_idesc_tf32(2 * TBM, n_mma, 0, 0);
+        constexpr uint32_t A_LBO = tile_lbo(TBM), B_LBO = tile_lbo(BH2);
+        constexpr uint32_t A_STEP = 2 * A_LBO, B_STEP = 2 * B_LBO;
+        for (int it = 0; it < n_iter; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            tc::mbar_wait(&full_bar[s], ph);
+            tc::mbar_wait_cluster(&peer_bar[s], ph);
+            tc::fence_after_sync();
+            if (lane == 0) {
+                const uint32_t a_hi = tc::smem_u32(stage_ptr(s, 0)), b_hi = tc::smem_u32(stage_ptr(s, 1));
+                const uint32_t a_lo = tc::smem_u32(stage_ptr(s, 2)), b_lo = tc::smem_u32(stage_ptr(s, 3));
+#pragma unroll
+                for (int j = 0; j < TBK / 8; ++j) {
+                    const uint64_t dah = tc::make_smem_desc(a_hi + j * A_STEP, A_LBO, TILE_SBO);
+                    const uint64_t dbh = tc::make_smem_desc(b_hi + j * B_STEP, B_LBO, TILE_SBO);
+                    tc::mma_tf32_ss_2cta(tmem_d, dah, dbh, idesc, (it | j) != 0);
+                    if (SPLIT) {
+                        const uint64_t dal = tc::make_smem_desc(a_lo + j * A_STEP, A_LBO, TILE_SBO);
+                        const uint64_t dbl = tc::make_smem_desc(b_lo + j * B_STEP, B_LBO, TILE_SBO);
+                        tc::mma_tf32_ss_2cta(tmem_d, dah, dbl, idesc, 1u);
+                        tc::mma_tf32_ss_2cta(tmem_d, dal, dbh, idesc, 1u);
+                    }
+                }
+                tc::mma_commit_2cta(&empty_bar[s], 3);
+                if (it == n_iter - 1) tc::mma_commit_2cta(&accum_bar, 3);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ============================ relay (peer CTA) ============================
+        for (int it = 0; it < n_iter; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            tc::mbar_wait(&full_bar[s], ph);
+            if (lane == 0) tc::mbar_arrive_remote(&peer_bar[s], 0);
+            __syncwarp();
+        }
+    }
+
+    // ============================ epilogue (warps 0-7 of each CTA, its own 128 rows) ============
+    if (warp < 8) {
+        if (n_iter > 0) {
+            tc::mbar_wait(&accum_bar, 0);
+            tc::fence_after_sync();
+        }
+        tc_epilogue_tile<BN2>(p, tmem_d, m0, n0, n_mma, n_iter, warp, lane);
+    }
+    tc::fence_before_sync();
+    tc::cluster_sync();              // the peer's shared memory / TMEM stay alive until both are done
+    if (warp == 8) tc::tmem_dealloc_2cta<BN2>(tmem_d);
+}
+
+template <bool AMN, bool BMN, bool VA, bool VB, bool SPLIT>
+int launch_one2(const TcGemmParams& p, dim3 grid, cudaStream_t st) {
+    constexpr int bytes = Cfg2<SPLIT>::STAGES * (SPLIT ? 2 : 1) * (slot_bytes(TBM) + slot_bytes(BH2));
+    static_assert(bytes <= 113 * 1024, "two CTAs per SM");
+    auto kern = gemm_tcgen05_2cta_kernel<AMN, BMN, VA, VB, SPLIT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        configured = true;
+    }
+    kern<<<grid, NTHREADS, bytes, st>>>(p);
+    return 0;
+}
+
+template <bool AMN, bool BMN>
+int launch_vec2(const TcGemmParams& p, bool va, bool vb, dim3 grid, cudaStream_t st) {
+    const bool split = p.passes == 3;
+    if (va && vb) {
+        return split ? launch_one2<AMN, BMN, true, true, true>(p, grid, st)
+                     : launch_one2<AMN, BMN, true, true, false>(p, grid, st);
+    }
+    if (va) return launch_one2<AMN, BMN, true, false, true>(p, grid, st);
+    if (vb) return launch_one2<AMN, BMN, false, true, true>(p, grid, st);
+    return launch_one2<AMN, BMN, false, false, true>(p, grid, st);
+}
+
+}  // namespace
+}  // namespace plnlp
+
+extern "C" int plnlp_gemm_tf32_2cta(int passes, int transa, int transb, int64_t M, int64_t N, int64_t K,
+                                    const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                                    int64_t ldc, float beta, const float* bias, int act, const float* aux,
+                                    int64_t ldaux, float drop_p, uint64_t seed, float* workspace,
+                                    int64_t workspace_bytes, int split_k, void* stream) {
+    using namespace plnlp;
+    using namespace plnlp::tcgemm;
+    PLNLP_REQUIRE(passes == 1 || passes == 3, PLNLP_E_UNSUPPORTED);
+    PLNLP_REQUIRE(M >= 0 && N >= 0 && K >= 0, PLNLP_E_SIZE);
+    if (M == 0 || N == 0) return 0;
+    PLNLP_REQUIRE(A && B && C, PLNLP_E_NULL);
+    PLNLP_REQUIRE(lda >= (transa ? M : K) && ldb >= (transb ? K : N) && ldc >= N, PLNLP_E_SIZE);
+    PLNLP_REQUIRE(act >= 0 && act <= 2 && drop_p >= 0.0f && drop_p < 1.0f, PLNLP_E_SIZE);
+    if (act == PLNLP_ACT_RELU_GRAD) PLNLP_REQUIRE(aux && ldaux >= N, PLNLP_E_NULL);
+    if (split_k < 1 || K == 0) split_k = 1;
+    TcGemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
+    p.beta = beta; p.bias = bias; p.act = act; p.aux = aux; p.ldaux = ldaux; p.drop_p = drop_p; p.seed = seed;
+    p.passes = passes;
+    int64_t kper = ceil_div(ceil_div(K, split_k), TBK) * TBK;
+    if (kper == 0) kper = TBK;
+    p.k_per_split = kper;
+    p.split_k = split_k = static_cast<int>(K == 0 ? 1 : ceil_div(K, kper));
+    p.ws = workspace;
+    if (split_k > 1) {
+        PLNLP_REQUIRE(workspace, PLNLP_E_NULL);
+        PLNLP_REQUIRE(workspace_bytes >= static_cast<int64_t>(split_k) * M * N * 4, PLNLP_E_WORKSPACE);
+        PLNLP_REQUIRE(aligned(workspace, 16), PLNLP_E_ALIGN);
+    }
+    const bool amn = transa != 0, bmn = transb == 0;
+    const bool va = aligned(A, 16) && (lda % 4 == 0) && ((transa ? M : K) % 4 == 0);
+    const bool vb = aligned(B, 16) && (ldb % 4 == 0) && ((transb ? K : N) % 4 == 0);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // grid.x = 2 CTAs per 256-row pair tile (cluster dimension 2 along x)
+    const dim3 grid(static_cast<unsigned>(2 * ceil_div(M, 2 * TBM)), static_cast<unsigned>(ceil_div(N, BN2)),
+                    static_cast<unsigned>(split_k));
+    int rc;
+    if (!amn && !bmn) rc = launch_vec2<false, false>(p, va, vb, grid, st);
+    else if (!amn && bmn) rc = launch_vec2<false, true>(p, va, vb, grid, st);
+    else if (amn && !bmn) rc = launch_vec2<true, false>(p, va, vb, grid, st);
+    else rc = launch_vec2<true, true>(p, va, vb, grid, st);
+    if (rc != 0) return rc;
+    PLNLP_LAUNCH_CHECK();
+    if (split_k > 1) {
+        // the split-k reduction (and its epilogue) is shared with the 1-CTA kernel
+        return tc_splitk_reduce(p, st);
+    }
+    return 0;
+}

@@ -413,3 +413,32 @@ def test_gemm_tf32x3_splitk(ops):
     outs = [ops.gemm_raw(A.cuda(), B.cuda(), transa=True, split_k=9, backend="tf32x3").cpu() for _ in range(2)]
     assert torch.equal(outs[0], outs[1])
     assert rel_err(outs[0], A.double().t() @ B.double()) < TOL
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 32), (128, 256, 64), (512, 512, 512), (4267, 512, 512),
+                                   (300, 200, 178), (129, 257, 50), (512, 512, 4100), (1000, 72, 96)])
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])
+def test_gemm_tf32x3_2cta_layouts(ops, M, N, K, ta, tb):
+    """CTA-pair (cta_group::2) variant: same bar, every layout, ragged M / N / K"""
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    A = torch.randn((K, M) if ta else (M, K), generator=g)
+    B = torch.randn((N, K) if tb else (K, N), generator=g)
+    got = ops.gemm_raw(A.cuda(), B.cuda(), transa=ta, transb=tb, backend="tf32x3c2").cpu()
+    want = ((A.t() if ta else A).double() @ (B.t() if tb else B).double())
+    assert rel_err(got, want) < TOL, rel_err(got, want)
+
+
+def test_gemm_tf32x3_2cta_epilogues_and_splitk(ops):
+    g = torch.Generator().manual_seed(6)
+    A, W = torch.randn(1000, 512, generator=g), torch.randn(384, 512, generator=g)
+    bias, C0 = torch.randn(384, generator=g), torch.randn(1000, 384, generator=g)
+    want = A.double() @ W.double().t()
+    C = C0.clone().cuda()
+    ops.gemm_raw(A.cuda(), W.cuda(), transb=True, C=C, beta=1.0, bias=bias.cuda(), act=ops.ACT_RELU, backend="tf32x3c2")
+    assert rel_err(C.cpu(), torch.relu(want + C0.double() + bias.double())) < TOL
+    d1 = ops.gemm_raw(A.cuda(), W.cuda(), transb=True, act=ops.ACT_RELU, drop_p=0.3, seed=99, backend="tf32x3c2")
+    d2 = ops.gemm_raw(A.cuda(), W.cuda(), transb=True, act=ops.ACT_RELU, drop_p=0.3, seed=99, backend="ffma")
+    assert torch.equal(d1 == 0, d2 == 0) and rel_err(d1, d2) < TOL
+    X, Y = torch.randn(30000, 512, generator=g), torch.randn(30000, 512, generator=g)
+    outs = [ops.gemm_raw(X.cuda(), Y.cuda(), transa=True, backend="tf32x3c2").cpu() for _ in range(2)]
+    assert torch.equal(outs[0], outs[1]) and rel_err(outs[0], X.double().t() @ Y.double()) < TOL

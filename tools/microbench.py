@@ -88,7 +88,7 @@ def ddi():
     bench_spmm("ddi", adj, H, "mean", None)
     bench_spmm("ddi(L2 flushed)", adj, H, "mean", flush)
     P = B * (1 + k)
-    for be in (["ffma"] if "noffma" not in sys.argv else []) + ["tf32x3", "tf32"]:
+    for be in (["ffma"] if "noffma" not in sys.argv else []) + ["tf32x3", "tf32x3c2", "tf32", "tf32c2"]:
         bench_gemm(N, H, H, backend=be)
         bench_gemm(P, H, H, backend=be)                       # predictor layer 1 fwd
         bench_gemm(P, H, H, tb=False, backend=be)             # dA0 = dZ1 @ W1
