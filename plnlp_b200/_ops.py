@@ -20,9 +20,10 @@ LOSS_KINDS = {"AUC": 0, "HingeAUC": 1, "WeightedHingeAUC": 2}
 # or "atomic" (red.global.add, order non-deterministic)
 SCATTER_MODE = "sorted"
 
-# dense-layer backend: "tf32x3" = tcgen05 tensor cores with error-compensated 3xTF32 (fp32 parity,
-# default), "tf32" = plain TF32 tensor cores (fast path, ~1e-3 relative), "ffma" = exact fp32 CUDA cores
-GEMM_BACKEND = os.environ.get("PLNLP_GEMM", "tf32x3")
+# dense-layer backend: "tf32x3c2" = tcgen05 tensor cores, CTA pairs (cta_group::2), error-compensated
+# 3xTF32 (fp32 parity, default); "tf32x3" = the same with one CTA per tile; "tf32c2" / "tf32" = plain TF32
+# (fast path, ~1e-3 relative, stated separately); "ffma" = exact fp32 on the CUDA cores
+GEMM_BACKEND = os.environ.get("PLNLP_GEMM", "tf32x3c2")
 
 
 def _f32c(t):
