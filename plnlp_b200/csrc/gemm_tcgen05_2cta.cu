@@ -95,7 +95,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 2)
             tc::mbar_wait(&empty_bar[s], ph ^ 1);
             la.template stash<SPLIT>(stage_ptr(s, 0), stage_ptr(s, 2), a);
             lb.template stash<SPLIT>(stage_ptr(s, 1), stage_ptr(s, 3), b);
+#ifndef PLNLP_CONSUMER_SIDE_PROXY_FENCE
             tc::fence_proxy_async_smem();
+#endif
             tc::mbar_arrive(&full_bar[s]);
         };
         fetch(0, ra[0], rb[0]);
@@ -118,6 +120,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 2)
             const uint32_t ph = (it / STAGES) & 1;
             tc::mbar_wait(&full_bar[s], ph);
             tc::mbar_wait_cluster(&peer_bar[s], ph);
+#ifdef PLNLP_CONSUMER_SIDE_PROXY_FENCE
+            tc::fence_proxy_async_smem();     // EXPERIMENT: proxy fence on the consumer side only
+#endif
             tc::fence_after_sync();
             if (lane == 0) {
                 const uint32_t a_hi = tc::smem_u32(stage_ptr(s, 0)), b_hi = tc::smem_u32(stage_ptr(s, 1));
