@@ -35,6 +35,12 @@ WORKLOADS = {
     "ddi": dict(name="ddi-shape", N=4267, E=1067911, feats=0, emb=512, hid=512, gnn_layers=2, mlp_layers=2,
                 encoder="SAGE", predictor="MLP", loss="AUC", sampler="global", num_neg=3, batch=65536,
                 dropout=0.3, clip=2.0, use_feats=False, directed=False),
+    # BASELINE.json configs[2] / SURVEY.md 8d config 3: the training pairs of every epoch come from the
+    # random-walk augmentation (main.py:228-253, README.md:35), walk_length 10 from both endpoints
+    "collab": dict(name="collab-shape", N=235868, E=1285465, feats=0, emb=256, hid=256, gnn_layers=1, mlp_layers=2,
+                   encoder="SAGE", predictor="DOT", loss="WeightedHingeAUC", sampler="global", num_neg=1,
+                   batch=65536, dropout=0.3, clip=1.0, use_feats=False, directed=False, powerlaw=True,
+                   weighted=True, walk_length=10),
     # BASELINE.json configs[3] / SURVEY.md 8d config 4
     "citation2": dict(name="citation2-shape", N=2927963, E=30561187, feats=128, emb=50, hid=200, gnn_layers=2,
                       mlp_layers=2, encoder="GCN", predictor="MLP", loss="AUC", sampler="local", num_neg=3,
@@ -62,7 +68,11 @@ def make_edges(cfg, device, seed=0):
     N, E = cfg["N"], cfg["E"]
     if not cfg["directed"]:
         lo = torch.randint(0, N, (int(E * 1.3),), generator=g, device=device)
-        hi = torch.randint(0, N, (int(E * 1.3),), generator=g, device=device)
+        if cfg.get("powerlaw"):      # collab-shape: power-law degrees (alpha ~ 2.1)
+            perm = torch.randperm(N, generator=g, device=device)
+            hi = perm[(N * torch.rand(int(E * 1.3), generator=g, device=device).pow(2.1)).long().clamp(max=N - 1)]
+        else:
+            hi = torch.randint(0, N, (int(E * 1.3),), generator=g, device=device)
         key = torch.unique(torch.minimum(lo, hi) * N + torch.maximum(lo, hi))
         key = key[torch.div(key, N, rounding_mode="floor") != key % N]
         key = key[torch.randperm(key.numel(), generator=g, device=device)[:E]]
@@ -88,7 +98,12 @@ def build_workload(cfg, device, graph_cls, normalize):
         split = {"train": {"source_node": ei[0].contiguous(), "target_node": ei[1].contiguous()}}
     else:
         und = torch.cat([ei, ei.flip(0)], 1)
-        adj = graph_cls.from_edge_index(und, None, N)
+        w = None
+        if cfg.get("weighted"):      # collab-shape: integer collaboration counts 1..5 (ignored by SAGE's mean)
+            gw = torch.Generator(device=device).manual_seed(2)
+            w1 = torch.randint(1, 6, (ei.size(1),), generator=gw, device=device).float()
+            w = torch.cat([w1, w1])
+        adj = graph_cls.from_edge_index(und, w, N)
         row, col, _ = adj.coo()
         data.edge_index = torch.stack([col, row], 0)
         split = {"train": {"edge": ei.t().contiguous()}}
@@ -217,16 +232,37 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    rw_len = cfg.get("walk_length", 0)
+
+    def rw_epoch(edges, n_pairs):
+        """random-walk augmentation (main.py:228-253): walks from both endpoints of `edges`, expanded to
+        weighted (start, visited) pairs; exactly n_pairs of them are kept"""
+        from plnlp_b200 import augment
+        pairs, wgt = augment.random_walk_pairs(data.adj_t, edges.reshape(-1), rw_len)
+        assert pairs.size(0) >= n_pairs, (pairs.size(0), n_pairs)
+        return pairs[:n_pairs].contiguous(), wgt[:n_pairs].contiguous()
+
+    def n_seed_edges(n_pairs):      # each seed edge yields 2 walks x rw_len pairs, a few are self pairs
+        return int(n_pairs / (2 * rw_len) * 1.15) + 64
+
     def device_steps(n, seed_shift):
-        """n steps on HBM-resident edges; negatives for exactly these n batches sampled on the GPU"""
+        """n steps on HBM-resident edges; the per-epoch producers of exactly these n batches (random-walk
+        augmentation where the recipe has it, negative sampling) run on the GPU inside the call"""
         g = torch.Generator(device=device).manual_seed(1000 + seed_shift + rank)
-        idx = torch.randint(0, E, (n * B,), generator=g, device=device)
-        sub = {"train": {"edge": pos_all[idx]}}
+        if rw_len:
+            idx = torch.randint(0, E, (n_seed_edges(n * B),), generator=g, device=device)
+            pos_e, wgt = rw_epoch(pos_all[idx], n * B)
+            sub = {"train": {"edge": pos_e, "weight": wgt}}
+        else:
+            idx = torch.randint(0, E, (n * B,), generator=g, device=device)
+            sub = {"train": {"edge": pos_all[idx]}}
+            wgt = None
         pos, neg = get_pos_neg_edges("train", sub, edge_index=data.edge_index, num_nodes=cfg["N"],
                                      neg_sampler_name=cfg["sampler"], num_neg=k, device=device)
         model.encoder.train(); model.predictor.train()
         for i in range(n):
-            model.train_batch(data, pos[i * B:(i + 1) * B], neg[i * B:(i + 1) * B].reshape(-1, 2), k)
+            model.train_batch(data, pos[i * B:(i + 1) * B], neg[i * B:(i + 1) * B].reshape(-1, 2), k,
+                              None if wgt is None else wgt[i * B:(i + 1) * B])
 
     # ---- value: device-resident ------------------------------------------------------------
     clk = ClockSampler(local).start()
@@ -256,16 +292,25 @@ def run_ours(args):
     # the "epoch" handed to train() holds exactly K (resp. W) full batches per rank, in pinned host memory
     def host_epoch(n_steps, seed):
         g = torch.Generator().manual_seed(seed)
-        idx = torch.randint(0, E, (n_steps * B * world,), generator=g)
+        n = n_seed_edges(n_steps * B) if rw_len else n_steps * B * world
+        idx = torch.randint(0, E, (n,), generator=g)
         return {"train": {kk: v.cpu()[idx].contiguous().pin_memory() for kk, v in split["train"].items()}}
 
+    def public_epoch(hs, n_steps):
+        """what main.py does per epoch: [random-walk augmentation of the train edges ->] BaseModel.train"""
+        if rw_len:
+            assert world == 1, "the collab-shape workload is single-GPU (north_star: smaller graphs stay single-GPU)"
+            pos_e, wgt = rw_epoch(hs["train"]["edge"].to(device, non_blocking=True), n_steps * B)
+            hs = {"train": {"edge": pos_e, "weight": wgt}}
+        return model.train(data, hs, batch_size=B, neg_sampler_name=cfg["sampler"], num_neg=k)
+
     warm_split, host_split = host_epoch(W, 11), host_epoch(K, 12)
-    model.train(data, warm_split, batch_size=B, neg_sampler_name=cfg["sampler"], num_neg=k)
-    model.train(data, host_split, batch_size=B, neg_sampler_name=cfg["sampler"], num_neg=k)   # allocator warm-up
+    public_epoch(warm_split, W)
+    public_epoch(host_split, K)                                   # allocator warm-up with the K-step sizes
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    model.train(data, host_split, batch_size=B, neg_sampler_name=cfg["sampler"], num_neg=k)
+    public_epoch(host_split, K)
     e1.record()
     barrier()
     assert model.last_epoch_stats == {"batches": K, "examples": K * B}, model.last_epoch_stats
@@ -370,7 +415,8 @@ def cpu_baseline(cfg, steps=2):
         idx = torch.randint(0, pos_all.size(0), (B,), generator=g)
         pos = pos_all[idx]
         neg = torch.stack([pos[:, :1].expand(B, k), torch.randint(0, N, (B, k), generator=g)], -1)
-        m.step(data.x, data.adj_t, pos, neg, k)
+        wgt = (1.0 / torch.randint(1, 11, (B,), generator=g).float()) if cfg["loss"] == "WeightedHingeAUC" else None
+        m.step(data.x, data.adj_t, pos, neg, k, wgt)
 
     one()                                    # warm-up (allocator, MKL)
     t0 = time.perf_counter()

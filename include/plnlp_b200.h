@@ -211,6 +211,20 @@ int plnlp_count_greater_f32(const float* pos, int64_t n, const float* thresh,
 int plnlp_mrr_counts_f32(const float* pos, const float* neg, int64_t ldn, int64_t S, int64_t K,
                          int32_t* gt, int32_t* ge, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Random-walk augmentation (replaces torch_cluster.random_walk and the pair /
+ * weight assembly of main.py:228-233, 241-253).  rowptr / col: the reference's int64 CSR arrays.
+ */
+/* walk [n_walks, L+1]: walk[n,0] = start[n]; each step moves to col[rowptr[cur] + floor(u*deg)] (stays
+ * put when deg == 0).  rand [n_walks, L] supplies the uniforms u in [0,1) (parity tests), or NULL:
+ * Philox4x32-10(seed). */
+int plnlp_random_walk(const int64_t* rowptr, const int64_t* col, const int64_t* start, int64_t n_walks,
+                      int walk_length, const float* rand, uint64_t seed, int64_t* walk, void* stream);
+/* pairs [L*n_walks, 2] (j-major: all walks for j = 0, then j = 1, ...) = (walk[n,0], walk[n,j+1]),
+ * weight = 1/(j+1), keep = 0 for self pairs (main.py:244-253). */
+int plnlp_walk_pairs(const int64_t* walk, int64_t n_walks, int walk_length, int64_t* pairs, float* weight,
+                     uint8_t* keep, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,8 @@ SIGNATURES = {
     "plnlp_kth_largest_f32": (c_int, [_P, _L, _L, _P, _P, _L, _P]),
     "plnlp_count_greater_f32": (c_int, [_P, _L, _P, _P, _P]),
     "plnlp_mrr_counts_f32": (c_int, [_P, _P, _L, _L, _L, _P, _P, _P]),
+    "plnlp_random_walk": (c_int, [_P, _P, _P, _L, _I, _P, _U, _P, _P]),
+    "plnlp_walk_pairs": (c_int, [_P, _L, _I, _P, _P, _P, _P]),
 }
 
 _ERRORS = {-1: "required pointer is NULL", -2: "bad size", -3: "misaligned pointer / leading dimension",

@@ -442,3 +442,41 @@ def test_gemm_tf32x3_2cta_epilogues_and_splitk(ops):
     X, Y = torch.randn(30000, 512, generator=g), torch.randn(30000, 512, generator=g)
     outs = [ops.gemm_raw(X.cuda(), Y.cuda(), transa=True, backend="tf32x3c2").cpu() for _ in range(2)]
     assert torch.equal(outs[0], outs[1]) and rel_err(outs[0], X.double().t() @ Y.double()) < TOL
+
+
+# ------------------------------------------------------------------ random-walk augmentation
+def test_random_walk_bit_exact_with_supplied_uniforms(ops):
+    from oracle import rw
+    from plnlp_b200 import augment
+    N = 500
+    ei, _ = rand_graph(N, 3000, seed=31, hub=True)                 # has isolated nodes (deg 0: stay put)
+    adj = sparse.to_sparse_tensor(ei, None, N)
+    rowptr, col, _ = adj.csr()
+    g = torch.Generator().manual_seed(4)
+    start = torch.randint(0, N, (4000,), generator=g)
+    rand = torch.rand(4000, 10, generator=g)
+    want = rw.random_walk(rowptr, col, start, 10, rand)
+    got = augment.random_walk(None, col.cuda(), start.cuda(), 10, rowptr=rowptr.cuda(), rand=rand.cuda())
+    assert torch.equal(got.cpu(), want)                             # index work: bit-exact
+    pw, ww = rw.walk_pairs(want)
+    pg, wg = augment.walk_pairs(got)
+    assert torch.equal(pg.cpu(), pw) and torch.equal(wg.cpu(), ww)
+
+
+def test_random_walk_philox_statistics(ops):
+    from plnlp_b200 import augment
+    from plnlp_b200.graph import CSRGraph
+    torch.manual_seed(5)
+    N = 64
+    src = torch.arange(N).repeat_interleave(N - 1)
+    dst = torch.stack([torch.cat([torch.arange(i), torch.arange(i + 1, N)]) for i in range(N)]).reshape(-1)
+    adj = CSRGraph.from_edge_index(torch.stack([src, dst]).cuda(), None, N)       # complete graph
+    start = torch.zeros(200000, dtype=torch.int64, device="cuda")
+    walk = augment.random_walk(None, adj.csr()[1], start, 3, rowptr=adj.csr()[0])
+    assert walk.shape == (200000, 4) and (walk[:, 0] == 0).all()
+    assert (walk[:, 1:] != walk[:, :-1]).all()                      # no self loops in the graph -> always moves
+    counts = torch.bincount(walk[:, 1], minlength=N).double().cpu()[1:]
+    chi2 = ((counts - counts.mean()) ** 2 / counts.mean()).sum().item()
+    assert chi2 < (N - 1) + 6 * (2 * (N - 1)) ** 0.5               # first step uniform over the 63 neighbours
+    edges, w = augment.random_walk_pairs(adj, start[:1000], 5)
+    assert edges.shape[1] == 2 and (edges[:, 0] != edges[:, 1]).all() and w.numel() == edges.size(0)

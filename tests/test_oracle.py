@@ -209,3 +209,26 @@ def test_train_replay_matches_reference(golden_dir, tag):
     pv, nv = plnlp_ref.eval_edges("valid", R["split"])
     assert rel_err(m.predict(R["x"], adj, pv), R["scores"]["pos_valid"]) < 5e-5
     assert rel_err(m.predict(R["x"], adj, nv), R["scores"]["neg_valid"]) < 5e-5
+
+
+def test_random_walk_oracle_bruteforce():
+    from oracle import rw
+    N = 30
+    ei, _ = rand_graph(N, 120, seed=8)
+    adj = sparse.to_sparse_tensor(ei, None, N)
+    rowptr, col, _ = adj.csr()
+    g = torch.Generator().manual_seed(3)
+    start = torch.randint(0, N, (50,), generator=g)
+    rand = torch.rand(50, 6, generator=g)
+    walk = rw.random_walk(rowptr, col, start, 6, rand)
+    for n in range(50):                      # python loop over every step
+        cur = int(start[n])
+        assert int(walk[n, 0]) == cur
+        for l in range(6):
+            b, e = int(rowptr[cur]), int(rowptr[cur + 1])
+            if e > b:
+                cur = int(col[b + min(int(float(rand[n, l]) * (e - b)), e - b - 1)])
+            assert int(walk[n, l + 1]) == cur
+    pairs, w = rw.walk_pairs(walk)
+    assert (pairs[:, 0] != pairs[:, 1]).all() and pairs.size(0) == w.numel()
+    assert set(w.tolist()) <= {float(torch.tensor(1.0) / (j + 1)) for j in range(6)}
