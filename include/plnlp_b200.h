@@ -119,6 +119,15 @@ int plnlp_gemm_tf32_2cta(int passes, int transa, int transb, int64_t M, int64_t 
  * a negative node index i addresses row n_rows + i, like the python indexing it replaces
  * (model.py:191-194 appends a mean row so that index -1 resolves).
  */
+/* FUSED forward of the 2-layer MLP head over gathered endpoints (model.py:152-156 + layer.py:80-87):
+ *   a0 = h[src_p] * h[dst_p]               gathered inside the GEMM's operand loader, never written to HBM
+ *   a1 = dropout(relu(a0 @ W1^T + b1))     tcgen05 CTA-pair GEMM; stored to `a1` [P, N1] only if a1 != NULL
+ *   score_part[q*score_ld + p] = a1[p, cols of partial q] . w2,   q in [0, 2*ceil(N1/256))
+ * the caller adds the partials in index order plus the output bias.  passes as plnlp_gemm_tf32. */
+int plnlp_edge_mlp_fwd_tf32(int passes, const float* h, int64_t ldh, int64_t n_rows, const int64_t* edges,
+                            int64_t P, int64_t H, const float* W1, int64_t ldw, const float* b1, int64_t N1,
+                            float drop_p, uint64_t seed, const float* w2, float* a1, int64_t lda1,
+                            float* score_part, int64_t score_ld, void* stream);
 /* out[p, :] = h[src_p, :] * h[dst_p, :] */
 int plnlp_gather_hadamard_f32(const float* h, int64_t ldh, int64_t n_rows, const int64_t* edges, int64_t P, int64_t H,
                               float* out, int64_t ldo, void* stream);

@@ -25,6 +25,9 @@ SCATTER_MODE = "sorted"
 # (fast path, ~1e-3 relative, stated separately); "ffma" = exact fp32 on the CUDA cores
 GEMM_BACKEND = os.environ.get("PLNLP_GEMM", "tf32x3c2")
 
+# fused edge scoring for the MLP head (gather + Hadamard + layer 1 + out layer in one tcgen05 kernel)
+FUSED_EDGE_MLP = os.environ.get("PLNLP_FUSED_EDGE", "1") != "0"
+
 
 def _f32c(t):
     if t.dtype != torch.float32:
@@ -166,6 +169,37 @@ def gather_hadamard_raw(h, edges):
         check(lib.plnlp_gather_hadamard_f32(ptr(h), _ld(h), h.size(0), ptr(edges), P, H, ptr(out), H, stream()),
               "plnlp_gather_hadamard_f32")
     return out
+
+
+def fused_edge_mlp_ok(h, params):
+    """the fused forward covers the reference recipes' head: MLPPredictor with ONE hidden layer
+    (mlp_num_layers = 2) on a tensor-core backend, hidden width <= 1024"""
+    if not FUSED_EDGE_MLP or GEMM_BACKEND not in ("tf32x3c2", "tf32c2") or len(params) != 4:
+        return False
+    W1, w2 = params[0], params[2]
+    return (W1.dim() == 2 and W1.size(1) == h.size(1) and w2.numel() == W1.size(0) and h.size(1) <= 1024
+            and h.size(1) >= 32 and W1.stride(1) == 1)
+
+
+def edge_mlp_fwd_raw(h, edges, W1, b1, w2, b2, drop_p=0.0, seed=0, need_a1=True):
+    """fused gather + Hadamard + Linear/relu/dropout + Linear(->1): -> (score [P], a1 [P, N1] or None)"""
+    lib = _lib.load()
+    h, edges, W1 = _rowmajor(h), _edges_i64(edges), _rowmajor(W1)
+    w2 = _f32c(w2).reshape(-1).contiguous()
+    P, H, N1 = edges.size(0), h.size(1), W1.size(0)
+    nq = 2 * ((N1 + 255) // 256)
+    part = torch.empty(nq, P, dtype=torch.float32, device=h.device)
+    a1 = torch.empty(P, N1, dtype=torch.float32, device=h.device) if need_a1 else None
+    passes = 3 if GEMM_BACKEND == "tf32x3c2" else 1
+    with profiling.span(f"edge_mlp_fwd_fused {P}x{N1}x{H}", 0, 2 * P * N1 * H):
+        check(lib.plnlp_edge_mlp_fwd_tf32(passes, ptr(h), _ld(h), h.size(0), ptr(edges), P, H, ptr(W1), _ld(W1),
+                                          ptr(b1), N1, float(drop_p), int(seed), ptr(w2), ptr(a1),
+                                          N1 if need_a1 else 0, ptr(part), P, stream()),
+              "plnlp_edge_mlp_fwd_tf32")
+    score = part[0].clone() if nq == 1 else part.sum(0)        # fixed order: partial 0 + 1 + 2 + ...
+    if b2 is not None:
+        score = score + b2.reshape(())
+    return score, a1
 
 
 def edge_dot_raw(h, edges):
@@ -435,23 +469,29 @@ class EdgeScoreLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, edges, weight, head, kind, num_neg, n_pos, drop_p, seed, *params):
         edges = _edges_i64(edges)
-        drops = []
+        fused = False
         if head == "DOT":
             score = edge_dot_raw(h, edges)
             acts = []
         else:
             L = len(params) // 2
-            a = gather_hadamard_raw(h, edges)
-            acts = [a]
-            for i in range(L - 1):
-                s = seed + 7919 * (i + 1)
-                a = gemm_raw(a, params[2 * i], transb=True, bias=params[2 * i + 1], act=ACT_RELU,
-                             drop_p=drop_p, seed=s)
-                acts.append(a)
-                drops.append(s)
-            score = mlp_out_fwd_raw(a, params[2 * (L - 1)], params[2 * (L - 1) + 1])
+            fused = fused_edge_mlp_ok(h, params)
+            if fused:
+                # ONE kernel: gather + Hadamard + layer 1 (tcgen05) + bias/relu/dropout + the out layer's dot;
+                # the Hadamard product a0 is never written to HBM (backward re-gathers it)
+                score, a1 = edge_mlp_fwd_raw(h, edges, params[0], params[1], params[2], params[3], drop_p,
+                                             seed + 7919, need_a1=True)
+                acts = [a1]
+            else:
+                a = gather_hadamard_raw(h, edges)
+                acts = [a]
+                for i in range(L - 1):
+                    a = gemm_raw(a, params[2 * i], transb=True, bias=params[2 * i + 1], act=ACT_RELU,
+                                 drop_p=drop_p, seed=seed + 7919 * (i + 1))
+                    acts.append(a)
+                score = mlp_out_fwd_raw(a, params[2 * (L - 1)], params[2 * (L - 1) + 1])
         loss, dpos, dneg = pair_loss_raw(kind, score[:n_pos], score[n_pos:], num_neg, weight)
-        ctx.head, ctx.drop_p, ctx.n_params = head, drop_p, len(params)
+        ctx.head, ctx.drop_p, ctx.n_params, ctx.fused = head, drop_p, len(params), fused
         ctx.save_for_backward(h, edges, dpos, dneg, *acts, *params)
         ctx.n_acts = len(acts)
         return loss.reshape(())
@@ -462,6 +502,8 @@ class EdgeScoreLoss(torch.autograd.Function):
         h, edges, dpos, dneg = saved[:4]
         acts = saved[4:4 + ctx.n_acts]
         params = saved[4 + ctx.n_acts:]
+        if ctx.fused:        # the forward never stored the Hadamard product: re-gather it for dW_0
+            acts = (gather_hadamard_raw(h, edges),) + tuple(acts)
         dscore = torch.cat([dpos, dneg]) * g
         if ctx.head == "DOT":
             gh = edge_scatter_raw(h, edges, dscore=dscore)

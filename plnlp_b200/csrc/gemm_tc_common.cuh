@@ -30,6 +30,12 @@ struct TcGemmParams {
     int split_k;
     int64_t k_per_split;
     int passes;                    // 1 or 3
+    // fused edge scoring (csrc/gemm_tcgen05_2cta.cu, plnlp_edge_mlp_fwd_tf32): when a_edges != NULL the A
+    // operand row p is the Hadamard product h[src_p, :] * h[dst_p, :] gathered on the fly (A = h, lda = ldh,
+    // a_rows = rows of h); when w_out != NULL the epilogue also accumulates score_part[q][r] = sum over
+    // this CTA's column half of C[r, c] * w_out[c]; C == NULL skips the store of C.
+    const int64_t* a_edges; int64_t a_rows;
+    const float* w_out; float* score_part; int64_t score_ld;
 };
 
 __host__ __device__ constexpr int tile_lbo(int rows) { return 18 * rows + 32; }
@@ -166,6 +172,69 @@ struct Loader {
     }
 };
 
+// A-operand provider of the fused edge-scoring kernel: slab tile row r is the Hadamard product of the two
+// endpoint embeddings of pair (r0 + r), gathered from h (K-contiguous, same chunk mapping and shared-memory
+// layout as Loader<R, false, VEC>).  Replaces h[edge[0]] * h[edge[1]] (model.py:155-156, layer.py:81)
+// without the [P, H] product ever existing in HBM.
+template <int R, bool VEC>
+struct GatherLoader {
+    static constexpr int NR = nreg(R, false);
+    const float* ps[NR];
+    const float* pd[NR];
+    int soff[NR];
+    int kq4[NR];
+    int nrow[NR];
+
+    __device__ __forceinline__ void init(const float* h, int64_t ldh, int64_t h_rows, const int64_t* edges,
+                                         int64_t r0, int64_t rows, int64_t kbeg, int tid) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const int c = tid + LOADERS * i;
+            const int kq = c % KQ, r = c / KQ;
+            const int64_t pr = r0 + r;
+            kq4[i] = kq * 4;
+            nrow[i] = pr < rows ? 1 : 0;
+            int64_t s = 0, d = 0;
+            if (nrow[i]) {
+                s = __ldg(edges + 2 * pr);
+                d = __ldg(edges + 2 * pr + 1);
+                if (s < 0) s += h_rows;
+                if (d < 0) d += h_rows;
+            }
+            soff[i] = kq * tile_lbo(R) + (r >> 3) * TILE_SBO + (r & 7) * 16;
+            ps[i] = h + s * ldh + kbeg + kq * 4;
+            pd[i] = h + d * ldh + kbeg + kq * 4;
+        }
+    }
+
+    __device__ __forceinline__ void fetch(int kleft, float (&reg)[NR][4]) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const int lim = kleft - kq4[i];
+            if (VEC) {
+                if (nrow[i] && lim > 0) {
+                    const float4 a = ld_stream4(ps[i]), b = ld_stream4(pd[i]);
+                    reg[i][0] = a.x * b.x; reg[i][1] = a.y * b.y; reg[i][2] = a.z * b.z; reg[i][3] = a.w * b.w;
+                } else {
+                    reg[i][0] = reg[i][1] = reg[i][2] = reg[i][3] = 0.0f;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    reg[i][e] = (nrow[i] && e < lim) ? __ldg(ps[i] + e) * __ldg(pd[i] + e) : 0.0f;
+            }
+            ps[i] += TBK;
+            pd[i] += TBK;
+        }
+    }
+
+    template <bool SPLIT>
+    __device__ __forceinline__ void stash(uint8_t* hi, uint8_t* lo, const float (&reg)[NR][4]) const {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) put_chunk<SPLIT>(hi, lo, soff[i], reg[i]);
+    }
+};
+
 __device__ __forceinline__ float tc_epilogue_one(const TcGemmParams& p, int64_t r, int64_t c, float v) {
     if (p.beta != 0.0f) v += p.beta * p.C[r * p.ldc + c];
     if (p.bias) v += __ldg(p.bias + c);
@@ -191,7 +260,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
     const bool split = p.split_k > 1;
     const bool plain = p.beta == 0.0f && p.bias == nullptr && p.act == PLNLP_ACT_NONE;
     const float keep_scale = 1.0f / (1.0f - p.drop_p);
-    const bool vec_epi = (p.N % 4 == 0) && (p.ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(p.C) % 16 == 0) &&
+    float score_part = 0.0f;
+    const bool vec_epi = (p.N % 4 == 0) && (!p.C || ((p.ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(p.C) % 16 == 0))) &&
                          (!p.bias || reinterpret_cast<uintptr_t>(p.bias) % 16 == 0) &&
                          (!p.aux || ((p.ldaux % 4 == 0) && reinterpret_cast<uintptr_t>(p.aux) % 16 == 0));
     float* wsz = split ? p.ws + static_cast<int64_t>(blockIdx.z) * p.M * p.N : nullptr;
@@ -258,19 +328,29 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
                             if (c0 + e < p.N) v[e] = tc_epilogue_one(p, r, c0 + e, v[e]);
                     }
                 }
-                float* dst = p.C + r * p.ldc + c0;
-                if ((p.ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(p.C) % 16 == 0) && c0 + 31 < p.N) {
-#pragma unroll
-                    for (int e = 0; e < 32; e += 4)
-                        *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-                } else {
+                if (p.w_out) {     // fused out_channels = 1 layer: this thread's share of a[r, :] . w_out
 #pragma unroll
                     for (int e = 0; e < 32; ++e)
-                        if (c0 + e < p.N) dst[e] = v[e];
+                        if (c0 + e < p.N) score_part = fmaf(v[e], __ldg(p.w_out + c0 + e), score_part);
+                }
+                if (p.C) {
+                    float* dst = p.C + r * p.ldc + c0;
+                    if ((p.ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(p.C) % 16 == 0) && c0 + 31 < p.N) {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4)
+                            *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            if (c0 + e < p.N) dst[e] = v[e];
+                    }
                 }
             }
         }
     }
+    // partial q = (column tile, column half): the caller adds the 2*ceil(N/BN) partials in index order
+    if (p.w_out && !split && r < p.M)
+        p.score_part[(static_cast<int64_t>(blockIdx.y) * 2 + half) * p.score_ld + r] = score_part;
 }
 
 // split-k partial reduction + epilogue (defined in gemm_tcgen05.cu)

@@ -16,6 +16,8 @@
 //                                k-steps x passes -> tcgen05.commit multicast to empty[s] of BOTH CTAs
 //   last k-slab                : commit multicast to accum of both CTAs -> each CTA runs the epilogue for
 //                                its own 128 rows.
+#include <type_traits>
+
 #include "gemm_tc_common.cuh"
 
 namespace plnlp {
@@ -32,7 +34,8 @@ struct Cfg2 {
     static constexpr int STAGES = SPLIT ? 3 : 6;      // 2 CTAs per SM share the 227 KB
 };
 
-template <bool AMN, bool BMN, bool VA, bool VB, bool SPLIT>
+// AGATHER: the A operand is gathered (GatherLoader): fused edge scoring, see plnlp_edge_mlp_fwd_tf32 below
+template <bool AMN, bool BMN, bool VA, bool VB, bool SPLIT, bool AGATHER = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 2)
     gemm_tcgen05_2cta_kernel(const TcGemmParams p) {
     constexpr int STAGES = Cfg2<SPLIT>::STAGES;
@@ -76,11 +79,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 2)
     if (warp < 8) {
         // ============================ loaders ============================
         float ra[2][nreg(TBM, AMN)][4], rb[2][nreg(BH2, BMN)][4];
-        Loader<TBM, AMN, VA> la;
+        typename std::conditional<AGATHER, GatherLoader<TBM, VA>, Loader<TBM, AMN, VA>>::type la;
         Loader<BH2, BMN, VB> lb;
         const int64_t b0 = n0 + static_cast<int64_t>(rank) * bhalf;
         const int64_t b_end = (b0 + bhalf) < p.N ? (b0 + bhalf) : p.N;   // rows past this CTA's half are zero
-        la.init(p.A, p.lda, m0, p.M, kbeg, tid);
+        if constexpr (AGATHER) la.init(p.A, p.lda, p.a_rows, p.a_edges, m0, p.M, kbeg, tid);
+        else la.init(p.A, p.lda, m0, p.M, kbeg, tid);
         lb.init(p.B, p.ldb, b0, b_end, kbeg, tid);
         const int ktot = static_cast<int>(kend - kbeg);
         auto fetch = [&](int it, float (&a)[nreg(TBM, AMN)][4], float (&b)[nreg(BH2, BMN)][4]) {
@@ -168,11 +172,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 2)
     if (warp == 8) tc::tmem_dealloc_2cta<BN2>(tmem_d);
 }
 
-template <bool AMN, bool BMN, bool VA, bool VB, bool SPLIT>
+template <bool AMN, bool BMN, bool VA, bool VB, bool SPLIT, bool AGATHER = false>
 int launch_one2(const TcGemmParams& p, dim3 grid, cudaStream_t st) {
     constexpr int bytes = Cfg2<SPLIT>::STAGES * (SPLIT ? 2 : 1) * (slot_bytes(TBM) + slot_bytes(BH2));
     static_assert(bytes <= 113 * 1024, "two CTAs per SM");
-    auto kern = gemm_tcgen05_2cta_kernel<AMN, BMN, VA, VB, SPLIT>;
+    auto kern = gemm_tcgen05_2cta_kernel<AMN, BMN, VA, VB, SPLIT, AGATHER>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -245,5 +249,46 @@ extern "C" int plnlp_gemm_tf32_2cta(int passes, int transa, int transb, int64_t 
         // the split-k reduction (and its epilogue) is shared with the 1-CTA kernel
         return tc_splitk_reduce(p, st);
     }
+    return 0;
+}
+
+
+// Fused edge scoring, MLP head forward (model.py:152-156 + layer.py:80-87 for the usual
+// 2-layer head): for every pair p
+//     a0 = h[src_p] * h[dst_p]                       gathered by the loader, never written to HBM
+//     a1 = dropout(relu(a0 @ W1^T + b1))             tensor cores; written to `a1` only if a1 != NULL
+//     score_part[q][p] = a1[p, cols of partial q] . w2
+// The caller adds the 2*ceil(N1/256) partials in index order and the output bias.
+extern "C" int plnlp_edge_mlp_fwd_tf32(int passes, const float* h, int64_t ldh, int64_t n_rows, const int64_t* edges,
+                                       int64_t P, int64_t H, const float* W1, int64_t ldw, const float* b1,
+                                       int64_t N1, float drop_p, uint64_t seed, const float* w2, float* a1,
+                                       int64_t lda1, float* score_part, int64_t score_ld, void* stream) {
+    using namespace plnlp;
+    using namespace plnlp::tcgemm;
+    PLNLP_REQUIRE(passes == 1 || passes == 3, PLNLP_E_UNSUPPORTED);
+    PLNLP_REQUIRE(P >= 0 && H > 0 && N1 > 0 && n_rows > 0, PLNLP_E_SIZE);
+    if (P == 0) return 0;
+    PLNLP_REQUIRE(h && edges && W1 && w2 && score_part, PLNLP_E_NULL);
+    PLNLP_REQUIRE(ldh >= H && ldw >= H && score_ld >= P && (!a1 || lda1 >= N1), PLNLP_E_SIZE);
+    PLNLP_REQUIRE(H <= 1024, PLNLP_E_UNSUPPORTED);     // one accumulator: keep K within the RZ error budget
+    PLNLP_REQUIRE(drop_p >= 0.0f && drop_p < 1.0f, PLNLP_E_SIZE);
+    TcGemmParams p{};
+    p.M = P; p.N = N1; p.K = H; p.A = h; p.lda = ldh; p.B = W1; p.ldb = ldw; p.C = a1; p.ldc = lda1;
+    p.beta = 0.0f; p.bias = b1; p.act = PLNLP_ACT_RELU; p.drop_p = drop_p; p.seed = seed; p.passes = passes;
+    p.split_k = 1; p.k_per_split = ceil_div(H, TBK) * TBK;
+    p.a_edges = edges; p.a_rows = n_rows; p.w_out = w2; p.score_part = score_part; p.score_ld = score_ld;
+    const bool va = aligned(h, 16) && (ldh % 4 == 0) && (H % 4 == 0);
+    const bool vb = aligned(W1, 16) && (ldw % 4 == 0) && (H % 4 == 0);
+    const dim3 grid(static_cast<unsigned>(2 * ceil_div(P, 2 * TBM)), static_cast<unsigned>(ceil_div(N1, BN2)), 1);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    if (va && vb) {
+        rc = passes == 3 ? launch_one2<false, false, true, true, true, true>(p, grid, st)
+                         : launch_one2<false, false, true, true, false, true>(p, grid, st);
+    } else {
+        rc = launch_one2<false, false, false, false, true, true>(p, grid, st);
+    }
+    if (rc != 0) return rc;
+    PLNLP_LAUNCH_CHECK();
     return 0;
 }

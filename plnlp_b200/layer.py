@@ -175,7 +175,15 @@ class MLPPredictor(torch.nn.Module):
         return self._tail(x_i * x_j)
 
     def score_edges(self, h, edges):
-        """predictor(h[edges[:,0]], h[edges[:,1]]) with the gather and Hadamard fused."""
+        """predictor(h[edges[:,0]], h[edges[:,1]]) with the gather and Hadamard fused.  Without autograd
+        (scoring in ``BaseModel.test``: up to 86.6 M pairs per split on citation2-shape) the whole head runs
+        as ONE kernel that neither materialises the Hadamard product nor stores the hidden activation."""
+        params = self.flat_params()
+        if not torch.is_grad_enabled() and self.lins[-1].out_features == 1 and _ops.fused_edge_mlp_ok(h, params):
+            p = self.dropout if self.training else 0.0
+            score, _ = _ops.edge_mlp_fwd_raw(h, edges, params[0], params[1], params[2], params[3], p,
+                                             _ops.new_seed() if p > 0 else 0, need_a1=False)
+            return score.reshape(-1, 1)
         return self._tail(_ops.GatherHadamard.apply(h, edges))
 
     def flat_params(self):
