@@ -480,3 +480,53 @@ def test_random_walk_philox_statistics(ops):
     assert chi2 < (N - 1) + 6 * (2 * (N - 1)) ** 0.5               # first step uniform over the 63 neighbours
     edges, w = augment.random_walk_pairs(adj, start[:1000], 5)
     assert edges.shape[1] == 2 and (edges[:, 0] != edges[:, 1]).all() and w.numel() == edges.size(0)
+
+
+# ------------------------------------------------------------------ fused edge scoring (MLP head)
+@pytest.mark.parametrize("N,H,P", [(77, 64, 300), (4267, 512, 5000), (999, 200, 1234), (500, 256, 257)])
+def test_fused_edge_mlp_forward(ops, N, H, P):
+    """gather + Hadamard + Linear/relu + Linear(->1) in one kernel vs the oracle predictor"""
+    g = torch.Generator().manual_seed(N + H)
+    h = torch.randn(N, H, generator=g)
+    edges = torch.randint(0, N, (P, 2), generator=g)
+    edges[1] = torch.tensor([-1, 3])
+    W1, b1 = torch.randn(H, H, generator=g) / H ** 0.5, torch.randn(H, generator=g)
+    w2, b2 = torch.randn(1, H, generator=g) / H ** 0.5, torch.randn(1, generator=g)
+    score, a1 = ops.edge_mlp_fwd_raw(h.cuda(), edges.cuda(), W1.cuda(), b1.cuda(), w2.cuda(), b2.cuda())
+    a0 = (h[edges[:, 0]] * h[edges[:, 1]]).double()
+    ref_a1 = torch.relu(a0 @ W1.double().t() + b1.double())
+    ref_s = (ref_a1 @ w2.double().t()).reshape(-1) + b2.double()
+    assert rel_err(a1.cpu(), ref_a1) < TOL
+    assert rel_err(score.cpu(), ref_s) < TOL
+    s2, none = ops.edge_mlp_fwd_raw(h.cuda(), edges.cuda(), W1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), need_a1=False)
+    assert none is None and torch.equal(s2, score)
+    # dropout: same Philox stream as the unfused GEMM epilogue
+    sd, ad = ops.edge_mlp_fwd_raw(h.cuda(), edges.cuda(), W1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), 0.3, 77)
+    a0g = ops.gather_hadamard_raw(h.cuda(), edges.cuda())
+    au = ops.gemm_raw(a0g, W1.cuda(), transb=True, bias=b1.cuda(), act=ops.ACT_RELU, drop_p=0.3, seed=77)
+    assert torch.equal(ad == 0, au == 0) and rel_err(ad, au) < TOL
+    assert rel_err(sd, ops.mlp_out_fwd_raw(au, w2.cuda(), b2.cuda())) < TOL
+
+
+def test_fused_and_unfused_step_agree(ops):
+    """EdgeScoreLoss with the fused forward vs the unfused kernels: same loss and gradients"""
+    g = torch.Generator().manual_seed(21)
+    N, H, B, k = 300, 128, 200, 3
+    h0 = torch.randn(N, H, generator=g)
+    pos, neg = torch.randint(0, N, (B, 2), generator=g), torch.randint(0, N, (B * k, 2), generator=g)
+    params0 = [torch.randn(H, H, generator=g) / H ** 0.5, torch.randn(H, generator=g),
+               torch.randn(1, H, generator=g) / H ** 0.5, torch.randn(1, generator=g)]
+    out = {}
+    for fused in (True, False):
+        ops.FUSED_EDGE_MLP = fused
+        try:
+            h = h0.cuda().requires_grad_(True)
+            params = [p.cuda().requires_grad_(True) for p in params0]
+            loss = ops.edge_score_loss(h, pos.cuda(), neg.cuda(), k, "AUC", head="MLP", params=params)
+            loss.backward()
+            out[fused] = [loss.detach(), h.grad] + [p.grad for p in params]
+        finally:
+            ops.FUSED_EDGE_MLP = True
+    floor = TOL * max(float(t.abs().max()) for t in out[False][1:])
+    for a, b in zip(out[True], out[False]):
+        assert rel_err(a, b) < 2e-5 or float((a - b).abs().max()) <= floor
