@@ -317,8 +317,16 @@ class SpMM(torch.autograd.Function):
     def forward(ctx, x, bias, adj, reduce, relu, drop_p, seed):
         st = structure_of(adj)
         mean = reduce == "mean"
-        plan = st.fwd_noval if mean else st.fwd
-        out = spmm_raw(plan, x, use_val=not mean, div_rows=mean, bias=bias, relu=relu, drop_p=drop_p, seed=seed)
+        ctx.dense = st.dense_ok and GEMM_BACKEND != "ffma" and x.size(1) >= 32
+        if ctx.dense:
+            # small, dense-ish adjacency (graph.Structure.dense_ok): multiply it as a dense matrix on the
+            # tensor cores; same epilogue and the same Philox indexing (row * F + col) as the gather kernel
+            out = gemm_raw(st.dense(mean), x, bias=bias, act=ACT_RELU if relu else ACT_NONE,
+                           drop_p=drop_p if relu else 0.0, seed=seed)
+        else:
+            plan = st.fwd_noval if mean else st.fwd
+            out = spmm_raw(plan, x, use_val=not mean, div_rows=mean, bias=bias, relu=relu, drop_p=drop_p,
+                           seed=seed)
         ctx.st, ctx.mean, ctx.relu, ctx.drop_p = st, mean, relu, drop_p
         ctx.has_bias = bias is not None
         ctx.save_for_backward(out if (relu or drop_p > 0) else None)
@@ -333,8 +341,11 @@ class SpMM(torch.autograd.Function):
         gb = colsum_raw(g) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
         gx = None
         if ctx.needs_input_grad[0]:
-            plan = ctx.st.bwd_mean if ctx.mean else ctx.st.bwd
-            gx = spmm_raw(plan, g, use_val=True if ctx.mean else ctx.st.has_value, div_rows=False)
+            if ctx.dense:
+                gx = gemm_raw(ctx.st.dense(ctx.mean), g, transa=True)          # A^T g on the tensor cores
+            else:
+                plan = ctx.st.bwd_mean if ctx.mean else ctx.st.bwd
+                gx = spmm_raw(plan, g, use_val=True if ctx.mean else ctx.st.has_value, div_rows=False)
         return gx, gb, None, None, None, None, None
 
 

@@ -530,3 +530,30 @@ def test_fused_and_unfused_step_agree(ops):
     floor = TOL * max(float(t.abs().max()) for t in out[False][1:])
     for a, b in zip(out[True], out[False]):
         assert rel_err(a, b) < 2e-5 or float((a - b).abs().max()) <= floor
+
+
+# ------------------------------------------------------------------ dense tensor-core path of the aggregation
+@pytest.mark.parametrize("weighted,reduce", [(False, "mean"), (True, "sum")])
+def test_dense_adjacency_path(ops, weighted, reduce):
+    """small dense-ish graphs (ddi-shape) aggregate through a dense tcgen05 GEMM: forward, backward and
+    the fused epilogue must match the oracle like the gather kernel does"""
+    from plnlp_b200.graph import structure_of
+    N, F = 300, 96
+    ei, w = rand_graph(N, 14000, seed=12, weighted=weighted, hub=True)          # ~15 % dense
+    o = sparse.to_sparse_tensor(ei, w, N)
+    g = _to_gpu_graph(o)
+    st = structure_of(g)
+    assert st.dense_ok and st.density > 0.06
+    x, gout, b = torch.randn(N, F), torch.randn(N, F), torch.randn(F)
+    xg, bg = x.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    out = ops.spmm(g, xg, reduce, bias=bg, relu=True)
+    out.backward(gout.cuda())
+    xc, bc = x.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.relu(sparse.matmul(o.set_value(None) if reduce == "mean" else o, xc, reduce) + bc)
+    ref.backward(gout)
+    assert rel_err(out.cpu(), ref) < TOL
+    assert rel_err(xg.grad.cpu(), xc.grad) < TOL and rel_err(bg.grad.cpu(), bc.grad) < TOL
+    # and it agrees with the gather kernel it replaces
+    plan = st.fwd_noval if reduce == "mean" else st.fwd
+    gk = ops.spmm_raw(plan, x.cuda(), use_val=reduce != "mean", div_rows=reduce == "mean")
+    assert rel_err(ops.spmm(g, x.cuda(), reduce), gk) < TOL
