@@ -271,7 +271,8 @@ def test_full_size_ddi_shape_properties():
     assert torch.equal(ax, _ops.spmm(adj, x, "mean"))
     ones = torch.ones(N, F, device=DEV)
     deg = adj.sum(dim=1)
-    assert rel_err(_ops.spmm(adj, ones, "mean")[deg > 0], ones[deg > 0]) < 1e-6
+    # (this graph is 11.7 % dense, so the aggregation runs on the dense 3xTF32 tensor-core path)
+    assert rel_err(_ops.spmm(adj, ones, "mean")[deg > 0], ones[deg > 0]) < TOL
     xr = x.clone().requires_grad_(True)
     _ops.spmm(adj, xr, "mean").backward(y)
     lhs = (ax.double() * y.double()).sum()
