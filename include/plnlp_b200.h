@@ -36,6 +36,13 @@ extern "C" {
 #define PLNLP_LOSS_AUC 0
 #define PLNLP_LOSS_HINGE_AUC 1
 #define PLNLP_LOSS_WEIGHTED_HINGE_AUC 2
+/* the remaining objectives of --loss_func (loss.py:17-28, 38-62) */
+#define PLNLP_LOSS_WEIGHTED_AUC 3
+#define PLNLP_LOSS_ADA_AUC 4
+#define PLNLP_LOSS_ADA_HINGE_AUC 5
+#define PLNLP_LOSS_LOG_RANK 6
+#define PLNLP_LOSS_CE 7
+#define PLNLP_LOSS_INFO_NCE 8
 
 /* GEMM epilogue activations */
 #define PLNLP_ACT_NONE 0

@@ -81,7 +81,29 @@ def pair_loss(kind, pos_out, neg_out, num_neg, weight=None):
     if kind == "WeightedHingeAUC":
         w = weight.reshape(-1, 1)
         return (w * (w - (p - n)).clamp(min=0).square()).sum()
+    if kind == "WeightedAUC":                      # loss.py:17-21
+        return (weight.reshape(-1, 1) * (1 - (p - n)).square()).sum()
+    if kind == "AdaAUC":                           # loss.py:24-28
+        return (weight.reshape(-1, 1) - (p - n)).square().sum()
+    if kind == "AdaHingeAUC":                      # loss.py:38-42
+        return (weight.reshape(-1, 1) - (p - n)).clamp(min=0).square().sum()
+    if kind == "LogRank":                          # loss.py:45-48
+        return -torch.log(torch.sigmoid(p - n) + 1e-15).mean()
+    if kind == "CE":                               # loss.py:51-54
+        return -torch.log(torch.sigmoid(pos_out) + 1e-15).mean() - torch.log(1 - torch.sigmoid(neg_out) + 1e-15).mean()
+    if kind == "InfoNCE":                          # loss.py:57-62
+        pe, ne = torch.exp(p), torch.exp(n).sum(1, keepdim=True)
+        return -torch.log(pe / (pe + ne) + 1e-15).mean()
     raise NotImplementedError(kind)
+
+
+def pair_loss_autograd(kind, pos_out, neg_out, num_neg, weight=None):
+    """(loss, d loss/d pos [B], d loss/d neg [B*num_neg]) through torch autograd, any kind"""
+    p = pos_out.detach().clone().reshape(-1).requires_grad_(True)
+    n = neg_out.detach().clone().reshape(-1).requires_grad_(True)
+    loss = pair_loss(kind, p, n, num_neg, weight)
+    gp, gn = torch.autograd.grad(loss, (p, n))
+    return loss.detach(), gp, gn
 
 
 def pair_loss_grad(kind, pos_out, neg_out, num_neg, weight=None):
@@ -106,10 +128,10 @@ def pair_loss_grad(kind, pos_out, neg_out, num_neg, weight=None):
 def select_loss(name, has_weight):
     """model.py:107-126 dispatch restricted to the in-scope losses: unknown names
     and weighted losses without a weight fall back to AUC."""
-    if name == "HingeAUC":
-        return "HingeAUC"
-    if name == "WeightedHingeAUC" and has_weight:
-        return "WeightedHingeAUC"
+    if name in ("CE", "InfoNCE", "LogRank", "HingeAUC"):
+        return name
+    if name in ("AdaAUC", "WeightedAUC", "AdaHingeAUC", "WeightedHingeAUC") and has_weight:
+        return name
     return "AUC"
 
 

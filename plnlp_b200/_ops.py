@@ -14,7 +14,8 @@ from ._lib import check, ptr, stream, workspace
 from .graph import structure_of
 
 ACT_NONE, ACT_RELU, ACT_RELU_GRAD = 0, 1, 2
-LOSS_KINDS = {"AUC": 0, "HingeAUC": 1, "WeightedHingeAUC": 2}
+LOSS_KINDS = {"AUC": 0, "HingeAUC": 1, "WeightedHingeAUC": 2, "WeightedAUC": 3, "AdaAUC": 4, "AdaHingeAUC": 5,
+              "LogRank": 6, "CE": 7, "InfoNCE": 8}
 
 # which scatter kernel backs the endpoint-gather backward: "sorted" (deterministic, default)
 # or "atomic" (red.global.add, order non-deterministic)

@@ -99,15 +99,13 @@ class BaseModel(object):
         return parts[0] if len(parts) == 1 else torch.cat(parts, dim=-1)
 
     def _loss_name(self, has_margin):
-        """model.py:107-126 restricted to the in-scope losses: weighted losses without a margin and
-        unknown names use AUC; out-of-scope names raise instead of silently changing objective."""
+        """the dispatch of model.py:107-126: margin / weight losses need split_edge['train']['weight'] and
+        fall back to AUC without it; unknown names are AUC"""
         name = self.loss_func_name
-        if name == 'HingeAUC':
-            return 'HingeAUC'
-        if name == 'WeightedHingeAUC':
-            return 'WeightedHingeAUC' if has_margin else 'AUC'
-        if name in ('CE', 'InfoNCE', 'LogRank') or (name in ('AdaAUC', 'WeightedAUC', 'AdaHingeAUC') and has_margin):
-            raise NotImplementedError(f"loss {name!r} is outside the hot-path scope (SURVEY.md section 8f)")
+        if name in ('CE', 'InfoNCE', 'LogRank', 'HingeAUC'):
+            return name
+        if name in ('AdaAUC', 'WeightedAUC', 'AdaHingeAUC', 'WeightedHingeAUC') and has_margin:
+            return name
         return 'AUC'
 
     def calculate_loss(self, pos_out, neg_out, num_neg, margin=None):
@@ -127,7 +125,7 @@ class BaseModel(object):
         head = 'DOT' if isinstance(self.predictor, DotPredictor) else 'MLP'
         p = self.predictor.dropout if (head == 'MLP' and self.predictor.training) else 0.0
         loss = _ops.edge_score_loss(h, pos_edge, neg_edge, num_neg, self._loss_name(weight_margin is not None),
-                                    weight=weight_margin if self.loss_func_name == 'WeightedHingeAUC' else None,
+                                    weight=weight_margin,
                                     head=head, params=self.predictor.flat_params(), drop_p=p,
                                     seed=_ops.new_seed() if p > 0 else 0)
         loss.backward()

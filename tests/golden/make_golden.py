@@ -93,10 +93,16 @@ def golden_losses():
         rec = {"pos": pos, "neg": neg, "weight": w}
         for name, fn, use_w in (("AUC", ref_loss.auc_loss, False),
                                 ("HingeAUC", ref_loss.hinge_auc_loss, False),
-                                ("WeightedHingeAUC", ref_loss.weighted_hinge_auc_loss, True)):
+                                ("WeightedHingeAUC", ref_loss.weighted_hinge_auc_loss, True),
+                                ("WeightedAUC", ref_loss.weighted_auc_loss, True),
+                                ("AdaAUC", ref_loss.adaptive_auc_loss, True),
+                                ("AdaHingeAUC", ref_loss.adaptive_hinge_auc_loss, True),
+                                ("LogRank", ref_loss.log_rank_loss, False),
+                                ("CE", ref_loss.ce_loss, None),
+                                ("InfoNCE", ref_loss.info_nce_loss, False)):
             p = pos.clone().requires_grad_(True)
             n = neg.clone().requires_grad_(True)
-            loss = fn(p, n, num_neg, w) if use_w else fn(p, n, num_neg)
+            loss = fn(p, n) if use_w is None else (fn(p, n, num_neg, w) if use_w else fn(p, n, num_neg))
             loss.backward()
             rec[name] = {"loss": loss.detach(), "gpos": p.grad.clone(), "gneg": n.grad.clone()}
         out[f"num_neg{num_neg}"] = rec

@@ -257,9 +257,16 @@ def test_losses_against_reference_golden(ops, golden_dir):
     for key, rec in G.items():
         k = int(key[-1])
         for name, fn in (("AUC", L.auc_loss), ("HingeAUC", L.hinge_auc_loss),
-                         ("WeightedHingeAUC", L.weighted_hinge_auc_loss)):
+                         ("WeightedHingeAUC", L.weighted_hinge_auc_loss), ("WeightedAUC", L.weighted_auc_loss),
+                         ("AdaAUC", L.adaptive_auc_loss), ("AdaHingeAUC", L.adaptive_hinge_auc_loss),
+                         ("LogRank", L.log_rank_loss), ("CE", L.ce_loss), ("InfoNCE", L.info_nce_loss)):
             p, n = rec["pos"].cuda().requires_grad_(True), rec["neg"].cuda().requires_grad_(True)
-            args = (p, n, k, rec["weight"].cuda()) if name == "WeightedHingeAUC" else (p, n, k)
+            if name == "CE":
+                args = (p, n)
+            elif name in ("WeightedHingeAUC", "WeightedAUC", "AdaAUC", "AdaHingeAUC"):
+                args = (p, n, k, rec["weight"].cuda())
+            else:
+                args = (p, n, k)
             loss = fn(*args)
             loss.backward()
             assert loss.dim() == 0

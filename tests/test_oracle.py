@@ -133,6 +133,11 @@ def test_losses_match_reference(golden_dir):
             assert rel_err(loss, rec[name]["loss"]) < 1e-6
             assert rel_err(gp, rec[name]["gpos"].reshape(-1)) < 1e-6
             assert rel_err(gn.reshape(-1), rec[name]["gneg"].reshape(-1)) < 1e-6
+        for name in ("WeightedAUC", "AdaAUC", "AdaHingeAUC", "LogRank", "CE", "InfoNCE"):
+            loss, gp, gn = plnlp_ref.pair_loss_autograd(name, rec["pos"], rec["neg"], k, rec["weight"])
+            assert rel_err(loss, rec[name]["loss"]) < 1e-6
+            assert rel_err(gp, rec[name]["gpos"].reshape(-1)) < 1e-6
+            assert rel_err(gn, rec[name]["gneg"].reshape(-1)) < 1e-6
 
 
 def test_predictors_match_reference(golden_dir):
