@@ -245,6 +245,19 @@ def mlp_out_bwd_raw(a, w, dscore, mask_a, drop_scale):
     return dz, dw, db
 
 
+_RANGE_CACHE = {}
+
+
+def _node_range(n_rows, dtype, device):
+    key = (n_rows, dtype, device)
+    r = _RANGE_CACHE.get(key)
+    if r is None:
+        if len(_RANGE_CACHE) > 8:
+            _RANGE_CACHE.clear()
+        r = _RANGE_CACHE[key] = torch.arange(n_rows + 1, dtype=dtype, device=device)
+    return r
+
+
 def edge_scatter_raw(h, edges, da=None, dscore=None, mode=None):
     """grad_h [n_rows, H] of the endpoint gather; da [P,H] (MLP head) or dscore [P] (DOT)."""
     lib = _lib.load()
@@ -267,14 +280,14 @@ def edge_scatter_raw(h, edges, da=None, dscore=None, mode=None):
     # entries t = 2p + side by node and, inside a node, by t -> fixed summation order.  One segment per
     # node (empty ones included, they write their zero row), so there is no data-dependent size and no
     # host synchronisation, and grad_h needs no separate zero fill.
-    _sp = profiling.span("torch: stable sort + bincount for sorted scatter")
+    _sp = profiling.span("torch: stable sort + searchsorted for sorted scatter")
     _sp.__enter__()
     flat = edges.reshape(-1)                          # entry id t = 2p + side  <->  flat[t]
     flat = torch.where(flat < 0, flat + n_rows, flat)
     key = flat.to(torch.int32) if n_rows < 2 ** 31 else flat
-    _, entry = torch.sort(key, stable=True)
-    seg_ptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=edges.device)
-    seg_ptr[1:] = torch.cumsum(torch.bincount(flat, minlength=n_rows), 0)
+    skey, entry = torch.sort(key, stable=True)
+    # seg_ptr[i] = first position whose node id is >= i (one binary search per node, no bincount / scan)
+    seg_ptr = torch.searchsorted(skey, _node_range(n_rows, key.dtype, edges.device))
     _sp.__exit__()
     grad_h = torch.empty(n_rows, H, dtype=torch.float32, device=h.device)
     with profiling.span("edge_scatter_sorted_f32", P * (5 * H * 4 + 32), 0):
