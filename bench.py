@@ -361,6 +361,14 @@ def run_ours(args):
             roof = {"kernel": top["kernel"], "bound": "hbm", "achieved": top.get("achieved_gbs"),
                     "peak": pk["hbm"], "unit": "GB/s", "frac": top.get("frac_hbm"), "traffic": None,
                     "peak_source": pk["src"]}
+        try:        # measured DRAM traffic per launch of that kernel, from the committed ncu --set full capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[args.workload][top["kernel"]]
+            roof["traffic"], roof["traffic_source"] = tr["bytes"], "profiles/" + tr["source"]
+        except Exception:
+            pass
+        if roof["bound"] == "tensor":
+            roof["note"] = ("3xTF32: every algorithmic FLOP costs 3 tensor-core MMA passes, so the tensor pipe is ~3x "
+                            "busier than achieved/peak suggests; peak is the bf16 figure, the tf32 pipe peaks at half")
         spmm = [r for r in kernels if r["kernel"].startswith("spmm")]
         if spmm:
             src_bytes = cfg["N"] * cfg["hid"] * 4
