@@ -98,8 +98,9 @@ def gemm_raw(A, B, transa=False, transb=False, C=None, beta=0.0, bias=None, act=
         C = torch.empty(M, N, dtype=torch.float32, device=A.device)
         beta = 0.0
     backend = backend or GEMM_BACKEND
-    if backend != "ffma" and (K < 32 or M * N < 128 * 128):
-        backend = "ffma"                      # too small to fill one tensor-core tile
+    if backend != "ffma" and (K < 32 or N < 16 or M * N * K < (1 << 20)):
+        backend = "ffma"                      # too little work for a tensor-core tile (a small M x N with a
+                                              # huge K -- weight gradients -- does go to the tensor cores)
     bn = 128 if backend == "ffma" or (N <= 128 and not backend.endswith("c2")) else 256
     if split_k is None:
         tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
