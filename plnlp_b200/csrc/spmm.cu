@@ -13,6 +13,8 @@
 //  * valued accumulation uses separate fp32 multiply and add (no FMA contraction) so that the
 //    result equals the reference CPU loop bit for bit; the kernel is memory-bound, the extra
 //    instruction is free.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace plnlp {
@@ -103,9 +105,9 @@ __device__ __forceinline__ void gather_block(const float* __restrict__ xb, int64
     }
 }
 
-template <int VEC, int U, bool HAS_VAL>
+// NB = neighbours whose rows are in flight together (NB x U 16-byte loads per lane)
+template <int VEC, int U, int NB, bool HAS_VAL>
 __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
-    constexpr int NB = (U == 1) ? 8 : (U == 2) ? 4 : 2;
     const int lane = threadIdx.x & 31;
     const int64_t item = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (item >= p.n_items) return;
@@ -188,8 +190,18 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
     const dim3 block(256);
     if (p.n_items > 0) {
         const dim3 grid(static_cast<unsigned>(ceil_div(p.n_items, 8)), slabs);
-        if (p.val) spmm_csr_kernel<VEC, U, true><<<grid, block, 0, st>>>(p);
-        else       spmm_csr_kernel<VEC, U, false><<<grid, block, 0, st>>>(p);
+        // default depth: 8 loads per lane in flight; PLNLP_SPMM_NB (2, 4 or 8 neighbours) overrides it for tuning
+        static const int nb_env = [] { const char* e = getenv("PLNLP_SPMM_NB"); return e ? atoi(e) : 0; }();
+        const int nb = nb_env ? nb_env : ((U == 1) ? 8 : (U == 2) ? 4 : 2);
+#define PLNLP_SPMM_LAUNCH(NBV)                                                          \
+    do {                                                                                \
+        if (p.val) spmm_csr_kernel<VEC, U, NBV, true><<<grid, block, 0, st>>>(p);       \
+        else       spmm_csr_kernel<VEC, U, NBV, false><<<grid, block, 0, st>>>(p);      \
+    } while (0)
+        if (nb >= 8) PLNLP_SPMM_LAUNCH(8);
+        else if (nb >= 4) PLNLP_SPMM_LAUNCH(4);
+        else PLNLP_SPMM_LAUNCH(2);
+#undef PLNLP_SPMM_LAUNCH
         PLNLP_LAUNCH_CHECK();
     }
     if (p.n_fix > 0) {
