@@ -83,6 +83,18 @@ int plnlp_spmm_csr_f32(const int32_t* item_ptr, const int32_t* item_row, const i
                        float* partial, const int32_t* fix_ptr, const int32_t* fix_row, int64_t n_fix,
                        void* stream);
 
+/* The same SpMM on bf16 feature storage (the "bf16 path, stated separately" of BASELINE.json's north_star;
+ * config 5 sweeps fp32 and bf16): x and out hold bf16 bit patterns, leading dims in ELEMENTS; every output
+ * element is accumulated in fp32 in CSR order and rounded once (RN) at the store; val / row_div / bias and
+ * the partial slots of split rows stay fp32.  Halves the gathered bytes: nnz*F*2 per launch.  16-byte loads
+ * (8 features per lane) for F >= 256, 8-byte for F >= 128, 4-byte below, alignment permitting. */
+int plnlp_spmm_csr_bf16(const int32_t* item_ptr, const int32_t* item_row, const int32_t* item_slot,
+                        int64_t n_items, const int32_t* col, const float* val,
+                        const float* row_div, const float* bias, int relu, float drop_p, uint64_t seed,
+                        const uint16_t* x, int64_t ldx, uint16_t* out, int64_t ldo, int64_t F,
+                        float* partial, const int32_t* fix_ptr, const int32_t* fix_row, int64_t n_fix,
+                        void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Dense layers (replace torch.nn.Linear -> cuBLAS sgemm under SAGEConv.lin_l/lin_r,
  * GCNConv.lin, MLPPredictor.lins: layer.py:20,23,82-86, and their two backward GEMMs).

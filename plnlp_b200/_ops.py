@@ -65,23 +65,36 @@ def new_seed():
 # raw launches
 # ---------------------------------------------------------------------------
 def spmm_raw(plan, x, use_val, div_rows, bias=None, relu=False, drop_p=0.0, seed=0, out=None):
+    """fp32 features, or bf16 features (bf16 storage in and out, fp32 accumulation -- the separately stated
+    bf16 path; autograd and the models stay fp32)."""
     lib = _lib.load()
-    x = _rowmajor(x)
+    bf16 = x.dtype == torch.bfloat16
+    if bf16:
+        if not x.is_cuda or x.dim() != 2:
+            raise RuntimeError("bf16 SpMM needs a 2-D CUDA tensor")
+        if x.stride(1) != 1:
+            x = x.contiguous()
+    else:
+        x = _rowmajor(x)
     F = x.size(1)
     if x.size(0) != plan.n_cols:
         raise RuntimeError(f"SpMM shape mismatch: adjacency has {plan.n_cols} columns, x has {x.size(0)} rows")
     if out is None:
-        out = torch.empty(plan.n_rows, F, dtype=torch.float32, device=x.device)
+        out = torch.empty(plan.n_rows, F, dtype=x.dtype, device=x.device)
+    elif out.dtype != x.dtype:
+        raise RuntimeError("SpMM output dtype must match the feature dtype")
     partial = None
     if plan.n_fix:
         partial = workspace.get("spmm_partial", plan.n_partial * F * 4, x.device)
     val = plan.val if use_val else None
-    with profiling.span("spmm_csr_f32", plan.alg_bytes(F) - (0 if use_val or plan.val is None else plan.nnz * 4), 0):
-        check(lib.plnlp_spmm_csr_f32(ptr(plan.item_ptr), ptr(plan.item_row), ptr(plan.item_slot), plan.n_items,
-                                     ptr(plan.col), ptr(val), ptr(plan.row_cnt if div_rows else None), ptr(bias),
-                                     int(relu), float(drop_p), int(seed), ptr(x), _ld(x), ptr(out), _ld(out), F,
-                                     ptr(partial), ptr(plan.fix_ptr), ptr(plan.fix_row), plan.n_fix, stream()),
-              "plnlp_spmm_csr_f32")
+    alg = plan.alg_bytes(F, 2 if bf16 else 4) - (0 if use_val or plan.val is None else plan.nnz * 4)
+    fn, name = (lib.plnlp_spmm_csr_bf16, "spmm_csr_bf16") if bf16 else (lib.plnlp_spmm_csr_f32, "spmm_csr_f32")
+    with profiling.span(name, alg, 0):
+        check(fn(ptr(plan.item_ptr), ptr(plan.item_row), ptr(plan.item_slot), plan.n_items,
+                 ptr(plan.col), ptr(val), ptr(plan.row_cnt if div_rows else None), ptr(bias),
+                 int(relu), float(drop_p), int(seed), ptr(x), _ld(x), ptr(out), _ld(out), F,
+                 ptr(partial), ptr(plan.fix_ptr), ptr(plan.fix_row), plan.n_fix, stream()),
+              "plnlp_" + name)
     return out
 
 

@@ -33,11 +33,15 @@ inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_
 
 
 // ---------------------------------------------------------------------------------------
-// VEC-wide (1/2/4 floats) global loads and stores
+// VEC-wide (1/2/4 floats; 8 = two 16-byte accesses) global loads and stores
 // ---------------------------------------------------------------------------------------
 template <int VEC>
 __device__ __forceinline__ void load_vec(float (&d)[VEC], const float* p) {
-    if constexpr (VEC == 4) {
+    static_assert(VEC == 1 || VEC == 2 || VEC == 4 || VEC == 8, "unsupported vector width");
+    if constexpr (VEC == 8) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+    } else if constexpr (VEC == 4) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(p));
         d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
     } else if constexpr (VEC == 2) {
@@ -50,7 +54,11 @@ __device__ __forceinline__ void load_vec(float (&d)[VEC], const float* p) {
 
 template <int VEC>
 __device__ __forceinline__ void store_vec(float* p, const float (&d)[VEC]) {
-    if constexpr (VEC == 4) {
+    static_assert(VEC == 1 || VEC == 2 || VEC == 4 || VEC == 8, "unsupported vector width");
+    if constexpr (VEC == 8) {
+        reinterpret_cast<float4*>(p)[0] = make_float4(d[0], d[1], d[2], d[3]);
+        reinterpret_cast<float4*>(p)[1] = make_float4(d[4], d[5], d[6], d[7]);
+    } else if constexpr (VEC == 4) {
         *reinterpret_cast<float4*>(p) = make_float4(d[0], d[1], d[2], d[3]);
     } else if constexpr (VEC == 2) {
         *reinterpret_cast<float2*>(p) = make_float2(d[0], d[1]);

@@ -15,11 +15,15 @@
 //    instruction is free.
 #include <cstdlib>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace plnlp {
 
-struct SpmmParams {
+// T = feature / output element type: float, or __nv_bfloat16 (bf16 storage, fp32 accumulation)
+template <typename T>
+struct SpmmParamsT {
     const int32_t* item_ptr;
     const int32_t* item_row;
     const int32_t* item_slot;
@@ -31,9 +35,9 @@ struct SpmmParams {
     int relu;
     float drop_p;
     uint64_t seed;
-    const float* x;
+    const T* x;
     int64_t ldx;
-    float* out;
+    T* out;
     int64_t ldo;
     int F;
     float* partial;
@@ -41,10 +45,51 @@ struct SpmmParams {
     const int32_t* fix_row;
     int64_t n_fix;
 };
+using SpmmParams = SpmmParamsT<float>;
+
+// bf16 rows: VEC elements per lane (16 / 8 / 4 / 2 bytes), widened to fp32 in registers
+template <int VEC>
+__device__ __forceinline__ void load_vec(float (&d)[VEC], const __nv_bfloat16* p) {
+    if constexpr (VEC == 8) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            d[2 * i] = __uint_as_float(w[i] << 16);
+            d[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    } else if constexpr (VEC == 4) {
+        const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+        d[0] = __uint_as_float(t.x << 16); d[1] = __uint_as_float(t.x & 0xffff0000u);
+        d[2] = __uint_as_float(t.y << 16); d[3] = __uint_as_float(t.y & 0xffff0000u);
+    } else if constexpr (VEC == 2) {
+        const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(p));
+        d[0] = __uint_as_float(t << 16); d[1] = __uint_as_float(t & 0xffff0000u);
+    } else {
+        d[0] = __bfloat162float(p[0]);
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_vec(__nv_bfloat16* p, const float (&d)[VEC]) {
+    if constexpr (VEC == 1) {
+        p[0] = __float2bfloat16_rn(d[0]);
+    } else {
+        uint32_t w[VEC / 2];
+#pragma unroll
+        for (int i = 0; i < VEC / 2; ++i) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(d[2 * i], d[2 * i + 1]);
+            w[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        if constexpr (VEC == 8) *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+        else if constexpr (VEC == 4) *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[1]);
+        else *reinterpret_cast<uint32_t*>(p) = w[0];
+    }
+}
 
 // finished-row epilogue for the VEC features starting at column f of row `row`
-template <int VEC>
-__device__ __forceinline__ void finish_store(const SpmmParams& p, int row, int f, float (&a)[VEC]) {
+template <typename T, int VEC>
+__device__ __forceinline__ void finish_store(const SpmmParamsT<T>& p, int row, int f, float (&a)[VEC]) {
     if (p.row_div) {
         const float d = __ldg(p.row_div + row);
 #pragma unroll
@@ -69,8 +114,8 @@ __device__ __forceinline__ void finish_store(const SpmmParams& p, int row, int f
     store_vec<VEC>(p.out + static_cast<int64_t>(row) * p.ldo + f, a);
 }
 
-template <int VEC, int U, int NB, bool HAS_VAL, bool PRED>
-__device__ __forceinline__ void gather_block(const float* __restrict__ xb, int64_t ldx, int c, float v,
+template <typename T, int VEC, int U, int NB, bool HAS_VAL, bool PRED>
+__device__ __forceinline__ void gather_block(const T* __restrict__ xb, int64_t ldx, int c, float v,
                                              int j, int n, const bool (&act)[U], float (&acc)[U][VEC]) {
     float t[NB][U][VEC];
     float vv[NB];
@@ -81,7 +126,7 @@ __device__ __forceinline__ void gather_block(const float* __restrict__ xb, int64
         const int cj = __shfl_sync(0xffffffffu, c, jj & 31);
         vv[b] = HAS_VAL ? __shfl_sync(0xffffffffu, v, jj & 31) : 1.0f;
         ok[b] = !PRED || (jj < n);
-        const float* row = xb + static_cast<int64_t>(cj) * ldx;
+        const T* row = xb + static_cast<int64_t>(cj) * ldx;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (ok[b] && act[u]) {
@@ -106,8 +151,8 @@ __device__ __forceinline__ void gather_block(const float* __restrict__ xb, int64
 }
 
 // NB = neighbours whose rows are in flight together (NB x U 16-byte loads per lane)
-template <int VEC, int U, int NB, bool HAS_VAL>
-__global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
+template <typename T, int VEC, int U, int NB, bool HAS_VAL>
+__global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParamsT<T> p) {
     const int lane = threadIdx.x & 31;
     const int64_t item = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (item >= p.n_items) return;
@@ -123,7 +168,7 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
         for (int e = 0; e < VEC; ++e) acc[u][e] = 0.0f;
 
     const int beg = __ldg(p.item_ptr + item), end = __ldg(p.item_ptr + item + 1);
-    const float* __restrict__ xb = p.x + fbase;
+    const T* __restrict__ xb = p.x + fbase;
     for (int base = beg; base < end; base += 32) {
         const int n = min(32, end - base);
         int c = 0;
@@ -135,11 +180,11 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
         if (n == 32) {
 #pragma unroll 1
             for (int j = 0; j < 32; j += NB)
-                gather_block<VEC, U, NB, HAS_VAL, false>(xb, p.ldx, c, v, j, n, act, acc);
+                gather_block<T, VEC, U, NB, HAS_VAL, false>(xb, p.ldx, c, v, j, n, act, acc);
         } else {
 #pragma unroll 1
             for (int j = 0; j < n; j += NB)
-                gather_block<VEC, U, NB, HAS_VAL, true>(xb, p.ldx, c, v, j, n, act, acc);
+                gather_block<T, VEC, U, NB, HAS_VAL, true>(xb, p.ldx, c, v, j, n, act, acc);
         }
     }
 
@@ -152,14 +197,14 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
         if (slot >= 0) {
             store_vec<VEC>(p.partial + static_cast<int64_t>(slot) * p.F + f, acc[u]);
         } else {
-            finish_store<VEC>(p, row, f, acc[u]);
+            finish_store<T, VEC>(p, row, f, acc[u]);
         }
     }
 }
 
 // second pass for split (hub) rows: sum the partial slots in slot order, then the epilogue
-template <int VEC, int U>
-__global__ void __launch_bounds__(256) spmm_fix_kernel(const SpmmParams p) {
+template <typename T, int VEC, int U>
+__global__ void __launch_bounds__(256) spmm_fix_kernel(const SpmmParamsT<T> p) {
     const int lane = threadIdx.x & 31;
     const int64_t j = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (j >= p.n_fix) return;
@@ -179,45 +224,47 @@ __global__ void __launch_bounds__(256) spmm_fix_kernel(const SpmmParams p) {
 #pragma unroll
             for (int e = 0; e < VEC; ++e) a[e] = __fadd_rn(a[e], t[e]);
         }
-        finish_store<VEC>(p, row, f, a);
+        finish_store<T, VEC>(p, row, f, a);
     }
 }
 
-template <int VEC, int U>
-static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
+template <typename T, int VEC, int U>
+static int launch_spmm(const SpmmParamsT<T>& p, cudaStream_t st) {
     const int per = 32 * VEC * U;
     const unsigned slabs = static_cast<unsigned>(ceil_div(p.F, per));
     const dim3 block(256);
-    if (p.n_items > 0) {
-        const dim3 grid(static_cast<unsigned>(ceil_div(p.n_items, 8)), slabs);
-        // default depth: 8 loads per lane in flight; PLNLP_SPMM_NB (2, 4 or 8 neighbours) overrides it for tuning
-        static const int nb_env = [] { const char* e = getenv("PLNLP_SPMM_NB"); return e ? atoi(e) : 0; }();
-        const int nb = nb_env ? nb_env : ((U == 1) ? 8 : (U == 2) ? 4 : 2);
+    // loads in flight per lane: NB neighbours x U vectors.  Measured on the citation2-shape graph
+    // (tools/spmm_sweep.py): 4 x 16 B per lane is the sweet spot (deeper costs registers / occupancy, shallower
+    // leaves HBM idle); PLNLP_SPMM_NB (2, 4 or 8) overrides NB for tuning.
+    static const int nb_env = [] { const char* e = getenv("PLNLP_SPMM_NB"); return e ? atoi(e) : 0; }();
+    const int nb = nb_env ? nb_env : ((U == 1) ? 4 : (U == 2 && VEC < 8) ? 4 : 2);
 #define PLNLP_SPMM_LAUNCH(NBV)                                                          \
     do {                                                                                \
-        if (p.val) spmm_csr_kernel<VEC, U, NBV, true><<<grid, block, 0, st>>>(p);       \
-        else       spmm_csr_kernel<VEC, U, NBV, false><<<grid, block, 0, st>>>(p);      \
+        if (p.val) spmm_csr_kernel<T, VEC, U, NBV, true><<<grid, block, 0, st>>>(p);    \
+        else       spmm_csr_kernel<T, VEC, U, NBV, false><<<grid, block, 0, st>>>(p);   \
     } while (0)
+    if (p.n_items > 0) {
+        const dim3 grid(static_cast<unsigned>(ceil_div(p.n_items, 8)), slabs);
         if (nb >= 8) PLNLP_SPMM_LAUNCH(8);
         else if (nb >= 4) PLNLP_SPMM_LAUNCH(4);
         else PLNLP_SPMM_LAUNCH(2);
-#undef PLNLP_SPMM_LAUNCH
         PLNLP_LAUNCH_CHECK();
     }
+#undef PLNLP_SPMM_LAUNCH
     if (p.n_fix > 0) {
         const dim3 grid(static_cast<unsigned>(ceil_div(p.n_fix, 8)), slabs);
-        spmm_fix_kernel<VEC, U><<<grid, block, 0, st>>>(p);
+        spmm_fix_kernel<T, VEC, U><<<grid, block, 0, st>>>(p);
         PLNLP_LAUNCH_CHECK();
     }
     return 0;
 }
 
-template <int VEC>
-static int dispatch_u(const SpmmParams& p, cudaStream_t st) {
+template <typename T, int VEC>
+static int dispatch_u(const SpmmParamsT<T>& p, cudaStream_t st) {
     const int64_t lanes_needed = ceil_div(p.F, VEC);
-    if (lanes_needed <= 32) return launch_spmm<VEC, 1>(p, st);
-    if (lanes_needed <= 64) return launch_spmm<VEC, 2>(p, st);
-    return launch_spmm<VEC, 4>(p, st);
+    if (lanes_needed <= 32) return launch_spmm<T, VEC, 1>(p, st);
+    if (lanes_needed <= 64 || VEC == 8) return launch_spmm<T, VEC, 2>(p, st);
+    return launch_spmm<T, VEC, 4>(p, st);
 }
 
 }  // namespace plnlp
@@ -242,7 +289,39 @@ extern "C" int plnlp_spmm_csr_f32(const int32_t* item_ptr, const int32_t* item_r
                     (!partial || aligned(partial, 16));
     const bool v2 = (F % 2 == 0) && (ldx % 2 == 0) && (ldo % 2 == 0) && aligned(x, 8) && aligned(out, 8) &&
                     (!partial || aligned(partial, 8));
-    if (v4) return dispatch_u<4>(p, st);
-    if (v2) return dispatch_u<2>(p, st);
-    return dispatch_u<1>(p, st);
+    if (v4) return dispatch_u<float, 4>(p, st);
+    if (v2) return dispatch_u<float, 2>(p, st);
+    return dispatch_u<float, 1>(p, st);
+}
+
+// bf16 feature storage (x and out are bf16 bit patterns), fp32 accumulation in CSR order, one RN rounding at
+// the store.  Same plan, epilogue and Philox indexing as the fp32 entry point; `partial` stays fp32.
+extern "C" int plnlp_spmm_csr_bf16(const int32_t* item_ptr, const int32_t* item_row, const int32_t* item_slot,
+                                   int64_t n_items, const int32_t* col, const float* val,
+                                   const float* row_div, const float* bias, int relu, float drop_p,
+                                   uint64_t seed, const uint16_t* x, int64_t ldx, uint16_t* out, int64_t ldo,
+                                   int64_t F, float* partial, const int32_t* fix_ptr, const int32_t* fix_row,
+                                   int64_t n_fix, void* stream) {
+    using namespace plnlp;
+    PLNLP_REQUIRE(n_items >= 0 && n_fix >= 0 && F > 0 && F < (1 << 30), PLNLP_E_SIZE);
+    if (n_items == 0) return 0;
+    PLNLP_REQUIRE(item_ptr && item_row && item_slot && x && out, PLNLP_E_NULL);
+    PLNLP_REQUIRE(ldx >= F && ldo >= F, PLNLP_E_SIZE);
+    PLNLP_REQUIRE(drop_p >= 0.0f && drop_p < 1.0f, PLNLP_E_SIZE);
+    if (n_fix > 0) PLNLP_REQUIRE(partial && fix_ptr && fix_row, PLNLP_E_NULL);
+    SpmmParamsT<__nv_bfloat16> p{item_ptr, item_row, item_slot, n_items, col, val, row_div, bias, relu, drop_p, seed,
+                                 reinterpret_cast<const __nv_bfloat16*>(x), ldx,
+                                 reinterpret_cast<__nv_bfloat16*>(out), ldo, static_cast<int>(F), partial, fix_ptr,
+                                 fix_row, n_fix};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto ok = [&](int v) {   // v bf16 elements per access: 2v bytes for x / out, 4v (<= 16-byte pieces) for partial
+        return (F % v == 0) && (ldx % v == 0) && (ldo % v == 0) && aligned(x, 2 * v) && aligned(out, 2 * v) &&
+               (!partial || aligned(partial, v >= 4 ? 16 : 4 * v));
+    };
+    // widest access that still keeps a full warp busy on one row (F / v >= 32), else the widest legal one
+    if (ok(8) && F >= 256) return dispatch_u<__nv_bfloat16, 8>(p, st);
+    if (ok(4) && F >= 128) return dispatch_u<__nv_bfloat16, 4>(p, st);
+    if (ok(2)) return dispatch_u<__nv_bfloat16, 2>(p, st);
+    if (ok(4)) return dispatch_u<__nv_bfloat16, 4>(p, st);
+    return dispatch_u<__nv_bfloat16, 1>(p, st);
 }

@@ -17,7 +17,7 @@ import torch
 
 from . import _ops
 from .layer import *  # noqa: F401,F403
-from .layer import GCN, SAGE, DotPredictor, MLPPredictor
+from .layer import GCN, SAGE, DotPredictor, MLPPredictor, mark_constant
 from .loss import *  # noqa: F401,F403
 from .utils import *  # noqa: F401,F403
 from .utils import evaluate_hits, evaluate_mrr, get_pos_neg_edges
@@ -84,14 +84,23 @@ class BaseModel(object):
     def input_parts(self, data):
         """the blocks of the encoder input, in the column order of model.py:98-105."""
         if self.use_node_feats:
-            x = data.x
-            if x.device != self.device:
-                x = x.to(self.device)
-            x = x.to(torch.float32)
+            x = self._features(data)
             if self.train_node_emb:
                 return (self.emb.weight, x)
             return (x,)
         return (self.emb.weight,)
+
+    def _features(self, data):
+        """data.x on the device in fp32, converted once per tensor and marked constant so the first conv can
+        keep its aggregate (layer.mark_constant)"""
+        x = data.x
+        key = (id(x), x.data_ptr(), x._version)
+        if getattr(self, "_x_key", None) != key:
+            xd = x.to(self.device).to(torch.float32)
+            if xd is x:
+                xd = x.view(x.shape)          # do not tag the caller's tensor object
+            self._x_key, self._x_dev = key, mark_constant(xd.detach())
+        return self._x_dev
 
     def create_input_feat(self, data):
         """model.py:98-105 (materialised; the training loop uses ``input_parts`` instead)."""

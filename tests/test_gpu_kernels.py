@@ -76,6 +76,40 @@ def test_spmm_split_rows(ops, chunk):
     assert torch.equal(got, got2)            # deterministic
 
 
+def test_spmm_all_rows_empty(ops):
+    from plnlp_b200.graph import CSRGraph
+    N, F = 70, 8
+    g = CSRGraph(torch.zeros(N + 1, dtype=torch.int64).cuda(), torch.zeros(0, dtype=torch.int64).cuda(), None, (N, N))
+    b = torch.randn(F).cuda()
+    out = ops.spmm(g, torch.randn(N, F).cuda(), "sum", bias=b)
+    assert torch.equal(out, b.expand(N, F))
+
+
+@pytest.mark.parametrize("F", [2, 7, 50, 64, 128, 200, 256, 520])
+@pytest.mark.parametrize("reduce", ["sum", "mean"])
+def test_spmm_bf16_storage(ops, F, reduce):
+    """the separately stated bf16 path: bf16 feature storage, fp32 accumulation in CSR order, ONE rounding at
+    the store.  Oracle: the in-order fp32 loop on the bf16-rounded inputs, rounded to bf16 -> identical bits
+    for unsplit rows (allowing 1 bf16 ulp where a hub row's partial sums are combined in a different order)."""
+    from plnlp_b200.graph import Structure
+    N = 211
+    ei, w = rand_graph(N, 1500, seed=F, weighted=(reduce == "sum"), hub=True)
+    o = sparse.to_sparse_tensor(ei, w, N)
+    st = Structure(_to_gpu_graph(o))
+    x = torch.randn(N, F).to(torch.bfloat16)
+    plan = st.fwd if reduce == "sum" else st.fwd_noval
+    got = ops.spmm_raw(plan, x.cuda(), use_val=(reduce == "sum"), div_rows=(reduce == "mean"))
+    assert got.dtype == torch.bfloat16
+    oref = o.set_value(None) if reduce == "mean" else o
+    rowptr, col, val = oref.csr()
+    want32 = cspmm.spmm(rowptr, col, val, x.float(), reduce)
+    want = want32.to(torch.bfloat16)
+    deg = rowptr[1:] - rowptr[:-1]
+    unsplit = deg <= plan.chunk
+    assert torch.equal(got.cpu()[unsplit], want[unsplit])
+    assert rel_err(got.cpu().float(), want32) < 2.0 ** -8
+
+
 @pytest.mark.parametrize("weighted,reduce", [(False, "mean"), (True, "sum")])
 def test_spmm_backward_nonsymmetric(ops, weighted, reduce):
     N, F = 97, 40
