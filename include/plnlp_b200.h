@@ -150,6 +150,17 @@ int plnlp_edge_mlp_fwd_tf32(int passes, const float* h, int64_t ldh, int64_t n_r
 /* out[p, :] = h[src_p, :] * h[dst_p, :] */
 int plnlp_gather_hadamard_f32(const float* h, int64_t ldh, int64_t n_rows, const int64_t* edges, int64_t P, int64_t H,
                               float* out, int64_t ldo, void* stream);
+/* Plain endpoint gather out[p, :] = h[idx[p * idx_stride], :] (negative indices wrap) and its backward
+ * grad_h[n, :] = sum_{t in segment n} g[entry[t], :] over a node-sorted entry list (seg_ptr has n_seg + 1
+ * offsets, one segment per node, empty segments write zero rows; fixed summation order -> deterministic).
+ * Replace x_i = h[edge[0]], x_j = h[edge[1]] (model.py:155-156) and autograd's index_put_(accumulate) for the
+ * predictors that consume the two rows separately (MLPCatPredictor / MLPDotPredictor / MLPBilPredictor,
+ * layer.py:90-164).  idx_stride = 2 reads one column of an int64 [P, 2] edge tensor in place. */
+int plnlp_gather_rows_f32(const float* h, int64_t ldh, int64_t n_rows, const int64_t* idx, int64_t idx_stride,
+                          int64_t P, int64_t H, float* out, int64_t ldo, void* stream);
+int plnlp_row_scatter_sorted_f32(const float* g, int64_t ldg_in, int64_t H, const int64_t* seg_ptr,
+                                 int64_t n_seg, const int64_t* entry, float* grad_h, int64_t ldg, void* stream);
+
 /* score[p] = sum_d h[src_p, d] * h[dst_p, d]   (DotPredictor) */
 int plnlp_edge_dot_fwd_f32(const float* h, int64_t ldh, int64_t n_rows, const int64_t* edges, int64_t P, int64_t H,
                            float* score, void* stream);

@@ -186,6 +186,35 @@ def gather_hadamard_raw(h, edges):
     return out
 
 
+def gather_rows_raw(h, edges, side):
+    """h[edges[:, side]] -> [P, H] (the column of the int64 [P, 2] edge tensor is read in place)"""
+    lib = _lib.load()
+    h, edges = _rowmajor(h), _edges_i64(edges)
+    P, H = edges.size(0), h.size(1)
+    out = torch.empty(P, H, dtype=torch.float32, device=h.device)
+    with profiling.span("gather_rows_f32", P * (2 * H * 4 + 8), 0):
+        check(lib.plnlp_gather_rows_f32(ptr(h), _ld(h), h.size(0), edges.data_ptr() + 8 * int(side), 2, P, H,
+                                        ptr(out), H, stream()), "plnlp_gather_rows_f32")
+    return out
+
+
+def row_scatter_raw(g, idx, n_rows):
+    """grad_h [n_rows, H] with grad_h[n] = sum of g[p] over {p : idx[p] = n}, summed in increasing p (stable sort
+    -> deterministic); the backward of ``gather_rows_raw``"""
+    lib = _lib.load()
+    g = _rowmajor(g)
+    H = g.size(1)
+    idx = torch.where(idx < 0, idx + n_rows, idx)
+    key = idx.to(torch.int32) if n_rows < 2 ** 31 else idx
+    skey, entry = torch.sort(key, stable=True)
+    seg_ptr = torch.searchsorted(skey, _node_range(n_rows, key.dtype, g.device))
+    grad_h = torch.empty(n_rows, H, dtype=torch.float32, device=g.device)
+    with profiling.span("row_scatter_sorted_f32", g.numel() * 4 + grad_h.numel() * 4 + idx.numel() * 16, 0):
+        check(lib.plnlp_row_scatter_sorted_f32(ptr(g), _ld(g), H, ptr(seg_ptr), n_rows, ptr(entry), ptr(grad_h), H,
+                                               stream()), "plnlp_row_scatter_sorted_f32")
+    return grad_h
+
+
 def fused_edge_mlp_ok(h, params):
     """the fused forward covers the reference recipes' head: MLPPredictor with ONE hidden layer
     (mlp_num_layers = 2) on a tensor-core backend, hidden width <= 1024"""
@@ -431,6 +460,56 @@ def fused_linear(xs, ws, bias=None, act=ACT_NONE, drop_p=0.0, seed=0):
     return FusedLinear.apply(bias, int(act), float(drop_p), int(seed), len(xs), *xs, *ws)
 
 
+class AggLinear(torch.autograd.Function):
+    """Y = act( [A x_0 | A x_1 | ...] W^T + bias ) for GCNConv's "aggregate first" order (layer.GCNConv).
+
+    ``buf`` [N, K] is a persistent buffer whose CONSTANT column blocks (the aggregate of data.x) were filled once
+    by the caller; the blocks of the inputs that change between steps (``xs``, at column offsets ``offs``) are
+    written by the SpMM kernel straight into their slice of ``buf`` (leading dimension K), so the layer is one
+    SpMM per live block and ONE GEMM over K instead of a GEMM per block, and its weight gradient is one GEMM too.
+    ``holder['stamp']`` counts forwards: if another forward overwrote ``buf`` before this node's backward runs,
+    the live blocks are recomputed first."""
+
+    @staticmethod
+    def forward(ctx, W, bias, adj, buf, holder, offs, act, drop_p, seed, *xs):
+        st = structure_of(adj)
+        for off, x in zip(offs, xs):
+            spmm_raw(st.fwd, x, use_val=st.has_value, div_rows=False, out=buf[:, off:off + x.size(1)])
+        holder["stamp"] = holder.get("stamp", 0) + 1
+        Y = gemm_raw(buf, W, transb=True, bias=bias, act=act, drop_p=drop_p, seed=seed)
+        ctx.st, ctx.buf, ctx.holder, ctx.stamp, ctx.offs = st, buf, holder, holder["stamp"], offs
+        ctx.act, ctx.drop_p, ctx.has_bias = act, drop_p, bias is not None
+        ctx.save_for_backward(Y if act == ACT_RELU else None, W, *xs)
+        return Y
+
+    @staticmethod
+    def backward(ctx, g):
+        Y, W = ctx.saved_tensors[:2]
+        xs = ctx.saved_tensors[2:]
+        st, buf = ctx.st, ctx.buf
+        g = _rowmajor(g)
+        if Y is not None:
+            g = relu_drop_bwd_raw(Y, g, 1.0 / (1.0 - ctx.drop_p))
+        if ctx.holder["stamp"] != ctx.stamp:          # buf was reused by a later forward: restore our blocks
+            for off, x in zip(ctx.offs, xs):
+                spmm_raw(st.fwd, x, use_val=st.has_value, div_rows=False, out=buf[:, off:off + x.size(1)])
+            ctx.holder["stamp"] += 1
+        gW = gemm_raw(g, buf, transa=True) if ctx.needs_input_grad[0] else None             # dW = dY^T [A x]
+        gb = colsum_raw(g) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
+        gxs = []
+        for i, (off, x) in enumerate(zip(ctx.offs, xs)):
+            if not ctx.needs_input_grad[9 + i]:
+                gxs.append(None)
+                continue
+            gu = gemm_raw(g, W[:, off:off + x.size(1)])                                      # d(A x_i) = dY W_i
+            gxs.append(spmm_raw(st.bwd, gu, use_val=st.has_value, div_rows=False))            # A^T .
+        return (gW, gb, None, None, None, None, None, None, None, *gxs)
+
+
+def agg_linear(adj, buf, holder, offs, xs, W, bias, act=ACT_NONE, drop_p=0.0, seed=0):
+    return AggLinear.apply(W, bias, adj, buf, holder, tuple(offs), int(act), float(drop_p), int(seed), *xs)
+
+
 class GatherHadamard(torch.autograd.Function):
     """h[edges[:,0]] * h[edges[:,1]] in one kernel (model.py:155-156 + layer.py:81)."""
 
@@ -457,6 +536,43 @@ class EdgeDot(torch.autograd.Function):
     def backward(ctx, g):
         h, edges = ctx.saved_tensors
         return edge_scatter_raw(h, edges, dscore=g), None
+
+
+class GatherRows(torch.autograd.Function):
+    """x = h[edges[:, side]] (model.py:155-156, one endpoint); backward = deterministic sorted segment sum."""
+
+    @staticmethod
+    def forward(ctx, h, edges, side):
+        ctx.save_for_backward(edges)
+        ctx.side, ctx.n_rows = side, h.size(0)
+        return gather_rows_raw(h, edges, side)
+
+    @staticmethod
+    def backward(ctx, g):
+        (edges,) = ctx.saved_tensors
+        return row_scatter_raw(g, edges[:, ctx.side], ctx.n_rows), None, None
+
+
+class PairMean(torch.autograd.Function):
+    """(x[:P] + x[P:]) / 2 for a [2P] score vector (MLPCatPredictor averages the two concatenation orders,
+    layer.py:115); the column-sum kernel on the [2, P] view."""
+
+    @staticmethod
+    def forward(ctx, x):
+        P = x.numel() // 2
+        return colsum_raw(x.reshape(2, P), 0.5)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (0.5 * g).repeat(2)
+
+
+def row_dot(a, b):
+    """sum(a * b, -1) for two [P, H] matrices with autograd, on the edge-dot kernels (rows p of a and b are the
+    two endpoints of pair p in the stacked matrix)."""
+    P = a.size(0)
+    ar = torch.arange(P, device=a.device)
+    return EdgeDot.apply(torch.cat([a, b], 0), torch.stack([ar, ar + P], 1))
 
 
 class MLPOut(torch.autograd.Function):

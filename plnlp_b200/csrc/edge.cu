@@ -255,6 +255,70 @@ __global__ void __launch_bounds__(256) edge_scatter_sorted_kernel(const float* _
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// plain row gather out[p,:] = h[idx[p*idx_stride],:] and its backward (sorted segment sum): the pair-level
+// predictors of layer.py:90-189 (MLPCAT, and MLPDOT / MLPBIL while dropout is active) need the two endpoint
+// rows separately rather than their product.
+// ---------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ h, int64_t ldh, int64_t n_rows,
+                                                          const int64_t* __restrict__ idx, int64_t idx_stride,
+                                                          int64_t P, int H, float* __restrict__ out, int64_t ldo) {
+    const int lane = threadIdx.x & 31;
+    const int64_t p = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= P) return;
+    const float* src = h + wrap_index(__ldg(idx + p * idx_stride), n_rows) * ldh;
+    float* o = out + p * ldo;
+    for (int f = lane * VEC; f < H; f += 32 * VEC) {
+        float a[VEC];
+        load_vec<VEC>(a, src + f);
+        store_vec<VEC>(o + f, a);
+    }
+}
+
+// one warp per node: grad_h[node,:] = sum of g[entry[t],:] over the node's segment, in list order
+template <int VEC>
+__global__ void __launch_bounds__(256) row_scatter_sorted_kernel(const float* __restrict__ g, int64_t ldg_in, int H,
+                                                                 const int64_t* __restrict__ seg_ptr, int64_t n_seg,
+                                                                 const int64_t* __restrict__ entry,
+                                                                 float* __restrict__ grad_h, int64_t ldg) {
+    constexpr int U = 4;
+    const int lane = threadIdx.x & 31;
+    const int64_t sg = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (sg >= n_seg) return;
+    const int64_t t0 = __ldg(seg_ptr + sg), t1 = __ldg(seg_ptr + sg + 1);
+    for (int f0 = 0; f0 < H; f0 += 32 * VEC * U) {
+        float acc[U][VEC];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[u][e] = 0.0f;
+        for (int64_t base = t0; base < t1; base += 32) {
+            const int n = (t1 - base) < 32 ? static_cast<int>(t1 - base) : 32;
+            int64_t p = 0;
+            if (lane < n) p = __ldg(entry + base + lane);
+            for (int j = 0; j < n; ++j) {
+                const int64_t pj = __shfl_sync(0xffffffffu, p, j);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int f = f0 + (u * 32 + lane) * VEC;
+                    if (f < H) {
+                        float v[VEC];
+                        load_vec<VEC>(v, g + pj * ldg_in + f);
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) acc[u][e] += v[e];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int f = f0 + (u * 32 + lane) * VEC;
+            if (f < H) store_vec<VEC>(grad_h + sg * ldg + f, acc[u]);
+        }
+    }
+}
+
 }  // namespace plnlp
 
 using namespace plnlp;
@@ -378,6 +442,42 @@ extern "C" int plnlp_edge_scatter_sorted_f32(const float* h, int64_t ldh, int64_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define CALL(V) \
     edge_scatter_sorted_kernel<V><<<grid, 256, 0, st>>>(h, ldh, n_rows, edges, static_cast<int>(H), da, ldda, dscore, seg_ptr, seg_node, n_seg, entry, grad_h, ldg)
+    DISPATCH_VEC(vec, CALL);
+#undef CALL
+    PLNLP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int plnlp_gather_rows_f32(const float* h, int64_t ldh, int64_t n_rows, const int64_t* idx,
+                                     int64_t idx_stride, int64_t P, int64_t H, float* out, int64_t ldo,
+                                     void* stream) {
+    PLNLP_REQUIRE(P >= 0 && H > 0 && n_rows > 0 && idx_stride >= 1, PLNLP_E_SIZE);
+    if (P == 0) return 0;
+    PLNLP_REQUIRE(h && idx && out, PLNLP_E_NULL);
+    PLNLP_REQUIRE(ldh >= H && ldo >= H, PLNLP_E_SIZE);
+    const int vec = pick_vec(H, {ldh, ldo}, {h, out});
+    const unsigned grid = static_cast<unsigned>(ceil_div(P, 8));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CALL(V) \
+    gather_rows_kernel<V><<<grid, 256, 0, st>>>(h, ldh, n_rows, idx, idx_stride, P, static_cast<int>(H), out, ldo)
+    DISPATCH_VEC(vec, CALL);
+#undef CALL
+    PLNLP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int plnlp_row_scatter_sorted_f32(const float* g, int64_t ldg_in, int64_t H, const int64_t* seg_ptr,
+                                            int64_t n_seg, const int64_t* entry, float* grad_h, int64_t ldg,
+                                            void* stream) {
+    PLNLP_REQUIRE(H > 0 && n_seg >= 0, PLNLP_E_SIZE);
+    if (n_seg == 0) return 0;
+    PLNLP_REQUIRE(seg_ptr && grad_h, PLNLP_E_NULL);
+    PLNLP_REQUIRE(ldg >= H && (!g || ldg_in >= H), PLNLP_E_SIZE);
+    const int vec = pick_vec(H, {ldg, g ? ldg_in : 4}, {g, grad_h});
+    const unsigned grid = static_cast<unsigned>(ceil_div(n_seg, 8));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CALL(V) \
+    row_scatter_sorted_kernel<V><<<grid, 256, 0, st>>>(g, ldg_in, static_cast<int>(H), seg_ptr, n_seg, entry, grad_h, ldg)
     DISPATCH_VEC(vec, CALL);
 #undef CALL
     PLNLP_LAUNCH_CHECK();

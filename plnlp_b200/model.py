@@ -17,7 +17,8 @@ import torch
 
 from . import _ops
 from .layer import *  # noqa: F401,F403
-from .layer import GCN, SAGE, DotPredictor, MLPPredictor, mark_constant
+from .layer import (GCN, SAGE, BilinearPredictor, DotPredictor, MLPBilPredictor, MLPCatPredictor,
+                    MLPDotPredictor, MLPPredictor, mark_constant)
 from .loss import *  # noqa: F401,F403
 from .utils import *  # noqa: F401,F403
 from .utils import evaluate_hits, evaluate_mrr, get_pos_neg_edges
@@ -131,12 +132,18 @@ class BaseModel(object):
             # endpoints -> all-gather once per step (backward: reduce-scatter of grad_h)
             from . import parallel
             h = parallel.gather_rows(h)
-        head = 'DOT' if isinstance(self.predictor, DotPredictor) else 'MLP'
-        p = self.predictor.dropout if (head == 'MLP' and self.predictor.training) else 0.0
-        loss = _ops.edge_score_loss(h, pos_edge, neg_edge, num_neg, self._loss_name(weight_margin is not None),
-                                    weight=weight_margin,
-                                    head=head, params=self.predictor.flat_params(), drop_p=p,
-                                    seed=_ops.new_seed() if p > 0 else 0)
+        loss_name = self._loss_name(weight_margin is not None)
+        if isinstance(self.predictor, (DotPredictor, MLPPredictor)):
+            head = 'DOT' if isinstance(self.predictor, DotPredictor) else 'MLP'
+            p = self.predictor.dropout if (head == 'MLP' and self.predictor.training) else 0.0
+            loss = _ops.edge_score_loss(h, pos_edge, neg_edge, num_neg, loss_name, weight=weight_margin,
+                                        head=head, params=self.predictor.flat_params(), drop_p=p,
+                                        seed=_ops.new_seed() if p > 0 else 0)
+        else:
+            # the other --predictor choices (layer.py:90-189): positives and negatives scored in one pass
+            score = self.predictor.score_edges(h, torch.cat([pos_edge, neg_edge], 0)).reshape(-1)
+            B = pos_edge.size(0)
+            loss = _ops.pair_loss(loss_name, score[:B], score[B:], num_neg, weight_margin)
         loss.backward()
         if getattr(self, 'world_size', 1) > 1:
             self._allreduce_grads()
@@ -282,8 +289,14 @@ def create_predictor_layer(hidden_channels, num_layers, dropout=0, predictor_nam
         return DotPredictor()
     if name == 'MLP':
         return MLPPredictor(hidden_channels, hidden_channels, 1, num_layers, dropout)
-    if name in ('BIL', 'MLPDOT', 'MLPBIL', 'MLPCAT'):
-        raise NotImplementedError(f"predictor {predictor_name!r} is outside the hot-path scope (SURVEY.md 8f)")
+    if name == 'BIL':
+        return BilinearPredictor(hidden_channels)
+    if name == 'MLPDOT':          # the reference passes hidden_channels = 1 here (model.py:271): kept as is
+        return MLPDotPredictor(hidden_channels, 1, num_layers, dropout)
+    if name == 'MLPBIL':
+        return MLPBilPredictor(hidden_channels, 1, num_layers, dropout)
+    if name == 'MLPCAT':
+        return MLPCatPredictor(hidden_channels, hidden_channels, 1, num_layers, dropout)
     return None
 
 

@@ -268,8 +268,44 @@ def golden_train(tag, *, encoder, predictor, loss, num_neg, sampler, gnn_layers,
             "losses": losses, "test": res, "scores": scores}
 
 
+def golden_predictors_extra():
+    """the predictors of SURVEY 8f rank 3 (layer.py:90-189): BIL, MLPDOT, MLPBIL, MLPCAT.  Outputs in eval
+    mode plus the gradients of <out, g> w.r.t. both inputs and every parameter, from the real reference."""
+    torch.manual_seed(15)
+    out = {}
+    H, P = 20, 45
+
+    def record(key, m):
+        m.eval()
+        xi = torch.randn(P, H).requires_grad_(True)
+        xj = torch.randn(P, H).requires_grad_(True)
+        y = m(xi, xj)
+        g = torch.randn_like(y)
+        y.backward(g)
+        out[key] = {"state": sd(m), "xi": xi.detach().clone(), "xj": xj.detach().clone(), "out": y.detach(),
+                    "g": g, "gxi": xi.grad.clone(), "gxj": xj.grad.clone(),
+                    "gparams": {k: v.grad.clone() for k, v in m.named_parameters()}}
+
+    record("bil", ref_layer.BilinearPredictor(H))
+    for L in (1, 2):
+        record(f"mlpdot_L{L}", ref_layer.MLPDotPredictor(H, H, L, 0.0))
+        record(f"mlpbil_L{L}", ref_layer.MLPBilPredictor(H, H, L, 0.0))
+    for L in (1, 2, 3):
+        record(f"mlpcat_L{L}", ref_layer.MLPCatPredictor(H, H, 1, L, 0.0))
+    # sample_perm_copy (negative_sample.py:61-76): shapes and the multiset property the copies keep
+    torch.manual_seed(16)
+    e = torch.randint(0, 50, (2, 30))
+    for target, k in ((30, 3), (40, 2)):
+        r = ref_ns.sample_perm_copy(e, target, k)
+        out[f"perm_copy_{target}_{k}"] = {"edge_index": e, "target": target, "k": k, "out": r}
+    return out
+
+
 def main():
     torch.set_num_threads(1)
+    if len(sys.argv) > 1 and sys.argv[1] == "extra":       # later additions: leave the earlier fixtures untouched
+        torch.save(golden_predictors_extra(), os.path.join(HERE, "predictors_extra.pt"))
+        return
     torch.save(golden_losses(), os.path.join(HERE, "losses.pt"))
     torch.save(golden_predictors(), os.path.join(HERE, "predictors.pt"))
     torch.save(golden_encoders(), os.path.join(HERE, "encoders.pt"))

@@ -366,6 +366,50 @@ def test_global_neg_sample_pads_when_short(ops):
     assert (out[..., 0] != out[..., 1]).all()
 
 
+def test_global_perm_neg_sample(ops):
+    """negative_sample.py:23-28: num_samples distinct non-edges, then num_neg - 1 permuted copies of the SAME set,
+    in the reference's [E, k, 2] reshape of the concatenated copies"""
+    from plnlp_b200.negative_sample import global_perm_neg_sample
+    torch.manual_seed(3)
+    N = 300
+    ei, _ = rand_graph(N, 9000, seed=17)
+    E, k = 4000, 3
+    out = global_perm_neg_sample(ei.cuda(), N, E, k).cpu()
+    assert out.shape == (E, k, 2) and out.dtype == torch.int64
+    flat = out.reshape(-1, 2)                         # = the k concatenated copies, copy c = rows c*E .. (c+1)*E
+    ids = flat[:, 0] * N + flat[:, 1]
+    assert not np.isin(ids.numpy(), (ei[0] * N + ei[1]).numpy()).any()
+    assert (flat[:, 0] != flat[:, 1]).all()
+    base = ids[:E]
+    assert base.unique().numel() == E                 # the first copy is E distinct negatives
+    for c in range(1, k):                             # every further copy is a permutation of the first
+        assert torch.equal(torch.sort(ids[c * E:(c + 1) * E])[0], torch.sort(base)[0])
+        assert not torch.equal(ids[c * E:(c + 1) * E], base)
+
+
+@pytest.mark.parametrize("H", [1, 6, 50, 128, 200])
+def test_gather_rows_and_sorted_row_scatter(ops, H):
+    """x = h[edges[:, side]] read in place from the [P, 2] tensor (negative index = last rows), and its backward
+    against index_add_ in fp64; deterministic"""
+    N, P = 97, 1500
+    g = torch.Generator().manual_seed(H)
+    h = torch.randn(N, H, generator=g)
+    edges = torch.randint(0, N - 5, (P, 2), generator=g)          # last rows never referenced
+    edges[::50, 1] = -1
+    gout = torch.randn(P, H, generator=g)
+    for side in (0, 1):
+        hg = h.cuda().requires_grad_(True)
+        x = ops.GatherRows.apply(hg, edges.cuda(), side)
+        assert torch.equal(x.detach().cpu(), h[edges[:, side]])
+        x.backward(gout.cuda())
+        idx = torch.where(edges[:, side] < 0, edges[:, side] + N, edges[:, side])
+        want = torch.zeros(N, H, dtype=torch.float64).index_add_(0, idx, gout.double())
+        assert rel_err(hg.grad.cpu(), want) < TOL
+        assert torch.all(hg.grad[N - 5:N - 1] == 0)
+        again = ops.row_scatter_raw(gout.cuda(), edges[:, side].cuda(), N)
+        assert torch.equal(again, hg.grad)
+
+
 # ------------------------------------------------------------------ ranking
 @pytest.mark.parametrize("n,K", [(1, 1), (50, 20), (1000, 100), (101882, 20), (101882, 50), (300000, 100)])
 def test_kth_largest_and_hits(ops, n, K):

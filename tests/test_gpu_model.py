@@ -154,6 +154,184 @@ def test_first_step_gradients_match_reference(golden_dir, tag, scatter):
         check(name, p.grad, "pred." + name[len("lins."):])
 
 
+@pytest.mark.parametrize("mode", ["buffer", "reassoc_only", "reference_order"])
+def test_gcn_feature_plus_embedding_layer_orders(golden_dir, mode, monkeypatch):
+    """GCNConv on [emb | x] (citation2 recipe): the three evaluation orders -- aggregate-first into one buffer
+    with the constant-feature aggregate cached (default on sparse graphs), aggregate-first per block, and the
+    reference's linear-first order -- all match the oracle's first-step loss and gradients."""
+    from plnlp_b200 import graph, layer
+    monkeypatch.setattr(graph, "DENSE_SPMM", False)          # the golden graph is tiny: force the CSR kernels
+    if mode == "reassoc_only":
+        monkeypatch.setattr(layer, "_agg_buffer_ok", lambda adj, parts: False)
+    if mode == "reference_order":
+        monkeypatch.setattr(layer, "REASSOCIATE", False)
+    R = torch.load(os.path.join(golden_dir, "train_runs.pt"))["citation_like"]
+    cfg, model, data = _setup_run(R)
+    pos = plnlp_ref.train_pos_edges(R["split"])
+    st = {"enc." + k[len("convs."):]: v for k, v in R["init"]["encoder"].items()}
+    st.update({"pred." + k[len("lins."):]: v for k, v in R["init"]["predictor"].items()})
+    st["emb"] = R["init"]["emb"]
+    ref = plnlp_ref.OracleModel(num_nodes=cfg["num_nodes"], emb_hidden=cfg["emb"], gnn_hidden=cfg["hid"],
+                                mlp_hidden=cfg["hid"], gnn_layers=cfg["gnn_layers"], mlp_layers=cfg["mlp_layers"],
+                                encoder=cfg["encoder"], predictor=cfg["predictor"], loss=cfg["loss"], lr=cfg["lr"],
+                                clip_norm=-1.0, num_node_feats=cfg["feats"], use_node_feats=cfg["use_feats"],
+                                dtype=torch.float64)
+    ref.load({k: v.double() for k, v in st.items()})
+    adj = sparse.SparseTensor(rowptr=R["adj_rowptr"], col=R["adj_col"], value=R["adj_val"].double(),
+                              sparse_sizes=(cfg["num_nodes"],) * 2, is_sorted=True)
+    model.encoder.train(); model.predictor.train()
+    model.clip_norm = -1.0
+    model.optimizer.param_groups[0]["lr"] = 0.0           # two batches from the same parameters
+    for b in range(min(2, len(R["perms"][0]))):           # the second pass reuses the cached aggregate / buffer
+        perm, neg = R["perms"][0][b], R["negs"][0]
+        loss = model.train_batch(data, pos[perm].cuda(), neg[perm].reshape(-1, 2).cuda(), cfg["num_neg"], None)
+        rloss, _ = ref.step(R["x"].double(), adj, pos[perm], neg[perm], cfg["num_neg"], None, do_update=False)
+        assert rel_err(loss.cpu(), rloss) < TOL
+        assert rel_err(model.emb.weight.grad.cpu(), ref.params["emb"].grad) < 2 * TOL
+        for name, p in model.encoder.named_parameters():
+            assert rel_err(p.grad.cpu(), ref.params["enc." + name[len("convs."):]].grad) < 2 * TOL, name
+    used_buffer = "_plnlp_agg_buffer" in data.adj_t.__dict__
+    assert used_buffer == (mode == "buffer")
+
+
+def test_gcn_aggregate_buffer_survives_interleaved_forwards(monkeypatch):
+    """the aggregate buffer is shared by every forward on one adjacency: a backward that runs after a LATER
+    forward must first restore its own live block (AggLinear's stamp check)"""
+    from plnlp_b200 import graph
+    from plnlp_b200.layer import GCNConv, mark_constant
+    monkeypatch.setattr(graph, "DENSE_SPMM", False)
+    N, Fe, Ff, H = 150, 6, 10, 24
+    ei, _ = rand_graph(N, 900, seed=11)
+    o = sparse.gcn_normalization(sparse.to_sparse_tensor(ei, None, N).to_symmetric())
+    rowptr, col, val = o.csr()
+    g = _gpu_graph(rowptr, col, val, N)
+    torch.manual_seed(3)
+    conv = GCNConv(Fe + Ff, H).cuda()
+    feat = mark_constant(torch.randn(N, Ff).cuda())
+    e1 = torch.randn(N, Fe).cuda().requires_grad_(True)
+    e2 = torch.randn(N, Fe).cuda().requires_grad_(True)
+    y1 = conv((e1, feat), g)
+    y2 = conv((e2, feat), g)                         # overwrites the live columns of the shared buffer
+    gout = torch.randn(N, H).cuda()
+    y1.backward(gout)
+    A = o.to_dense().double()
+    W, bias = conv.lin.weight.detach().double().cpu(), conv.bias.detach().double().cpu()
+    e1c = e1.detach().double().cpu().requires_grad_(True)
+    Wc = W.clone().requires_grad_(True)
+    yref = A @ (torch.cat([e1c, feat.double().cpu()], 1) @ Wc.t()) + bias
+    yref.backward(gout.double().cpu())
+    assert rel_err(y1.detach().cpu(), yref.detach()) < TOL
+    assert rel_err(e1.grad.cpu(), e1c.grad) < TOL
+    assert rel_err(conv.lin.weight.grad.cpu(), Wc.grad) < TOL
+    assert e2.grad is None and y2.shape == y1.shape
+
+
+def test_extra_predictors_against_reference_golden(golden_dir):
+    """BIL / MLPDOT / MLPBIL / MLPCAT (layer.py:90-189): forward and every gradient against
+    outputs of the real reference modules; the edge-level entry ``score_edges`` (node-level transform where no
+    dropout is active) must agree with the pair-level ``forward``"""
+    from plnlp_b200 import layer
+    G = torch.load(os.path.join(golden_dir, "predictors_extra.pt"))
+    H = 20
+    for key, rec in G.items():
+        if key.startswith("perm_copy"):
+            continue
+        L = int(key.split("_L")[1]) if "_L" in key else 0
+        if key == "bil":
+            m = layer.BilinearPredictor(H)
+        elif key.startswith("mlpdot"):
+            m = layer.MLPDotPredictor(H, H, L, 0.0)
+        elif key.startswith("mlpbil"):
+            m = layer.MLPBilPredictor(H, H, L, 0.0)
+        else:
+            m = layer.MLPCatPredictor(H, H, 1, L, 0.0)
+        m = m.cuda()
+        assert sorted(k for k, _ in m.named_parameters()) == sorted(rec["state"])
+        _load_module(m, rec["state"])
+        m.eval()
+        xi = rec["xi"].cuda().requires_grad_(True)
+        xj = rec["xj"].cuda().requires_grad_(True)
+        out = m(xi, xj)
+        assert out.shape == rec["out"].shape, key
+        assert rel_err(out.detach().cpu(), rec["out"]) < TOL, key
+        out.backward(rec["g"].cuda())
+        assert rel_err(xi.grad.cpu(), rec["gxi"]) < TOL and rel_err(xj.grad.cpu(), rec["gxj"]) < TOL, key
+        for name, p in m.named_parameters():
+            assert rel_err(p.grad.cpu(), rec["gparams"][name]) < 2 * TOL, (key, name)
+        # edge-level entry on a node table: rows of xi and xj stacked, pair p = (p, P + p)
+        P = xi.size(0)
+        h = torch.cat([rec["xi"], rec["xj"]], 0).cuda().requires_grad_(True)
+        ar = torch.arange(P, device=DEV)
+        edges = torch.stack([ar, ar + P], 1)
+        m.zero_grad()
+        s2 = m.score_edges(h, edges)
+        assert rel_err(s2.detach().reshape(-1).cpu(), rec["out"].reshape(-1)) < TOL, key
+        s2.backward(rec["g"].cuda().reshape(s2.shape))
+        assert rel_err(h.grad[:P].cpu(), rec["gxi"]) < TOL and rel_err(h.grad[P:].cpu(), rec["gxj"]) < TOL, key
+        for name, p in m.named_parameters():
+            assert rel_err(p.grad.cpu(), rec["gparams"][name]) < 2 * TOL, (key, name)
+        # dropout active: pair-level path with independent masks per side still runs and keeps the shape
+        if hasattr(m, "dropout"):
+            m.dropout = 0.5
+            m.train()
+            assert m.score_edges(h.detach(), edges).shape == s2.shape
+
+
+@pytest.mark.parametrize("predictor", ["BIL", "MLPDOT", "MLPBIL", "MLPCAT"])
+def test_train_step_with_extra_predictors(predictor):
+    """BaseModel.train_batch through the generic scoring path: loss and gradients against the same modules
+    evaluated pair-level in fp64 torch (CPU) from the model's own parameters"""
+    from plnlp_b200.model import BaseModel
+    torch.manual_seed(4)
+    N, H, k, B = 120, 16, 2, 64
+    ei, _ = rand_graph(N, 700, seed=8)
+    o = sparse.to_sparse_tensor(torch.cat([ei, ei.flip(0)], 1), None, N)
+    rowptr, col, val = o.csr()
+    data = Data()
+    data.adj_t, data.x, data.edge_index = _gpu_graph(rowptr, col, val, N), None, ei.cuda()
+    model = BaseModel(lr=0.0, dropout=0.0, grad_clip_norm=-1.0, gnn_num_layers=1, mlp_num_layers=2,
+                      emb_hidden_channels=H, gnn_hidden_channels=H, mlp_hidden_channels=H, num_nodes=N,
+                      num_node_feats=0, gnn_encoder_name="SAGE", predictor_name=predictor, loss_func="AUC",
+                      optimizer_name="SGD", device=DEV, use_node_feats=False, train_node_emb=True)
+    model.param_init()
+    model.encoder.train(); model.predictor.train()
+    pos = ei.t()[:B].contiguous()
+    neg = torch.randint(0, N, (B * k, 2))
+    loss = model.train_batch(data, pos.cuda(), neg.cuda(), k)
+    # fp64 reference: same encoder through the oracle's SAGE restatement, predictor pair-level in torch
+    import copy
+    pred = copy.deepcopy(model.predictor).cpu().double()
+    emb = model.emb.weight.detach().cpu().double().requires_grad_(True)
+    conv = model.encoder.convs[0]
+    Wl, bl, Wr = (t.detach().cpu().double() for t in (conv.lin_l.weight, conv.lin_l.bias, conv.lin_r.weight))
+    hh = torch.relu(sparse.matmul(o, emb, "mean") @ Wl.t() + bl + emb @ Wr.t())
+    edges = torch.cat([pos, neg], 0)
+    xi, xj = hh[edges[:, 0]], hh[edges[:, 1]]
+
+    def lin(mod, x, relu=False):
+        y = x @ mod.weight.t() + (mod.bias if mod.bias is not None else 0)
+        return torch.relu(y) if relu else y
+    if predictor == "BIL":
+        s = (lin(pred.bilin, xi) * xj).sum(-1)
+    elif predictor in ("MLPDOT", "MLPBIL"):
+        for l in pred.lins:
+            xi, xj = lin(l, xi, True), lin(l, xj, True)
+        s = ((lin(pred.bilin, xi) if predictor == "MLPBIL" else xi) * xj).sum(-1)
+    else:
+        x1, x2 = torch.cat([xi, xj], -1), torch.cat([xj, xi], -1)
+        for l in pred.lins[:-1]:
+            x1, x2 = lin(l, x1, True), lin(l, x2, True)
+        s = ((lin(pred.lins[-1], x1) + lin(pred.lins[-1], x2)) / 2).reshape(-1)
+    rloss = plnlp_ref.pair_loss("AUC", s[:B], s[B:], k)
+    rloss.backward()
+    assert rel_err(loss.cpu(), rloss.detach()) < TOL
+    assert rel_err(model.emb.weight.grad.cpu(), emb.grad) < 2 * TOL
+    for (name, p), (_, q) in zip(model.predictor.named_parameters(), pred.named_parameters()):
+        ok, msg = fp32_close(p.grad.cpu(), q.grad.float(), q.grad, 2 * TOL,
+                             floor=2 * TOL * float(emb.grad.abs().max()))
+        assert ok, (name, msg)
+
+
 def _check_update(name, got, init, final, lr, steps, adam):
     """compare the parameter UPDATE (final - init) of a whole replayed trajectory"""
     got, init, final = got.detach().double().cpu(), init.double(), final.double()
