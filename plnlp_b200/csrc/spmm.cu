@@ -151,8 +151,12 @@ __device__ __forceinline__ void gather_block(const T* __restrict__ xb, int64_t l
 }
 
 // NB = neighbours whose rows are in flight together (NB x U 16-byte loads per lane)
+// The kernel is latency bound (ncu: >80 % of the stall samples are long-scoreboard waits on the gathers), so
+// resident warps matter more than per-warp depth: variants whose in-flight tile fits 8 registers are held to
+// 32 registers per thread (8 blocks = all 64 warp slots of the SM), 16-register tiles to 40 (6 blocks).
 template <typename T, int VEC, int U, int NB, bool HAS_VAL>
-__global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParamsT<T> p) {
+__global__ void __launch_bounds__(256, (NB * U * VEC <= 8) ? 8 : (NB * U * VEC <= 16) ? 6 : (sizeof(T) == 2) ? 4 : 3)
+    spmm_csr_kernel(const SpmmParamsT<T> p) {
     const int lane = threadIdx.x & 31;
     const int64_t item = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (item >= p.n_items) return;
@@ -234,10 +238,12 @@ static int launch_spmm(const SpmmParamsT<T>& p, cudaStream_t st) {
     const unsigned slabs = static_cast<unsigned>(ceil_div(p.F, per));
     const dim3 block(256);
     // loads in flight per lane: NB neighbours x U vectors.  Measured on the citation2-shape graph
-    // (tools/spmm_sweep.py): 4 x 16 B per lane is the sweet spot (deeper costs registers / occupancy, shallower
-    // leaves HBM idle); PLNLP_SPMM_NB (2, 4 or 8) overrides NB for tuning.
+    // (tools/spmm_sweep.py, profiles/r01_spmm_sweep.txt): with 16-byte loads two neighbours per lane are enough
+    // and leave the most warps resident (F=128: 83 %, F=256: 91 % of the HBM peak; 66 % / 87 % at eight);
+    // 8- and 4-byte loads (odd widths such as F=50, bf16 below 256) want four.  PLNLP_SPMM_NB (2, 4 or 8)
+    // overrides NB for tuning.
     static const int nb_env = [] { const char* e = getenv("PLNLP_SPMM_NB"); return e ? atoi(e) : 0; }();
-    const int nb = nb_env ? nb_env : ((U == 1) ? 4 : (U == 2 && VEC < 8) ? 4 : 2);
+    const int nb = nb_env ? nb_env : (VEC * static_cast<int>(sizeof(T)) >= 16 ? 2 : 4);
 #define PLNLP_SPMM_LAUNCH(NBV)                                                          \
     do {                                                                                \
         if (p.val) spmm_csr_kernel<T, VEC, U, NBV, true><<<grid, block, 0, st>>>(p);    \
