@@ -76,7 +76,27 @@ class _Unavailable(torch.nn.Module):
         raise NotImplementedError("out of scope (SURVEY.md section 2.1 rows 2)")
 
 
-GraphConv = TransformerConv = _Unavailable
+class GraphConv(torch.nn.Module):
+    """torch_geometric 2.0.1 nn.GraphConv(in, out, aggr='add') restated [from memory -- parity unpinned, like
+    the rest of this layer]: lin_rel(sum_j w_ij x_j) + lin_root(x_i); with a SparseTensor ``adj_t`` the
+    aggregation is ``matmul(adj_t, x, reduce='add')``, which uses the stored values as edge weights; bias in
+    lin_rel only.  Used by the reference's WSAGE encoder (plnlp/layer.py:48-54)."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin_rel = torch.nn.Linear(in_channels, out_channels, bias=True)
+        self.lin_root = torch.nn.Linear(in_channels, out_channels, bias=False)
+
+    def reset_parameters(self):
+        self.lin_rel.reset_parameters()
+        self.lin_root.reset_parameters()
+
+    def forward(self, x, adj_t):
+        return self.lin_rel(matmul(adj_t, x, reduce="sum")) + self.lin_root(x)
+
+
+TransformerConv = _Unavailable
 
 
 def add_self_loops(edge_index, edge_weight=None, num_nodes=None):

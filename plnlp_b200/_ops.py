@@ -26,6 +26,9 @@ SCATTER_MODE = "sorted"
 # (fast path, ~1e-3 relative, stated separately); "ffma" = exact fp32 on the CUDA cores
 GEMM_BACKEND = os.environ.get("PLNLP_GEMM", "tf32x3c2")
 
+# 3xTF32: largest K one TMEM accumulator may take before the split-k reduction combines partials (see gemm_raw)
+TF32X3_KCAP = int(os.environ.get("PLNLP_GEMM_KCAP", "1024"))
+
 # fused edge scoring for the MLP head (gather + Hadamard + layer 1 + out layer in one tcgen05 kernel)
 FUSED_EDGE_MLP = os.environ.get("PLNLP_FUSED_EDGE", "1") != "0"
 
@@ -123,7 +126,7 @@ def gemm_raw(A, B, transa=False, transb=False, C=None, beta=0.0, bias=None, act=
     if backend in ("tf32x3", "tf32x3c2"):
         # the tensor core accumulates with round-toward-zero: keep K per accumulator <= 1024 and
         # let the split-k reduction (RN adds on the CUDA cores) combine the partials
-        split_k = max(split_k, (K + 1023) // 1024)
+        split_k = max(split_k, (K + TF32X3_KCAP - 1) // TF32X3_KCAP)
     ws = None
     ws_bytes = 0
     if split_k > 1:

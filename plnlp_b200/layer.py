@@ -147,6 +147,31 @@ class SAGEConv(torch.nn.Module):
                                  _ops.new_seed() if drop_p > 0 else 0)
 
 
+class GraphConv(torch.nn.Module):
+    """PyG 2.0.1 ``GraphConv(in, out)`` (aggr='add'), the conv of the reference's WSAGE (layer.py:48-54):
+    lin_rel(sum_{j in N(i)} w_ij x_j) + lin_root(x_i) -- SAGEConv's shape with a WEIGHTED SUM in place of the
+    mean: the stored adjacency values are the edge weights (a value-less adjacency counts every edge once).
+    Parameters: lin_rel.weight, lin_rel.bias, lin_root.weight."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin_rel = _Lin(in_channels, out_channels, bias=True)
+        self.lin_root = _Lin(in_channels, out_channels, bias=False)
+
+    def reset_parameters(self):
+        self.lin_rel.reset_parameters()
+        self.lin_root.reset_parameters()
+
+    def forward(self, x, adj_t, act=_ops.ACT_NONE, drop_p=0.0):
+        parts = _as_parts(x)
+        aggs = [_const_aggregate(adj_t, p, "sum") if _is_const(p) else _ops.spmm(adj_t, p, reduce="sum")
+                for p in parts]
+        wl, wr = _split_cols(self.lin_rel.weight, parts), _split_cols(self.lin_root.weight, parts)
+        return _ops.fused_linear(aggs + parts, wl + wr, self.lin_rel.bias, act, drop_p,
+                                 _ops.new_seed() if drop_p > 0 else 0)
+
+
 class GCNConv(torch.nn.Module):
     """``GCNConv(in, out, normalize=False)`` (layer.py:45): A_hat @ (x W^T) + bias with the
     pre-normalised adjacency.  Parameters: lin.weight (glorot), bias (zeros)."""
@@ -225,6 +250,14 @@ class GCN(BaseGNN):
     def __init__(self, in_channels, hidden_channels, out_channels, num_layers, dropout):
         super().__init__(dropout, num_layers)
         self.convs.extend(_stack(GCNConv, in_channels, hidden_channels, out_channels, num_layers))
+
+
+class WSAGE(BaseGNN):
+    """layer.py:48-54: the weighted-sum variant of SAGE (PyG GraphConv)"""
+
+    def __init__(self, in_channels, hidden_channels, out_channels, num_layers, dropout):
+        super().__init__(dropout, num_layers)
+        self.convs.extend(_stack(GraphConv, in_channels, hidden_channels, out_channels, num_layers))
 
 
 class MLPPredictor(torch.nn.Module):
@@ -419,5 +452,4 @@ class MLPCatPredictor(torch.nn.Module):
         return self.forward(*_endpoints(h, edges))
 
 
-WSAGE = _out_of_scope("WSAGE", "layer.py:48-54")
 Transformer = _out_of_scope("Transformer", "layer.py:57-63")

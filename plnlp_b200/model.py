@@ -17,7 +17,7 @@ import torch
 
 from . import _ops
 from .layer import *  # noqa: F401,F403
-from .layer import (GCN, SAGE, BilinearPredictor, DotPredictor, MLPBilPredictor, MLPCatPredictor,
+from .layer import (GCN, SAGE, WSAGE, BilinearPredictor, DotPredictor, MLPBilPredictor, MLPCatPredictor,
                     MLPDotPredictor, MLPPredictor, mark_constant)
 from .loss import *  # noqa: F401,F403
 from .utils import *  # noqa: F401,F403
@@ -276,7 +276,7 @@ def create_gnn_layer(input_channels, hidden_channels, num_layers, dropout=0, enc
     if name == 'GCN':
         return GCN(input_channels, hidden_channels, hidden_channels, num_layers, dropout)
     if name == 'WSAGE':
-        return WSAGE(input_channels, hidden_channels, hidden_channels, num_layers, dropout)  # noqa: F405
+        return WSAGE(input_channels, hidden_channels, hidden_channels, num_layers, dropout)
     if name == 'TRANSFORMER':
         return Transformer(input_channels, hidden_channels, hidden_channels, num_layers, dropout)  # noqa: F405
     return SAGE(input_channels, hidden_channels, hidden_channels, num_layers, dropout)

@@ -292,6 +292,21 @@ def golden_predictors_extra():
         record(f"mlpbil_L{L}", ref_layer.MLPBilPredictor(H, H, L, 0.0))
     for L in (1, 2, 3):
         record(f"mlpcat_L{L}", ref_layer.MLPCatPredictor(H, H, 1, L, 0.0))
+    # WSAGE (layer.py:48-54): the reference's layer stacking over the GraphConv restatement, weighted graph
+    torch.manual_seed(17)
+    N = 50
+    ei, w = make_graph(N, 140, seed=23, weighted=True)
+    adj = sparse.to_sparse_tensor(ei, w, N)
+    for L in (1, 2):
+        m = ref_layer.WSAGE(12, 16, 16, L, 0.0)
+        m.eval()
+        x = torch.randn(N, 12).requires_grad_(True)
+        y = m(x, adj)
+        g = torch.randn_like(y)
+        y.backward(g)
+        out[f"wsage_L{L}"] = {"state": sd(m), "x": x.detach().clone(), "out": y.detach(), "g": g,
+                              "gx": x.grad.clone(), "gparams": {k: v.grad.clone() for k, v in m.named_parameters()},
+                              "edge_index": ei, "edge_weight": w, "num_nodes": N}
     # sample_perm_copy (negative_sample.py:61-76): shapes and the multiset property the copies keep
     torch.manual_seed(16)
     e = torch.randint(0, 50, (2, 30))

@@ -226,6 +226,35 @@ def test_gcn_aggregate_buffer_survives_interleaved_forwards(monkeypatch):
     assert e2.grad is None and y2.shape == y1.shape
 
 
+def test_wsage_against_reference_golden(golden_dir):
+    """WSAGE (layer.py:48-54; PyG GraphConv = weighted-sum SAGE): the reference's stacking over the restated
+    conv, forward and every gradient, 1 and 2 layers; sparse and dense aggregation paths"""
+    from plnlp_b200 import graph
+    from plnlp_b200.layer import WSAGE
+    G = torch.load(os.path.join(golden_dir, "predictors_extra.pt"))
+    for dense in (True, False):
+        graph.DENSE_SPMM = dense
+        try:
+            for L in (1, 2):
+                rec = G[f"wsage_L{L}"]
+                N = rec["num_nodes"]
+                o = sparse.to_sparse_tensor(rec["edge_index"], rec["edge_weight"], N)
+                rowptr, col, val = o.csr()
+                g = _gpu_graph(rowptr, col, val, N)
+                m = WSAGE(12, 16, 16, L, 0.0).cuda()
+                _load_module(m, rec["state"])
+                m.eval()
+                x = rec["x"].cuda().requires_grad_(True)
+                y = m(x, g)
+                assert rel_err(y.detach().cpu(), rec["out"]) < TOL
+                y.backward(rec["g"].cuda())
+                assert rel_err(x.grad.cpu(), rec["gx"]) < TOL
+                for name, p in m.named_parameters():
+                    assert rel_err(p.grad.cpu(), rec["gparams"][name]) < 2 * TOL, name
+        finally:
+            graph.DENSE_SPMM = True
+
+
 def test_extra_predictors_against_reference_golden(golden_dir):
     """BIL / MLPDOT / MLPBIL / MLPCAT (layer.py:90-189): forward and every gradient against
     outputs of the real reference modules; the edge-level entry ``score_edges`` (node-level transform where no

@@ -9,8 +9,10 @@ from plnlp_b200 import _ops  # noqa: E402
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 37888          # 296 M-tiles x 2 N-tiles = 4 full waves
 backend = sys.argv[2] if len(sys.argv) > 2 else "tf32x3"
-A = torch.randn(M, 512, device="cuda")
-W = torch.randn(512, 512, device="cuda")
+N = int(sys.argv[3]) if len(sys.argv) > 3 else 512
+K = int(sys.argv[4]) if len(sys.argv) > 4 else 512
+A = torch.randn(M, K, device="cuda")
+W = torch.randn(N, K, device="cuda")
 for _ in range(3):
     C = _ops.gemm_raw(A, W, transb=True, backend=backend)
 torch.cuda.synchronize()
