@@ -263,7 +263,7 @@ def test_extra_predictors_against_reference_golden(golden_dir):
     G = torch.load(os.path.join(golden_dir, "predictors_extra.pt"))
     H = 20
     for key, rec in G.items():
-        if key.startswith("perm_copy"):
+        if key.startswith(("perm_copy", "wsage")):
             continue
         L = int(key.split("_L")[1]) if "_L" in key else 0
         if key == "bil":
