@@ -204,6 +204,21 @@ def gather_rows_raw(h, edges, side):
     return out
 
 
+def gather_rows_idx_raw(h, idx):
+    """h[idx] for a 1-D int64 index vector -> [len(idx), H]"""
+    lib = _lib.load()
+    h = _rowmajor(h)
+    if idx.dtype != torch.int64 or not idx.is_cuda or idx.dim() != 1:
+        raise RuntimeError("idx must be a 1-D CUDA int64 tensor")
+    idx = idx.contiguous()
+    P, H = idx.numel(), h.size(1)
+    out = torch.empty(P, H, dtype=torch.float32, device=h.device)
+    with profiling.span("gather_rows_f32", P * (2 * H * 4 + 8), 0):
+        check(lib.plnlp_gather_rows_f32(ptr(h), _ld(h), h.size(0), ptr(idx), 1, P, H, ptr(out), H, stream()),
+              "plnlp_gather_rows_f32")
+    return out
+
+
 def row_scatter_raw(g, idx, n_rows):
     """grad_h [n_rows, H] with grad_h[n] = sum of g[p] over {p : idx[p] = n}, summed in increasing p (stable sort
     -> deterministic); the backward of ``gather_rows_raw``"""

@@ -128,10 +128,16 @@ class BaseModel(object):
         self.optimizer.zero_grad(set_to_none=True)
         h = self.encoder(self.input_parts(data), data.adj_t)
         if self.partitioned:
-            # row-partitioned encoder: h is this rank's row block; scoring needs arbitrary
-            # endpoints -> all-gather once per step (backward: reduce-scatter of grad_h)
+            # row-partitioned encoder: h is this rank's row block and scoring needs arbitrary
+            # endpoints.  Fetch just the distinct endpoint rows of this rank's batch from their owners
+            # (parallel.FetchRows; gradients return the same way) and score on that compact table.
             from . import parallel
-            h = parallel.gather_rows(h)
+            if parallel.EXCHANGE == "rows":
+                ids, inv = torch.unique(torch.cat([pos_edge, neg_edge], 0), return_inverse=True)
+                h = parallel.fetch_rows(h, ids)
+                pos_edge, neg_edge = inv[:pos_edge.size(0)], inv[pos_edge.size(0):]
+            else:       # all-gather the whole matrix (backward: reduce-scatter of grad_h)
+                h = parallel.gather_rows(h)
         loss_name = self._loss_name(weight_margin is not None)
         if isinstance(self.predictor, (DotPredictor, MLPPredictor)):
             head = 'DOT' if isinstance(self.predictor, DotPredictor) else 'MLP'

@@ -95,3 +95,44 @@ def test_partitioned_spmm_matches_single_process_gloo_ws2():
             yl, gl, lo, hi = ret[r][reduce]
             assert rel_err(yl, y.detach()[lo:hi]) < 1e-6
             assert rel_err(gl, xr.grad[lo:hi]) < 1e-5             # summation order differs across ranks
+
+
+def _fetch_worker(rank, world_size, port, N, F, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        g = torch.Generator().manual_seed(5)
+        H = torch.randn(N, F, generator=g)
+        blk = parallel.block_size(N, world_size)
+        lo, hi = parallel.row_block(N, rank, world_size)
+        h_local = parallel.pad_rows(H[lo:hi].clone(), blk).requires_grad_(True)
+        gr = torch.Generator().manual_seed(100 + rank)
+        # this rank's distinct endpoint rows: rank 1 asks for nothing owned by rank 0's first rows, both ask for
+        # rows of both owners, one id is requested by every rank
+        ids = torch.unique(torch.cat([torch.randint(0, N, (9 + 4 * rank,), generator=gr), torch.tensor([N - 1])]))
+        rows = parallel.fetch_rows(
+            h_local, ids, gather_fn=lambda h, i: h[i],
+            scatter_fn=lambda gg, i, b: torch.zeros(b, gg.size(1)).index_add_(0, i, gg))
+        assert torch.equal(rows.detach(), H[ids])
+        gout = torch.randn(ids.numel(), F, generator=gr)
+        rows.backward(gout)
+        ret[rank] = (ids, gout, h_local.grad.clone(), lo, hi)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fetch_rows_exchange_gloo_ws3():
+    """the compact endpoint-row exchange of the partitioned scoring step: every rank receives exactly H[ids],
+    and the owners' gradient blocks add up to the single-process index_add of all ranks' gradient rows"""
+    N, F, ws = 23, 5, 3
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_fetch_worker, args=(ws, port, N, F, ret), nprocs=ws, join=True)
+    want = torch.zeros(N, F)
+    for r in range(ws):
+        ids, gout, _, _, _ = ret[r]
+        want.index_add_(0, ids, gout)
+    for r in range(ws):
+        _, _, grad_local, lo, hi = ret[r]
+        assert rel_err(grad_local[: hi - lo], want[lo:hi]) < 1e-6
+        assert torch.all(grad_local[hi - lo:] == 0)               # padding rows receive nothing
