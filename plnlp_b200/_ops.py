@@ -481,6 +481,28 @@ def fused_linear(xs, ws, bias=None, act=ACT_NONE, drop_p=0.0, seed=0):
     return FusedLinear.apply(bias, int(act), float(drop_p), int(seed), len(xs), *xs, *ws)
 
 
+def aggregate_into(adj, x, out):
+    """out = A @ x through the raw kernel (no autograd), ``out`` possibly a column slice of a wider buffer.
+    Row-partitioned adjacency: x is this rank's row block, all-gathered first (parallel.ShardedAdj)."""
+    if isinstance(adj, parallel.ShardedAdj):
+        st = structure_of(adj.local)
+        x = parallel.all_gather_rows(parallel.pad_rows(x, adj.blk), adj.group)
+    else:
+        st = structure_of(adj)
+    return spmm_raw(st.fwd, x, use_val=st.has_value, div_rows=False, out=out)
+
+
+def aggregate_t(adj, g):
+    """A^T @ g through the raw kernel; row-partitioned: the transposed product over all columns is
+    reduce-scattered to the owners of the rows"""
+    if isinstance(adj, parallel.ShardedAdj):
+        st = structure_of(adj.local)
+        full = spmm_raw(st.bwd, g, use_val=st.has_value, div_rows=False)
+        return parallel._reduce_scatter_rows(full, adj.blk, adj.group)
+    st = structure_of(adj)
+    return spmm_raw(st.bwd, g, use_val=st.has_value, div_rows=False)
+
+
 class AggLinear(torch.autograd.Function):
     """Y = act( [A x_0 | A x_1 | ...] W^T + bias ) for GCNConv's "aggregate first" order (layer.GCNConv).
 
@@ -489,16 +511,15 @@ class AggLinear(torch.autograd.Function):
     written by the SpMM kernel straight into their slice of ``buf`` (leading dimension K), so the layer is one
     SpMM per live block and ONE GEMM over K instead of a GEMM per block, and its weight gradient is one GEMM too.
     ``holder['stamp']`` counts forwards: if another forward overwrote ``buf`` before this node's backward runs,
-    the live blocks are recomputed first."""
+    the live blocks are recomputed first.  Works on a row-partitioned adjacency too (``aggregate_into``)."""
 
     @staticmethod
     def forward(ctx, W, bias, adj, buf, holder, offs, act, drop_p, seed, *xs):
-        st = structure_of(adj)
         for off, x in zip(offs, xs):
-            spmm_raw(st.fwd, x, use_val=st.has_value, div_rows=False, out=buf[:, off:off + x.size(1)])
+            aggregate_into(adj, x, buf[:, off:off + x.size(1)])
         holder["stamp"] = holder.get("stamp", 0) + 1
         Y = gemm_raw(buf, W, transb=True, bias=bias, act=act, drop_p=drop_p, seed=seed)
-        ctx.st, ctx.buf, ctx.holder, ctx.stamp, ctx.offs = st, buf, holder, holder["stamp"], offs
+        ctx.adj, ctx.buf, ctx.holder, ctx.stamp, ctx.offs = adj, buf, holder, holder["stamp"], offs
         ctx.act, ctx.drop_p, ctx.has_bias = act, drop_p, bias is not None
         ctx.save_for_backward(Y if act == ACT_RELU else None, W, *xs)
         return Y
@@ -507,13 +528,13 @@ class AggLinear(torch.autograd.Function):
     def backward(ctx, g):
         Y, W = ctx.saved_tensors[:2]
         xs = ctx.saved_tensors[2:]
-        st, buf = ctx.st, ctx.buf
+        buf = ctx.buf
         g = _rowmajor(g)
         if Y is not None:
             g = relu_drop_bwd_raw(Y, g, 1.0 / (1.0 - ctx.drop_p))
         if ctx.holder["stamp"] != ctx.stamp:          # buf was reused by a later forward: restore our blocks
             for off, x in zip(ctx.offs, xs):
-                spmm_raw(st.fwd, x, use_val=st.has_value, div_rows=False, out=buf[:, off:off + x.size(1)])
+                aggregate_into(ctx.adj, x, buf[:, off:off + x.size(1)])
             ctx.holder["stamp"] += 1
         gW = gemm_raw(g, buf, transa=True) if ctx.needs_input_grad[0] else None             # dW = dY^T [A x]
         gb = colsum_raw(g) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
@@ -523,7 +544,7 @@ class AggLinear(torch.autograd.Function):
                 gxs.append(None)
                 continue
             gu = gemm_raw(g, W[:, off:off + x.size(1)])                                      # d(A x_i) = dY W_i
-            gxs.append(spmm_raw(st.bwd, gu, use_val=st.has_value, div_rows=False))            # A^T .
+            gxs.append(aggregate_t(ctx.adj, gu)[: x.size(0)])                                 # A^T .
         return (gW, gb, None, None, None, None, None, None, None, *gxs)
 
 

@@ -45,9 +45,11 @@ def _const_aggregate(adj_t, x, reduce):
 
 
 def _agg_buffer_ok(adj_t, parts):
-    """single-device sparse adjacency, fp32 blocks: the aggregates can live side by side in one buffer"""
+    """sparse adjacency (single device or row-partitioned), fp32 blocks: the aggregates can live side by side
+    in one buffer"""
     from . import parallel
-    if isinstance(adj_t, parallel.ShardedAdj) or _ops.structure_of(adj_t).dense_ok:
+    local = adj_t.local if isinstance(adj_t, parallel.ShardedAdj) else adj_t
+    if _ops.structure_of(local).dense_ok:
         return False
     return all(p.dim() == 2 and p.dtype == torch.float32 for p in parts)
 
@@ -60,13 +62,12 @@ def _agg_buffer(adj_t, parts):
     holder = adj_t.__dict__.setdefault("_plnlp_agg_buffer", {})
     if holder.get("key") != key:
         holder.clear()
-        st = _ops.structure_of(adj_t)
-        buf = torch.empty(st.n_rows, sum(p.size(1) for p in parts), dtype=torch.float32, device=parts[0].device)
+        buf = torch.empty(adj_t.size(0), sum(p.size(1) for p in parts), dtype=torch.float32, device=parts[0].device)
         off = 0
         with torch.no_grad():
             for p in parts:
                 if _is_const(p):
-                    _ops.spmm_raw(st.fwd, p, use_val=st.has_value, div_rows=False, out=buf[:, off:off + p.size(1)])
+                    _ops.aggregate_into(adj_t, p, buf[:, off:off + p.size(1)])
                 off += p.size(1)
         holder.update(key=key, buf=buf, stamp=0)
     offs, xs, off = [], [], 0

@@ -77,19 +77,24 @@ def _reduce_scatter_rows(full, blk, group=None):
     return out
 
 
+def all_gather_rows(x_local, group=None):
+    """[blk, F] row block -> [R*blk, F] (no autograd)"""
+    _, ws = world()
+    full = torch.empty(ws * x_local.size(0), x_local.size(1), dtype=x_local.dtype, device=x_local.device)
+    from . import profiling
+    with profiling.span("nccl all_gather (rows)", (ws - 1) * x_local.numel() * 4, 0):
+        dist.all_gather_into_tensor(full, x_local.contiguous(), group=group)
+    return full
+
+
 class GatherRows(torch.autograd.Function):
     """x_local [blk, F] (row block of a row-partitioned matrix, zero padded to blk) -> x_full [R*blk, F].
     Backward: reduce-scatter of the incoming gradient."""
 
     @staticmethod
     def forward(ctx, x_local, group):
-        _, ws = world()
         ctx.group, ctx.blk = group, x_local.size(0)
-        full = torch.empty(ws * x_local.size(0), x_local.size(1), dtype=x_local.dtype, device=x_local.device)
-        from . import profiling
-        with profiling.span("nccl all_gather (rows)", (ws - 1) * x_local.numel() * 4, 0):
-            dist.all_gather_into_tensor(full, x_local.contiguous(), group=group)
-        return full
+        return all_gather_rows(x_local, group)
 
     @staticmethod
     def backward(ctx, g):

@@ -70,6 +70,12 @@ def _worker(rank, ws, port, ret):
         pos_all = torch.randint(0, N, (ws * B, 2), generator=gg).to(dev)
         neg_all = torch.randint(0, N, (ws * B, k, 2), generator=gg).to(dev)
         feats = torch.randn(N, 8, generator=gg).to(dev)
+        # fresh adjacency objects with the dense tensor-core path off, so that the CSR kernels and the
+        # aggregate-buffer path of GCNConv (single-device and row-partitioned) are what is compared
+        from plnlp_b200 import graph
+        graph.DENSE_SPMM = False
+        adj = CSRGraph(*adj.csr(), (N, N))
+        sadj = parallel.shard_graph(adj, rank, ws, CSRGraph)
         single = _model(N, 8, dev, "GCN")
         d1 = Data(); d1.adj_t, d1.x, d1.edge_index = adj, feats, None
         single.encoder.train(); single.predictor.train()
@@ -101,6 +107,7 @@ def _worker(rank, ws, port, ret):
             for (n1, a), b in zip(part.predictor.named_parameters(), single.predictor.parameters()):
                 errs[mode + ".pred." + n1] = rel_err(a.grad, b.grad)
         parallel.EXCHANGE = "rows"
+        assert "_plnlp_agg_buffer" in sadj.__dict__ and "_plnlp_agg_buffer" in adj.__dict__
         ret[rank] = {"spmm_fwd": e_fwd, "spmm_bwd": e_bwd, **errs}
     finally:
         dist.destroy_process_group()
