@@ -70,7 +70,7 @@ def new_seed():
 # ---------------------------------------------------------------------------
 # raw launches
 # ---------------------------------------------------------------------------
-def spmm_raw(plan, x, use_val, div_rows, bias=None, relu=False, drop_p=0.0, seed=0, out=None):
+def spmm_raw(plan, x, use_val, div_rows, bias=None, relu=False, drop_p=0.0, seed=0, out=None, x_mask=None):
     """fp32 features, or bf16 features (bf16 storage in and out, fp32 accumulation -- the separately stated
     bf16 path; autograd and the models stay fp32)."""
     lib = _lib.load()
@@ -95,9 +95,13 @@ def spmm_raw(plan, x, use_val, div_rows, bias=None, relu=False, drop_p=0.0, seed
     val = plan.val if use_val else None
     alg = plan.alg_bytes(F, 2 if bf16 else 4) - (0 if use_val or plan.val is None else plan.nnz * 4)
     fn, name = (lib.plnlp_spmm_csr_bf16, "spmm_csr_bf16") if bf16 else (lib.plnlp_spmm_csr_f32, "spmm_csr_f32")
+    if x_mask is not None:
+        if x_mask.dtype != torch.uint8 or x_mask.numel() != plan.n_cols or not x_mask.is_cuda:
+            raise RuntimeError("x_mask must be a CUDA uint8 vector with one flag per row of x")
+        name += " (row-sparse operand)"     # algorithmic bytes stay those of the dense gather model
     with profiling.span(name, alg, 0):
         check(fn(ptr(plan.item_ptr), ptr(plan.item_row), ptr(plan.item_slot), plan.n_items,
-                 ptr(plan.col), ptr(val), ptr(plan.row_cnt if div_rows else None), ptr(bias),
+                 ptr(x_mask), ptr(plan.col), ptr(val), ptr(plan.row_cnt if div_rows else None), ptr(bias),
                  int(relu), float(drop_p), int(seed), ptr(x), _ld(x), ptr(out), _ld(out), F,
                  ptr(partial), ptr(plan.fix_ptr), ptr(plan.fix_row), plan.n_fix, stream()),
               "plnlp_" + name)
@@ -148,6 +152,52 @@ def gemm_raw(A, B, transa=False, transb=False, C=None, beta=0.0, bias=None, act=
         else:
             check(lib.plnlp_gemm_tf32(3 if backend == "tf32x3" else 1, *tail), "plnlp_gemm_tf32")
     return C
+
+
+def row_nonzero_mask_raw(x):
+    """uint8 [rows]: 1 where the row of x has a non-zero entry"""
+    lib = _lib.load()
+    x = _rowmajor(x)
+    mask = torch.empty(x.size(0), dtype=torch.uint8, device=x.device)
+    with profiling.span("row_nonzero_mask_f32", x.numel() * 4 + x.size(0), 0):
+        check(lib.plnlp_row_nonzero_mask_f32(ptr(x), _ld(x), x.size(0), x.size(1), ptr(mask), stream()),
+              "plnlp_row_nonzero_mask_f32")
+    return mask
+
+
+# Row-sparsity hints for gradients.  The gradient of the embeddings w.r.t. the scoring loss is non-zero only at
+# the endpoint rows of the edge batch; ``row_sparse_grad(h)`` (an identity in forward) measures that on the
+# incoming gradient and leaves a flag vector here, keyed by the gradient's storage, for the backward of the
+# layer that produced h: its A^T g product then skips the all-zero rows (spmm_raw(x_mask=)).  Ops that map zero
+# rows to zero rows (relu mask, g @ W) hand the hint on to their result.
+_ROW_HINTS = {}
+
+
+def _put_hint(t, mask):
+    if len(_ROW_HINTS) > 4:
+        _ROW_HINTS.clear()
+    _ROW_HINTS[t.data_ptr()] = (t.size(0), mask)
+
+
+def _take_hint(t):
+    hit = _ROW_HINTS.pop(t.data_ptr(), None)
+    return hit[1] if hit is not None and hit[0] == t.size(0) else None
+
+
+class RowSparseGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _rowmajor(g)
+        _put_hint(g, row_nonzero_mask_raw(g))
+        return g
+
+
+def row_sparse_grad(x):
+    return RowSparseGrad.apply(x)
 
 
 def colsum_raw(x, scale=1.0):
@@ -414,8 +464,9 @@ class SpMM(torch.autograd.Function):
     def backward(ctx, g):
         (out,) = ctx.saved_tensors
         g = _rowmajor(g)
+        hint = _take_hint(g)
         if out is not None:
-            g = relu_drop_bwd_raw(out, g, 1.0 / (1.0 - ctx.drop_p))
+            g = relu_drop_bwd_raw(out, g, 1.0 / (1.0 - ctx.drop_p))      # zero rows stay zero rows
         gb = colsum_raw(g) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
         gx = None
         if ctx.needs_input_grad[0]:
@@ -423,7 +474,8 @@ class SpMM(torch.autograd.Function):
                 gx = gemm_raw(ctx.st.dense(ctx.mean), g, transa=True)          # A^T g on the tensor cores
             else:
                 plan = ctx.st.bwd_mean if ctx.mean else ctx.st.bwd
-                gx = spmm_raw(plan, g, use_val=True if ctx.mean else ctx.st.has_value, div_rows=False)
+                gx = spmm_raw(plan, g, use_val=True if ctx.mean else ctx.st.has_value, div_rows=False,
+                              x_mask=hint)
         return gx, gb, None, None, None, None, None
 
 
@@ -464,12 +516,15 @@ class FusedLinear(torch.autograd.Function):
         Y, n = saved[0], ctx.n
         xs, ws = saved[1:1 + n], saved[1 + n:]
         g = _rowmajor(g)
+        hint = _take_hint(g)
         if Y is not None:
             g = relu_drop_bwd_raw(Y, g, 1.0 / (1.0 - ctx.drop_p))
         gb = colsum_raw(g) if (ctx.has_bias and ctx.needs_input_grad[0]) else None
         gxs, gws = [], []
         for i in range(n):
             gx = gemm_raw(g, ws[i]) if ctx.needs_input_grad[5 + i] else None          # dX = dY @ W
+            if gx is not None and hint is not None:
+                _put_hint(gx, hint)                                                   # zero rows of dY -> zero rows of dX
             gw = gemm_raw(g, xs[i], transa=True) if ctx.needs_input_grad[5 + n + i] else None  # dW = dY^T @ X
             gxs.append(gx)
             gws.append(gw)

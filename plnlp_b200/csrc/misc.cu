@@ -56,7 +56,27 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
     out[c] = static_cast<float>(acc) * scale;
 }
 
+// mask[r] = any(x[r, :] != 0): one warp per row, the row-sparsity flags of the SpMM's x_mask
+template <int VEC>
+__global__ void __launch_bounds__(256) row_nonzero_mask_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows,
+                                                               int F, uint8_t* __restrict__ mask) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const float* xr = x + r * ldx;
+    bool nz = false;
+    for (int f = lane * VEC; f < F; f += 32 * VEC) {
+        float a[VEC];
+        load_vec<VEC>(a, xr + f);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) nz |= !(a[e] == 0.0f);      // NaN counts as non-zero
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, nz);
+    if (lane == 0) mask[r] = any ? 1 : 0;
+}
+
 }  // namespace plnlp
+
 
 using namespace plnlp;
 
@@ -110,6 +130,22 @@ extern "C" int plnlp_colsum_f32(const float* x, int64_t ldx, int64_t rows, int64
         PLNLP_LAUNCH_CHECK();
     }
     colsum_final_kernel<<<gx, 256, 0, st>>>(ws, nblk, cols, scale, out);
+    PLNLP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int plnlp_row_nonzero_mask_f32(const float* x, int64_t ldx, int64_t rows, int64_t F, uint8_t* mask,
+                                          void* stream) {
+    using namespace plnlp;
+    PLNLP_REQUIRE(rows >= 0 && F > 0 && ldx >= F, PLNLP_E_SIZE);
+    if (rows == 0) return 0;
+    PLNLP_REQUIRE(x && mask, PLNLP_E_NULL);
+    const int vec = pick_vec(F, {ldx}, {x});
+    const unsigned grid = static_cast<unsigned>(ceil_div(rows, 8));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (vec == 4) row_nonzero_mask_kernel<4><<<grid, 256, 0, st>>>(x, ldx, rows, static_cast<int>(F), mask);
+    else if (vec == 2) row_nonzero_mask_kernel<2><<<grid, 256, 0, st>>>(x, ldx, rows, static_cast<int>(F), mask);
+    else row_nonzero_mask_kernel<1><<<grid, 256, 0, st>>>(x, ldx, rows, static_cast<int>(F), mask);
     PLNLP_LAUNCH_CHECK();
     return 0;
 }

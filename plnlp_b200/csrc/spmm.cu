@@ -28,6 +28,7 @@ struct SpmmParamsT {
     const int32_t* item_row;
     const int32_t* item_slot;
     int64_t n_items;
+    const uint8_t* x_mask;     // optional: x_mask[j] == 0 promises that row j of x is all zeros (skipped)
     const int32_t* col;
     const float* val;
     const float* row_div;
@@ -150,6 +151,46 @@ __device__ __forceinline__ void gather_block(const T* __restrict__ xb, int64_t l
     }
 }
 
+// Row-sparse operand: only the entries whose source row is flagged non-zero are gathered.  `live` is the warp's
+// ballot over the current 32 entries; the next NB set bits (in entry order, so the accumulation order of the
+// surviving terms is unchanged and the skipped terms are exact zeros) are consumed per call.
+template <typename T, int VEC, int U, int NB, bool HAS_VAL>
+__device__ __forceinline__ void gather_block_masked(const T* __restrict__ xb, int64_t ldx, int c, float v,
+                                                    unsigned& live, const bool (&act)[U], float (&acc)[U][VEC]) {
+    float t[NB][U][VEC];
+    float vv[NB];
+    bool ok[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        ok[b] = live != 0u;
+        const int src = ok[b] ? (__ffs(live) - 1) : 0;
+        live &= live - 1u;                                   // 0 stays 0
+        const int cj = __shfl_sync(0xffffffffu, c, src);
+        vv[b] = HAS_VAL ? __shfl_sync(0xffffffffu, v, src) : 1.0f;
+        const T* row = xb + static_cast<int64_t>(cj) * ldx;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (ok[b] && act[u]) {
+                load_vec<VEC>(t[b][u], row + u * 32 * VEC);
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) t[b][u][e] = 0.0f;
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        if (ok[b]) {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e)
+                    acc[u][e] = HAS_VAL ? __fadd_rn(acc[u][e], __fmul_rn(vv[b], t[b][u][e]))
+                                        : __fadd_rn(acc[u][e], t[b][u][e]);
+        }
+    }
+}
+
 // NB = neighbours whose rows are in flight together (NB x U 16-byte loads per lane)
 // The kernel is latency bound (ncu: >80 % of the stall samples are long-scoreboard waits on the gathers), so
 // resident warps matter more than per-warp depth: variants whose in-flight tile fits 8 registers are held to
@@ -181,7 +222,11 @@ __global__ void __launch_bounds__(256, (NB * U * VEC <= 8) ? 8 : (NB * U * VEC <
             c = __ldg(p.col + base + lane);
             if (HAS_VAL) v = __ldg(p.val + base + lane);
         }
-        if (n == 32) {
+        if (p.x_mask) {                                          // warp-uniform
+            unsigned live = __ballot_sync(0xffffffffu, lane < n && __ldg(p.x_mask + c) != 0);
+#pragma unroll 1
+            while (live) gather_block_masked<T, VEC, U, NB, HAS_VAL>(xb, p.ldx, c, v, live, act, acc);
+        } else if (n == 32) {
 #pragma unroll 1
             for (int j = 0; j < 32; j += NB)
                 gather_block<T, VEC, U, NB, HAS_VAL, false>(xb, p.ldx, c, v, j, n, act, acc);
@@ -276,7 +321,7 @@ static int dispatch_u(const SpmmParamsT<T>& p, cudaStream_t st) {
 }  // namespace plnlp
 
 extern "C" int plnlp_spmm_csr_f32(const int32_t* item_ptr, const int32_t* item_row, const int32_t* item_slot,
-                                  int64_t n_items, const int32_t* col, const float* val,
+                                  int64_t n_items, const uint8_t* x_mask, const int32_t* col, const float* val,
                                   const float* row_div, const float* bias, int relu, float drop_p,
                                   uint64_t seed, const float* x, int64_t ldx, float* out, int64_t ldo,
                                   int64_t F, float* partial, const int32_t* fix_ptr, const int32_t* fix_row,
@@ -288,7 +333,7 @@ extern "C" int plnlp_spmm_csr_f32(const int32_t* item_ptr, const int32_t* item_r
     PLNLP_REQUIRE(ldx >= F && ldo >= F, PLNLP_E_SIZE);
     PLNLP_REQUIRE(drop_p >= 0.0f && drop_p < 1.0f, PLNLP_E_SIZE);
     if (n_fix > 0) PLNLP_REQUIRE(partial && fix_ptr && fix_row, PLNLP_E_NULL);
-    SpmmParams p{item_ptr, item_row, item_slot, n_items, col, val, row_div, bias, relu, drop_p, seed,
+    SpmmParams p{item_ptr, item_row, item_slot, n_items, x_mask, col, val, row_div, bias, relu, drop_p, seed,
                  x, ldx, out, ldo, static_cast<int>(F), partial, fix_ptr, fix_row, n_fix};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool v4 = (F % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned(x, 16) && aligned(out, 16) &&
@@ -303,7 +348,7 @@ extern "C" int plnlp_spmm_csr_f32(const int32_t* item_ptr, const int32_t* item_r
 // bf16 feature storage (x and out are bf16 bit patterns), fp32 accumulation in CSR order, one RN rounding at
 // the store.  Same plan, epilogue and Philox indexing as the fp32 entry point; `partial` stays fp32.
 extern "C" int plnlp_spmm_csr_bf16(const int32_t* item_ptr, const int32_t* item_row, const int32_t* item_slot,
-                                   int64_t n_items, const int32_t* col, const float* val,
+                                   int64_t n_items, const uint8_t* x_mask, const int32_t* col, const float* val,
                                    const float* row_div, const float* bias, int relu, float drop_p,
                                    uint64_t seed, const uint16_t* x, int64_t ldx, uint16_t* out, int64_t ldo,
                                    int64_t F, float* partial, const int32_t* fix_ptr, const int32_t* fix_row,
@@ -315,7 +360,7 @@ extern "C" int plnlp_spmm_csr_bf16(const int32_t* item_ptr, const int32_t* item_
     PLNLP_REQUIRE(ldx >= F && ldo >= F, PLNLP_E_SIZE);
     PLNLP_REQUIRE(drop_p >= 0.0f && drop_p < 1.0f, PLNLP_E_SIZE);
     if (n_fix > 0) PLNLP_REQUIRE(partial && fix_ptr && fix_row, PLNLP_E_NULL);
-    SpmmParamsT<__nv_bfloat16> p{item_ptr, item_row, item_slot, n_items, col, val, row_div, bias, relu, drop_p, seed,
+    SpmmParamsT<__nv_bfloat16> p{item_ptr, item_row, item_slot, n_items, x_mask, col, val, row_div, bias, relu, drop_p, seed,
                                  reinterpret_cast<const __nv_bfloat16*>(x), ldx,
                                  reinterpret_cast<__nv_bfloat16*>(out), ldo, static_cast<int>(F), partial, fix_ptr,
                                  fix_row, n_fix};

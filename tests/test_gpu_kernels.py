@@ -76,6 +76,49 @@ def test_spmm_split_rows(ops, chunk):
     assert torch.equal(got, got2)            # deterministic
 
 
+@pytest.mark.parametrize("F", [3, 50, 200, 512])
+def test_spmm_row_sparse_operand_mask(ops, F, monkeypatch):
+    """x_mask skips the gathers of all-zero rows of x: identical bits to the dense kernel (the skipped terms are
+    exact zeros, the surviving ones keep their CSR order), valued and value-less, hub rows included; and the
+    autograd hint path (row_sparse_grad -> SpMM.backward) gives the same gradient as the plain path"""
+    from plnlp_b200 import graph
+    from plnlp_b200.graph import Structure
+    monkeypatch.setattr(graph, "DENSE_SPMM", False)       # CSR kernels also for the autograd part below
+    N = 260
+    ei, w = rand_graph(N, 4000, seed=F, weighted=True, hub=True)
+    g = _to_gpu_graph(sparse.to_sparse_tensor(ei, w, N))
+    st = Structure(g, chunk=64)
+    assert st.fwd.n_fix > 0
+    gen = torch.Generator().manual_seed(F)
+    x = torch.randn(N, F, generator=gen)
+    keep = torch.rand(N, generator=gen) < 0.15
+    keep[2] = True                                     # the hub column stays live
+    x[~keep] = 0
+    xg = x.cuda()
+    mask = ops.row_nonzero_mask_raw(xg)
+    assert torch.equal(mask.cpu().bool(), keep)
+    for use_val, div in ((True, False), (False, True)):
+        plan = st.fwd if use_val else st.fwd_noval
+        dense = ops.spmm_raw(plan, xg, use_val=use_val, div_rows=div)
+        sparse_ = ops.spmm_raw(plan, xg, use_val=use_val, div_rows=div, x_mask=mask)
+        assert torch.equal(dense, sparse_)
+    none = ops.spmm_raw(st.fwd, xg, use_val=True, div_rows=False, x_mask=torch.zeros_like(mask))
+    assert torch.all(none == 0)
+    # autograd: gradient that is non-zero only at a few rows
+    idx = torch.nonzero(keep).reshape(-1).cuda()
+    wgt = torch.randn(idx.numel(), F, generator=gen).cuda()
+    grads = []
+    for hinted in (False, True):
+        z = torch.randn(N, F, generator=torch.Generator().manual_seed(1)).cuda().requires_grad_(True)
+        y = ops.spmm(g, z, "sum", relu=True)
+        if hinted:
+            y = ops.row_sparse_grad(y)
+        (y[idx] * wgt).sum().backward()
+        grads.append(z.grad.clone())
+    assert torch.equal(grads[0], grads[1])
+    assert not ops._ROW_HINTS                          # the hint was consumed
+
+
 def test_spmm_all_rows_empty(ops):
     from plnlp_b200.graph import CSRGraph
     N, F = 70, 8
