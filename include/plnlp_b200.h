@@ -71,25 +71,31 @@ int64_t plnlp_launch_count(void);
  * loop).  Longer (hub) rows are split into several items that write fp32 partial sums to
  * partial[item_slot], combined in slot order by a second fixed-order pass (deterministic).
  *   fix_row[j] / fix_ptr[j..j+1] : split row j and its range of partial slots.
- * x_mask (optional, one byte per row of x): x_mask[j] == 0 is the caller's promise that row j of x is all
- * zeros; such entries are skipped without being gathered (the skipped terms are exact zeros and the
- * surviving ones keep their order, so the result is unchanged).  Used for the backward of the LAST conv,
- * whose incoming gradient is non-zero only at the endpoint rows of the edge batch (model.py:152-161):
- * ~10 % of citation2-shape's rows, ~25 % of the stored entries.  plnlp_row_nonzero_mask_f32 builds it.
+ * item_end (optional): explicit end offset of every item, for plans over a SUBSET of the rows (items are then
+ * not contiguous); NULL = item i ends at item_ptr[i+1].  With a subset plan item_row holds the COMPACT output row.
+ * Used for the forward of the LAST conv, whose output is only read at the endpoint rows of the edge batch
+ * (model.py:152-156): ~10 % of citation2-shape's rows, ~25 % of the stored entries.
+ * x_index (optional, one int32 per column of the adjacency): source j reads row x_index[j] of x; a negative
+ * value is the caller's promise that this source row is all zeros -- it is skipped without being gathered
+ * (the skipped terms are exact zeros and the surviving ones keep their order, so the result is unchanged).
+ * Used for the backward of the last conv: the incoming gradient is non-zero only at the endpoint rows, either
+ * as a compact [T, F] matrix (x_index = position in it) or as a full matrix (x_index[j] = j where row j is
+ * non-zero, plnlp_row_nonzero_index_f32 builds that).
  * val == NULL: value-less adjacency.  row_div == NULL: no division (sum); SAGE mean passes
  * row_div[r] = max(row_nnz, 1) and gets the IEEE division upstream performs.
  * F: feature width; x/out leading dims in floats.  16-byte vector loads are used when F,
  * ldx, ldo are multiples of 4 and the bases are 16-byte aligned; otherwise 8- or 4-byte.
  */
 int plnlp_spmm_csr_f32(const int32_t* item_ptr, const int32_t* item_row, const int32_t* item_slot,
-                       int64_t n_items, const uint8_t* x_mask, const int32_t* col, const float* val,
+                       int64_t n_items, const int32_t* item_end, const int32_t* x_index,
+                       const int32_t* col, const float* val,
                        const float* row_div, const float* bias, int relu, float drop_p, uint64_t seed,
                        const float* x, int64_t ldx, float* out, int64_t ldo, int64_t F,
                        float* partial, const int32_t* fix_ptr, const int32_t* fix_row, int64_t n_fix,
                        void* stream);
 
-/* mask[r] = 1 if any of x[r, 0..F) is non-zero (NaN counts as non-zero), else 0: the x_mask of the SpMM. */
-int plnlp_row_nonzero_mask_f32(const float* x, int64_t ldx, int64_t rows, int64_t F, uint8_t* mask, void* stream);
+/* index[r] = r if any of x[r, 0..F) is non-zero (NaN counts as non-zero), else -1: an x_index of the SpMM. */
+int plnlp_row_nonzero_index_f32(const float* x, int64_t ldx, int64_t rows, int64_t F, int32_t* index, void* stream);
 
 /* The same SpMM on bf16 feature storage (the "bf16 path, stated separately" of BASELINE.json's north_star;
  * config 5 sweeps fp32 and bf16): x and out hold bf16 bit patterns, leading dims in ELEMENTS; every output
@@ -97,7 +103,8 @@ int plnlp_row_nonzero_mask_f32(const float* x, int64_t ldx, int64_t rows, int64_
  * the partial slots of split rows stay fp32.  Halves the gathered bytes: nnz*F*2 per launch.  16-byte loads
  * (8 features per lane) for F >= 256, 8-byte for F >= 128, 4-byte below, alignment permitting. */
 int plnlp_spmm_csr_bf16(const int32_t* item_ptr, const int32_t* item_row, const int32_t* item_slot,
-                        int64_t n_items, const uint8_t* x_mask, const int32_t* col, const float* val,
+                        int64_t n_items, const int32_t* item_end, const int32_t* x_index,
+                       const int32_t* col, const float* val,
                         const float* row_div, const float* bias, int relu, float drop_p, uint64_t seed,
                         const uint16_t* x, int64_t ldx, uint16_t* out, int64_t ldo, int64_t F,
                         float* partial, const int32_t* fix_ptr, const int32_t* fix_row, int64_t n_fix,

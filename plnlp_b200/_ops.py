@@ -70,7 +70,7 @@ def new_seed():
 # ---------------------------------------------------------------------------
 # raw launches
 # ---------------------------------------------------------------------------
-def spmm_raw(plan, x, use_val, div_rows, bias=None, relu=False, drop_p=0.0, seed=0, out=None, x_mask=None):
+def spmm_raw(plan, x, use_val, div_rows, bias=None, relu=False, drop_p=0.0, seed=0, out=None, x_index=None):
     """fp32 features, or bf16 features (bf16 storage in and out, fp32 accumulation -- the separately stated
     bf16 path; autograd and the models stay fp32)."""
     lib = _lib.load()
@@ -83,7 +83,7 @@ def spmm_raw(plan, x, use_val, div_rows, bias=None, relu=False, drop_p=0.0, seed
     else:
         x = _rowmajor(x)
     F = x.size(1)
-    if x.size(0) != plan.n_cols:
+    if x_index is None and x.size(0) != plan.n_cols:
         raise RuntimeError(f"SpMM shape mismatch: adjacency has {plan.n_cols} columns, x has {x.size(0)} rows")
     if out is None:
         out = torch.empty(plan.n_rows, F, dtype=x.dtype, device=x.device)
@@ -95,13 +95,15 @@ def spmm_raw(plan, x, use_val, div_rows, bias=None, relu=False, drop_p=0.0, seed
     val = plan.val if use_val else None
     alg = plan.alg_bytes(F, 2 if bf16 else 4) - (0 if use_val or plan.val is None else plan.nnz * 4)
     fn, name = (lib.plnlp_spmm_csr_bf16, "spmm_csr_bf16") if bf16 else (lib.plnlp_spmm_csr_f32, "spmm_csr_f32")
-    if x_mask is not None:
-        if x_mask.dtype != torch.uint8 or x_mask.numel() != plan.n_cols or not x_mask.is_cuda:
-            raise RuntimeError("x_mask must be a CUDA uint8 vector with one flag per row of x")
+    if x_index is not None:
+        if x_index.dtype != torch.int32 or x_index.numel() != plan.n_cols or not x_index.is_cuda:
+            raise RuntimeError("x_index must be a CUDA int32 vector with one entry per column of the adjacency")
         name += " (row-sparse operand)"     # algorithmic bytes stay those of the dense gather model
+    if getattr(plan, "subset", False):
+        name += " (row subset)"
     with profiling.span(name, alg, 0):
         check(fn(ptr(plan.item_ptr), ptr(plan.item_row), ptr(plan.item_slot), plan.n_items,
-                 ptr(x_mask), ptr(plan.col), ptr(val), ptr(plan.row_cnt if div_rows else None), ptr(bias),
+                 ptr(plan.item_end), ptr(x_index), ptr(plan.col), ptr(val), ptr(plan.row_cnt if div_rows else None), ptr(bias),
                  int(relu), float(drop_p), int(seed), ptr(x), _ld(x), ptr(out), _ld(out), F,
                  ptr(partial), ptr(plan.fix_ptr), ptr(plan.fix_row), plan.n_fix, stream()),
               "plnlp_" + name)
@@ -154,21 +156,21 @@ def gemm_raw(A, B, transa=False, transb=False, C=None, beta=0.0, bias=None, act=
     return C
 
 
-def row_nonzero_mask_raw(x):
-    """uint8 [rows]: 1 where the row of x has a non-zero entry"""
+def row_nonzero_index_raw(x):
+    """int32 [rows]: r where row r of x has a non-zero entry, else -1 (an ``x_index`` for spmm_raw)"""
     lib = _lib.load()
     x = _rowmajor(x)
-    mask = torch.empty(x.size(0), dtype=torch.uint8, device=x.device)
-    with profiling.span("row_nonzero_mask_f32", x.numel() * 4 + x.size(0), 0):
-        check(lib.plnlp_row_nonzero_mask_f32(ptr(x), _ld(x), x.size(0), x.size(1), ptr(mask), stream()),
-              "plnlp_row_nonzero_mask_f32")
-    return mask
+    index = torch.empty(x.size(0), dtype=torch.int32, device=x.device)
+    with profiling.span("row_nonzero_index_f32", x.numel() * 4 + x.size(0) * 4, 0):
+        check(lib.plnlp_row_nonzero_index_f32(ptr(x), _ld(x), x.size(0), x.size(1), ptr(index), stream()),
+              "plnlp_row_nonzero_index_f32")
+    return index
 
 
 # Row-sparsity hints for gradients.  The gradient of the embeddings w.r.t. the scoring loss is non-zero only at
 # the endpoint rows of the edge batch; ``row_sparse_grad(h)`` (an identity in forward) measures that on the
-# incoming gradient and leaves a flag vector here, keyed by the gradient's storage, for the backward of the
-# layer that produced h: its A^T g product then skips the all-zero rows (spmm_raw(x_mask=)).  Ops that map zero
+# incoming gradient and leaves an index vector here, keyed by the gradient's storage, for the backward of the
+# layer that produced h: its A^T g product then skips the all-zero rows (spmm_raw(x_index=)).  Ops that map zero
 # rows to zero rows (relu mask, g @ W) hand the hint on to their result.
 _ROW_HINTS = {}
 
@@ -192,7 +194,7 @@ class RowSparseGrad(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         g = _rowmajor(g)
-        _put_hint(g, row_nonzero_mask_raw(g))
+        _put_hint(g, row_nonzero_index_raw(g))
         return g
 
 
@@ -475,7 +477,7 @@ class SpMM(torch.autograd.Function):
             else:
                 plan = ctx.st.bwd_mean if ctx.mean else ctx.st.bwd
                 gx = spmm_raw(plan, g, use_val=True if ctx.mean else ctx.st.has_value, div_rows=False,
-                              x_mask=hint)
+                              x_index=hint)
         return gx, gb, None, None, None, None, None
 
 
@@ -487,6 +489,53 @@ def spmm(adj, x, reduce="sum", bias=None, relu=False, drop_p=0.0, seed=0):
     if reduce not in ("sum", "mean"):
         raise NotImplementedError(f"reduce={reduce!r}")
     return SpMM.apply(x, bias, adj, reduce, bool(relu), float(drop_p), int(seed))
+
+
+class SpMMRows(torch.autograd.Function):
+    """out[t, :] = epi( (A @ x)[rows[t], :] ): the SpMM for a SUBSET of the output rows, written compactly.
+
+    The last conv's output is read only at the endpoint rows of the edge batch (model.py:152-156), so the other
+    rows are never computed: ~10 % of citation2-shape's rows / ~25 % of the stored entries per batch.  The values
+    at the selected rows are those of the full product, bit for bit (same per-row accumulation order).  Backward:
+    A[rows, :]^T @ g with the compact gradient as a row-sparse operand of the transposed plan (x_index)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, adj, rows, reduce, relu, drop_p, seed):
+        from .graph import build_subset_plan
+        st = structure_of(adj)
+        mean = reduce == "mean"
+        parent = st.fwd_noval if mean else st.fwd
+        plan = build_subset_plan(parent, st.rowptr, rows)
+        out = spmm_raw(plan, x, use_val=not mean, div_rows=mean, bias=bias, relu=relu, drop_p=drop_p, seed=seed)
+        ctx.st, ctx.mean, ctx.drop_p, ctx.has_bias = st, mean, drop_p, bias is not None
+        ctx.save_for_backward(rows, out if (relu or drop_p > 0) else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        rows, out = ctx.saved_tensors
+        st = ctx.st
+        g = _rowmajor(g)
+        if out is not None:
+            g = relu_drop_bwd_raw(out, g, 1.0 / (1.0 - ctx.drop_p))
+        gb = colsum_raw(g) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            x_index = torch.full((st.n_rows,), -1, dtype=torch.int32, device=g.device)
+            x_index[rows] = torch.arange(rows.numel(), dtype=torch.int32, device=g.device)
+            plan = st.bwd_mean if ctx.mean else st.bwd
+            gx = spmm_raw(plan, g, use_val=True if ctx.mean else st.has_value, div_rows=False, x_index=x_index)
+        return gx, gb, None, None, None, None, None, None
+
+
+def spmm_rows(adj, x, rows, reduce="sum", bias=None, relu=False, drop_p=0.0, seed=0):
+    if reduce == "add":
+        reduce = "sum"
+    if reduce not in ("sum", "mean"):
+        raise NotImplementedError(f"reduce={reduce!r}")
+    if rows.dtype != torch.int64 or rows.dim() != 1 or not rows.is_cuda:
+        raise RuntimeError("rows must be a 1-D CUDA int64 tensor of distinct row ids")
+    return SpMMRows.apply(x, bias, adj, rows, reduce, bool(relu), float(drop_p), int(seed))
 
 
 class FusedLinear(torch.autograd.Function):

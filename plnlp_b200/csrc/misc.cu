@@ -56,10 +56,10 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
     out[c] = static_cast<float>(acc) * scale;
 }
 
-// mask[r] = any(x[r, :] != 0): one warp per row, the row-sparsity flags of the SpMM's x_mask
+// index[r] = any(x[r, :] != 0) ? r : -1: one warp per row, a row-sparsity x_index for the SpMM
 template <int VEC>
-__global__ void __launch_bounds__(256) row_nonzero_mask_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows,
-                                                               int F, uint8_t* __restrict__ mask) {
+__global__ void __launch_bounds__(256) row_nonzero_index_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows,
+                                                               int F, int32_t* __restrict__ index) {
     const int lane = threadIdx.x & 31;
     const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= rows) return;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) row_nonzero_mask_kernel(const float* __re
         for (int e = 0; e < VEC; ++e) nz |= !(a[e] == 0.0f);      // NaN counts as non-zero
     }
     const unsigned any = __ballot_sync(0xffffffffu, nz);
-    if (lane == 0) mask[r] = any ? 1 : 0;
+    if (lane == 0) index[r] = any ? static_cast<int32_t>(r) : -1;
 }
 
 }  // namespace plnlp
@@ -134,18 +134,18 @@ extern "C" int plnlp_colsum_f32(const float* x, int64_t ldx, int64_t rows, int64
     return 0;
 }
 
-extern "C" int plnlp_row_nonzero_mask_f32(const float* x, int64_t ldx, int64_t rows, int64_t F, uint8_t* mask,
-                                          void* stream) {
+extern "C" int plnlp_row_nonzero_index_f32(const float* x, int64_t ldx, int64_t rows, int64_t F, int32_t* index,
+                                           void* stream) {
     using namespace plnlp;
-    PLNLP_REQUIRE(rows >= 0 && F > 0 && ldx >= F, PLNLP_E_SIZE);
+    PLNLP_REQUIRE(rows >= 0 && rows < (1ll << 31) && F > 0 && ldx >= F, PLNLP_E_SIZE);
     if (rows == 0) return 0;
-    PLNLP_REQUIRE(x && mask, PLNLP_E_NULL);
+    PLNLP_REQUIRE(x && index, PLNLP_E_NULL);
     const int vec = pick_vec(F, {ldx}, {x});
     const unsigned grid = static_cast<unsigned>(ceil_div(rows, 8));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (vec == 4) row_nonzero_mask_kernel<4><<<grid, 256, 0, st>>>(x, ldx, rows, static_cast<int>(F), mask);
-    else if (vec == 2) row_nonzero_mask_kernel<2><<<grid, 256, 0, st>>>(x, ldx, rows, static_cast<int>(F), mask);
-    else row_nonzero_mask_kernel<1><<<grid, 256, 0, st>>>(x, ldx, rows, static_cast<int>(F), mask);
+    if (vec == 4) row_nonzero_index_kernel<4><<<grid, 256, 0, st>>>(x, ldx, rows, static_cast<int>(F), index);
+    else if (vec == 2) row_nonzero_index_kernel<2><<<grid, 256, 0, st>>>(x, ldx, rows, static_cast<int>(F), index);
+    else row_nonzero_index_kernel<1><<<grid, 256, 0, st>>>(x, ldx, rows, static_cast<int>(F), index);
     PLNLP_LAUNCH_CHECK();
     return 0;
 }

@@ -28,7 +28,8 @@ struct SpmmParamsT {
     const int32_t* item_row;
     const int32_t* item_slot;
     int64_t n_items;
-    const uint8_t* x_mask;     // optional: x_mask[j] == 0 promises that row j of x is all zeros (skipped)
+    const int32_t* item_end;   // optional explicit item ends (row-subset plans); NULL: item i ends at item_ptr[i+1]
+    const int32_t* x_index;    // optional: source j reads row x_index[j] of x; x_index[j] < 0 = an all-zero row (skipped)
     const int32_t* col;
     const float* val;
     const float* row_div;
@@ -212,7 +213,8 @@ __global__ void __launch_bounds__(256, (NB * U * VEC <= 8) ? 8 : (NB * U * VEC <
 #pragma unroll
         for (int e = 0; e < VEC; ++e) acc[u][e] = 0.0f;
 
-    const int beg = __ldg(p.item_ptr + item), end = __ldg(p.item_ptr + item + 1);
+    const int beg = __ldg(p.item_ptr + item);
+    const int end = p.item_end ? __ldg(p.item_end + item) : __ldg(p.item_ptr + item + 1);
     const T* __restrict__ xb = p.x + fbase;
     for (int base = beg; base < end; base += 32) {
         const int n = min(32, end - base);
@@ -222,8 +224,9 @@ __global__ void __launch_bounds__(256, (NB * U * VEC <= 8) ? 8 : (NB * U * VEC <
             c = __ldg(p.col + base + lane);
             if (HAS_VAL) v = __ldg(p.val + base + lane);
         }
-        if (p.x_mask) {                                          // warp-uniform
-            unsigned live = __ballot_sync(0xffffffffu, lane < n && __ldg(p.x_mask + c) != 0);
+        if (p.x_index) {                                         // warp-uniform
+            if (lane < n) c = __ldg(p.x_index + c);
+            unsigned live = __ballot_sync(0xffffffffu, lane < n && c >= 0);
 #pragma unroll 1
             while (live) gather_block_masked<T, VEC, U, NB, HAS_VAL>(xb, p.ldx, c, v, live, act, acc);
         } else if (n == 32) {
@@ -321,7 +324,7 @@ static int dispatch_u(const SpmmParamsT<T>& p, cudaStream_t st) {
 }  // namespace plnlp
 
 extern "C" int plnlp_spmm_csr_f32(const int32_t* item_ptr, const int32_t* item_row, const int32_t* item_slot,
-                                  int64_t n_items, const uint8_t* x_mask, const int32_t* col, const float* val,
+                                  int64_t n_items, const int32_t* item_end, const int32_t* x_index, const int32_t* col, const float* val,
                                   const float* row_div, const float* bias, int relu, float drop_p,
                                   uint64_t seed, const float* x, int64_t ldx, float* out, int64_t ldo,
                                   int64_t F, float* partial, const int32_t* fix_ptr, const int32_t* fix_row,
@@ -333,7 +336,7 @@ extern "C" int plnlp_spmm_csr_f32(const int32_t* item_ptr, const int32_t* item_r
     PLNLP_REQUIRE(ldx >= F && ldo >= F, PLNLP_E_SIZE);
     PLNLP_REQUIRE(drop_p >= 0.0f && drop_p < 1.0f, PLNLP_E_SIZE);
     if (n_fix > 0) PLNLP_REQUIRE(partial && fix_ptr && fix_row, PLNLP_E_NULL);
-    SpmmParams p{item_ptr, item_row, item_slot, n_items, x_mask, col, val, row_div, bias, relu, drop_p, seed,
+    SpmmParams p{item_ptr, item_row, item_slot, n_items, item_end, x_index, col, val, row_div, bias, relu, drop_p, seed,
                  x, ldx, out, ldo, static_cast<int>(F), partial, fix_ptr, fix_row, n_fix};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool v4 = (F % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned(x, 16) && aligned(out, 16) &&
@@ -348,7 +351,7 @@ extern "C" int plnlp_spmm_csr_f32(const int32_t* item_ptr, const int32_t* item_r
 // bf16 feature storage (x and out are bf16 bit patterns), fp32 accumulation in CSR order, one RN rounding at
 // the store.  Same plan, epilogue and Philox indexing as the fp32 entry point; `partial` stays fp32.
 extern "C" int plnlp_spmm_csr_bf16(const int32_t* item_ptr, const int32_t* item_row, const int32_t* item_slot,
-                                   int64_t n_items, const uint8_t* x_mask, const int32_t* col, const float* val,
+                                   int64_t n_items, const int32_t* item_end, const int32_t* x_index, const int32_t* col, const float* val,
                                    const float* row_div, const float* bias, int relu, float drop_p,
                                    uint64_t seed, const uint16_t* x, int64_t ldx, uint16_t* out, int64_t ldo,
                                    int64_t F, float* partial, const int32_t* fix_ptr, const int32_t* fix_row,
@@ -360,7 +363,7 @@ extern "C" int plnlp_spmm_csr_bf16(const int32_t* item_ptr, const int32_t* item_
     PLNLP_REQUIRE(ldx >= F && ldo >= F, PLNLP_E_SIZE);
     PLNLP_REQUIRE(drop_p >= 0.0f && drop_p < 1.0f, PLNLP_E_SIZE);
     if (n_fix > 0) PLNLP_REQUIRE(partial && fix_ptr && fix_row, PLNLP_E_NULL);
-    SpmmParamsT<__nv_bfloat16> p{item_ptr, item_row, item_slot, n_items, x_mask, col, val, row_div, bias, relu, drop_p, seed,
+    SpmmParamsT<__nv_bfloat16> p{item_ptr, item_row, item_slot, n_items, item_end, x_index, col, val, row_div, bias, relu, drop_p, seed,
                                  reinterpret_cast<const __nv_bfloat16*>(x), ldx,
                                  reinterpret_cast<__nv_bfloat16*>(out), ldo, static_cast<int>(F), partial, fix_ptr,
                                  fix_row, n_fix};

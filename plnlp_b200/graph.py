@@ -171,7 +171,7 @@ class SpmmPlan:
     """Device arrays consumed by ``plnlp_spmm_csr_f32`` for one CSR matrix."""
 
     __slots__ = ("n_rows", "n_cols", "nnz", "chunk", "col", "val", "item_ptr", "item_row", "item_slot",
-                 "n_items", "fix_ptr", "fix_row", "n_fix", "n_partial", "row_cnt")
+                 "n_items", "item_end", "subset", "fix_ptr", "fix_row", "n_fix", "n_partial", "row_cnt")
 
     def alg_bytes(self, F, elem=4):
         """ALGORITHMIC bytes of one launch: gathered rows + indices +
@@ -221,11 +221,56 @@ def build_plan(rowptr, col, val, n_rows, n_cols, chunk=None):
     p.item_row = item_row.to(torch.int32).contiguous()
     p.item_slot = item_slot.to(torch.int32).contiguous()
     p.n_items = n_items
+    p.item_end, p.subset = None, False
     p.fix_ptr = fix_ptr.to(torch.int32).contiguous()
     p.fix_row = fix_row.to(torch.int32).contiguous()
     p.n_fix = int(fix_row.numel())
     p.n_partial = int(fix_ptr[-1]) if fix_row.numel() else 0
     p.row_cnt = torch.clamp(deg, min=1).to(torch.float32).contiguous()  # mean divisor, max(row_nnz, 1)
+    return p
+
+
+def build_subset_plan(parent, rowptr, rows):
+    """Plan for the rows ``rows`` (int64 device vector of distinct row ids) of the matrix behind ``parent``:
+    output row t of the SpMM is matrix row rows[t].  Same chunking as ``build_plan`` (hub rows are cut into
+    several items whose partial sums a fixed-order pass combines); items carry explicit ends because the
+    selected rows are not contiguous.  Index arrays (col / val) are shared with the parent.  One host read
+    (the item count)."""
+    dev = rows.device
+    T = rows.numel()
+    chunk = parent.chunk
+    start = rowptr[rows]
+    length = rowptr[rows + 1] - start
+    n_it = torch.clamp((length + chunk - 1) // chunk, min=1)
+    n_items = int(n_it.sum())
+    t_ids = torch.arange(T, device=dev)
+    item_row = torch.repeat_interleave(t_ids, n_it, output_size=n_items)
+    first = torch.cumsum(n_it, 0) - n_it
+    k = torch.arange(n_items, device=dev) - first[item_row]
+    item_beg = start[item_row] + k * chunk
+    item_end = torch.minimum(item_beg + chunk, (start + length)[item_row])
+    multi_row = n_it > 1
+    multi_item = multi_row[item_row]
+    slot = torch.cumsum(multi_item.to(torch.int64), 0) - 1
+    item_slot = torch.where(multi_item, slot, torch.full_like(slot, -1))
+    fix_row = torch.nonzero(multi_row).reshape(-1)
+    fix_ptr = torch.zeros(fix_row.numel() + 1, dtype=torch.int64, device=dev)
+    if fix_row.numel():
+        fix_ptr[1:] = torch.cumsum(n_it[fix_row], 0)
+    p = SpmmPlan()
+    p.n_rows, p.n_cols, p.chunk = int(T), parent.n_cols, chunk
+    p.col, p.val = parent.col, parent.val
+    p.item_ptr = item_beg.to(torch.int32).contiguous()
+    p.item_end = item_end.to(torch.int32).contiguous()
+    p.item_row = item_row.to(torch.int32).contiguous()
+    p.item_slot = item_slot.to(torch.int32).contiguous()
+    p.n_items, p.subset = n_items, True
+    p.fix_ptr = fix_ptr.to(torch.int32).contiguous()
+    p.fix_row = fix_row.to(torch.int32).contiguous()
+    p.n_fix = int(fix_row.numel())
+    p.n_partial = int(multi_item.sum()) if p.n_fix else 0
+    p.nnz = int(length.sum())
+    p.row_cnt = torch.clamp(length, min=1).to(torch.float32).contiguous()
     return p
 
 
@@ -242,6 +287,7 @@ class Structure:
         self.has_value = val is not None
         # forward plans: valued (GCN, 'sum') and value-less (SAGE drops values, 'mean')
         self.fwd = build_plan(rowptr, col, val, M, N, chunk)
+        self.rowptr = rowptr                      # int64, for per-step row-subset plans (build_subset_plan)
         self.fwd_noval = self.fwd if val is None else _share_plan(self.fwd, None)
         # transposed structure (backward): sort entries by (col, row)
         deg = rowptr[1:] - rowptr[:-1]

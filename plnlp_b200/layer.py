@@ -191,10 +191,25 @@ class GCNConv(torch.nn.Module):
         torch.nn.init.uniform_(self.lin.weight, -a, a)
         torch.nn.init.zeros_(self.bias)
 
-    def forward(self, x, adj_t, act=_ops.ACT_NONE, drop_p=0.0):
+    def can_restrict(self, x, adj_t):
+        """whether ``forward(..., out_rows=)`` can compute just those output rows: the linear-first order on a
+        single-device sparse adjacency (the usual last layer, hidden -> hidden)"""
+        from . import parallel
+        if isinstance(adj_t, parallel.ShardedAdj) or _ops.structure_of(adj_t).dense_ok:
+            return False
+        live = sum(p.size(1) for p in _as_parts(x) if not _is_const(p))
+        return not (REASSOCIATE and live < self.out_channels)
+
+    def forward(self, x, adj_t, act=_ops.ACT_NONE, drop_p=0.0, out_rows=None):
         parts = _as_parts(x)
         ws = _split_cols(self.lin.weight, parts)
         seed = _ops.new_seed() if drop_p > 0 else 0
+        if out_rows is not None:           # only these rows of the layer output, as a compact matrix
+            if not self.can_restrict(x, adj_t):
+                raise RuntimeError("out_rows: this layer / adjacency cannot restrict its output rows")
+            z = _ops.fused_linear(parts, ws)
+            return _ops.spmm_rows(adj_t, z, out_rows, reduce="sum", bias=self.bias, relu=(act == _ops.ACT_RELU),
+                                  drop_p=drop_p, seed=seed)
         live = sum(p.size(1) for p in parts if not _is_const(p))
         if REASSOCIATE and live < self.out_channels:
             # A_hat (x W^T) = (A_hat x) W^T.  The aggregation is the HBM-bound half of the layer, so run it on
@@ -227,13 +242,20 @@ class BaseGNN(torch.nn.Module):
         for conv in self.convs:
             conv.reset_parameters()
 
-    def forward(self, x, adj_t):
+    def forward(self, x, adj_t, out_rows=None):
+        """``out_rows`` (extension; sorted distinct node ids): the caller only reads these rows of the output.
+        Returns ``(h, restricted)``: when the last conv can restrict itself, h is the compact [len(out_rows), H]
+        matrix of just those rows (restricted = True), otherwise the full output (restricted = False)."""
         p = self.dropout if self.training else 0.0
         last = len(self.convs) - 1
+        restricted = False
         for i, conv in enumerate(self.convs):
             fused = i < last or self.num_layers == 1
-            x = conv(x, adj_t, act=_ops.ACT_RELU if fused else _ops.ACT_NONE, drop_p=p if fused else 0.0)
-        return x
+            kw = {}
+            if i == last and out_rows is not None and getattr(conv, "can_restrict", None) and conv.can_restrict(x, adj_t):
+                kw["out_rows"], restricted = out_rows, True
+            x = conv(x, adj_t, act=_ops.ACT_RELU if fused else _ops.ACT_NONE, drop_p=p if fused else 0.0, **kw)
+        return x if out_rows is None else (x, restricted)
 
 
 def _stack(conv_cls, in_channels, hidden_channels, out_channels, num_layers):

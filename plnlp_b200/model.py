@@ -131,12 +131,23 @@ class BaseModel(object):
         """one optimisation step (model.py:148-167).  pos_edge [B,2], neg_edge [B*num_neg,2].
         Returns the batch loss as a 0-d device tensor (no host sync)."""
         self.optimizer.zero_grad(set_to_none=True)
-        h = self.encoder(self.input_parts(data), data.adj_t)
-        # d loss / d h is non-zero only at the endpoint rows of the batch(es): when those are a small part of the
-        # node set (citation2-shape: ~10 %), tell the last conv so its A^T g product skips the zero rows
+        # Scoring reads h only at the endpoint rows of the batch, and d loss / d h is non-zero only there.  When
+        # those are a small part of the node set (citation2-shape: ~10 %) the last conv computes just those
+        # rows (compact h, edges renumbered) and its backward gathers just their gradient rows; where the
+        # layer cannot restrict itself (row-partitioned run) only the backward skips the all-zero rows.
         touched = 2 * (pos_edge.size(0) + neg_edge.size(0)) * max(self.world_size if self.partitioned else 1, 1)
-        if ROW_SPARSE_GRAD and touched < 0.5 * self.num_nodes:
-            h = _ops.row_sparse_grad(h)
+        sparse_rows = ROW_SPARSE_GRAD and touched < 0.5 * self.num_nodes
+        if sparse_rows and not self.partitioned:
+            ids, inv = torch.unique(torch.cat([pos_edge, neg_edge], 0), return_inverse=True)
+            h, restricted = self.encoder(self.input_parts(data), data.adj_t, out_rows=ids)
+            if restricted:
+                pos_edge, neg_edge = inv[:pos_edge.size(0)], inv[pos_edge.size(0):]
+            else:
+                h = _ops.row_sparse_grad(h)
+        else:
+            h = self.encoder(self.input_parts(data), data.adj_t)
+            if sparse_rows:
+                h = _ops.row_sparse_grad(h)
         if self.partitioned:
             # row-partitioned encoder (SURVEY 8e): h is this rank's row block and scoring needs arbitrary
             # endpoints.  Fetch just the distinct endpoint rows of this rank's batch from their owners

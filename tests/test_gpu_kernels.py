@@ -78,7 +78,7 @@ def test_spmm_split_rows(ops, chunk):
 
 @pytest.mark.parametrize("F", [3, 50, 200, 512])
 def test_spmm_row_sparse_operand_mask(ops, F, monkeypatch):
-    """x_mask skips the gathers of all-zero rows of x: identical bits to the dense kernel (the skipped terms are
+    """x_index < 0 skips the gathers of all-zero rows of x: identical bits to the dense kernel (the skipped terms are
     exact zeros, the surviving ones keep their CSR order), valued and value-less, hub rows included; and the
     autograd hint path (row_sparse_grad -> SpMM.backward) gives the same gradient as the plain path"""
     from plnlp_b200 import graph
@@ -95,14 +95,14 @@ def test_spmm_row_sparse_operand_mask(ops, F, monkeypatch):
     keep[2] = True                                     # the hub column stays live
     x[~keep] = 0
     xg = x.cuda()
-    mask = ops.row_nonzero_mask_raw(xg)
-    assert torch.equal(mask.cpu().bool(), keep)
+    mask = ops.row_nonzero_index_raw(xg)
+    assert torch.equal(mask.cpu() >= 0, keep) and torch.equal(mask.cpu()[keep], torch.nonzero(keep).reshape(-1).int())
     for use_val, div in ((True, False), (False, True)):
         plan = st.fwd if use_val else st.fwd_noval
         dense = ops.spmm_raw(plan, xg, use_val=use_val, div_rows=div)
-        sparse_ = ops.spmm_raw(plan, xg, use_val=use_val, div_rows=div, x_mask=mask)
+        sparse_ = ops.spmm_raw(plan, xg, use_val=use_val, div_rows=div, x_index=mask)
         assert torch.equal(dense, sparse_)
-    none = ops.spmm_raw(st.fwd, xg, use_val=True, div_rows=False, x_mask=torch.zeros_like(mask))
+    none = ops.spmm_raw(st.fwd, xg, use_val=True, div_rows=False, x_index=torch.full_like(mask, -1))
     assert torch.all(none == 0)
     # autograd: gradient that is non-zero only at a few rows
     idx = torch.nonzero(keep).reshape(-1).cuda()
@@ -117,6 +117,37 @@ def test_spmm_row_sparse_operand_mask(ops, F, monkeypatch):
         grads.append(z.grad.clone())
     assert torch.equal(grads[0], grads[1])
     assert not ops._ROW_HINTS                          # the hint was consumed
+
+
+@pytest.mark.parametrize("F", [3, 50, 200])
+@pytest.mark.parametrize("reduce", ["sum", "mean"])
+def test_spmm_row_subset_matches_full_product(ops, F, reduce, monkeypatch):
+    """spmm_rows: the selected output rows carry the bits of the full product (hub rows cut into items, empty
+    rows, epilogue), and its backward equals the backward of 'full product, then pick the rows'"""
+    from plnlp_b200 import graph
+    monkeypatch.setattr(graph, "DENSE_SPMM", False)
+    N = 260
+    ei, w = rand_graph(N, 4000, seed=F + 1, weighted=(reduce == "sum"), hub=True)
+    g = _to_gpu_graph(sparse.to_sparse_tensor(ei, w, N))
+    graph._CACHE[id(g)] = (g, graph.Structure(g, chunk=64))          # hub rows split into several items
+    gen = torch.Generator().manual_seed(F)
+    rows = torch.unique(torch.cat([torch.randint(0, N, (40,), generator=gen), torch.tensor([2, N - 1])])).cuda()
+    b = torch.randn(F, generator=gen).cuda()
+    wgt = torch.randn(rows.numel(), F, generator=gen).cuda()
+    outs, grads = [], []
+    for restricted in (False, True):
+        x = torch.randn(N, F, generator=torch.Generator().manual_seed(3)).cuda().requires_grad_(True)
+        bb = b.clone().requires_grad_(True)
+        if restricted:
+            y = ops.spmm_rows(g, x, rows, reduce, bias=bb, relu=True)
+        else:
+            y = ops.spmm(g, x, reduce, bias=bb, relu=True)[rows]
+        (y * wgt).sum().backward()
+        outs.append(y.detach().clone())
+        grads.append((x.grad.clone(), bb.grad.clone()))
+    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(grads[0][0], grads[1][0])
+    assert rel_err(grads[1][1], grads[0][1]) < TOL            # bias gradient: column sums over different row sets
 
 
 def test_spmm_all_rows_empty(ops):

@@ -90,6 +90,34 @@ def test_spmm_plan_covers_every_row_once(chunk):
         assert rel_err(got, sparse.matmul(adj, x, reduce)) < 1e-5
 
 
+def test_subset_plan_covers_exactly_the_selected_rows():
+    """build_subset_plan: items tile the stored entries of the selected rows (in order, chunked like the parent
+    plan), empty rows get one empty item, split rows get consecutive partial slots"""
+    from plnlp_b200.graph import build_subset_plan
+    N = 120
+    ei, _ = rand_graph(N, 900, seed=12, hub=True)
+    o = sparse.to_sparse_tensor(ei, None, N)
+    rowptr, col, _ = o.csr()
+    parent = build_plan(rowptr, col, None, N, N, chunk=32)
+    rows = torch.tensor([0, 2, 5, 17, 60, N - 2, N - 1])           # row 2 is the hub, the last rows are empty
+    p = build_subset_plan(parent, rowptr, rows)
+    assert p.subset and p.n_rows == rows.numel() and p.n_cols == N and p.col is parent.col
+    beg, end, irow, slot = (t.long() for t in (p.item_ptr, p.item_end, p.item_row, p.item_slot))
+    assert p.n_items == beg.numel() == end.numel()
+    for t, r in enumerate(rows.tolist()):
+        sel = irow == t
+        assert sel.any()
+        b, e = beg[sel], end[sel]
+        assert int(b[0]) == int(rowptr[r]) and int(e[-1]) == int(rowptr[r + 1])
+        assert torch.equal(b[1:], e[:-1]) and bool(((e - b) <= 32).all())
+        if sel.sum() > 1:
+            assert bool((slot[sel] >= 0).all()) and torch.equal(slot[sel], slot[sel][0] + torch.arange(int(sel.sum())))
+        else:
+            assert int(slot[sel][0]) == -1
+    assert p.nnz == int((rowptr[rows + 1] - rowptr[rows]).sum())
+    assert p.n_fix == int(((rowptr[rows + 1] - rowptr[rows]) > 32).sum()) and p.n_partial == int((slot >= 0).sum())
+
+
 def test_adjust_lr_and_loss_dispatch():
     from plnlp_b200.model import BaseModel, adjust_lr
     opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0)
