@@ -192,24 +192,22 @@ class GCNConv(torch.nn.Module):
         torch.nn.init.zeros_(self.bias)
 
     def can_restrict(self, x, adj_t):
-        """whether ``forward(..., out_rows=)`` can compute just those output rows: the linear-first order on a
-        single-device sparse adjacency (the usual last layer, hidden -> hidden)"""
+        """whether ``forward(..., out_rows=)`` can compute just those output rows: a single-device sparse
+        adjacency (the row-partitioned run and the dense tensor-core path compute every row)"""
         from . import parallel
-        if isinstance(adj_t, parallel.ShardedAdj) or _ops.structure_of(adj_t).dense_ok:
-            return False
-        live = sum(p.size(1) for p in _as_parts(x) if not _is_const(p))
-        return not (REASSOCIATE and live < self.out_channels)
+        return not (isinstance(adj_t, parallel.ShardedAdj) or _ops.structure_of(adj_t).dense_ok)
 
     def forward(self, x, adj_t, act=_ops.ACT_NONE, drop_p=0.0, out_rows=None):
         parts = _as_parts(x)
         ws = _split_cols(self.lin.weight, parts)
         seed = _ops.new_seed() if drop_p > 0 else 0
-        if out_rows is not None:           # only these rows of the layer output, as a compact matrix
+        if out_rows is not None:
+            # only these rows of the layer output, as a compact [T, out] matrix: (A_hat[rows, :] x) W^T + b.
+            # Aggregating first keeps the linear map and both of its backward GEMMs at T rows instead of N.
             if not self.can_restrict(x, adj_t):
                 raise RuntimeError("out_rows: this layer / adjacency cannot restrict its output rows")
-            z = _ops.fused_linear(parts, ws)
-            return _ops.spmm_rows(adj_t, z, out_rows, reduce="sum", bias=self.bias, relu=(act == _ops.ACT_RELU),
-                                  drop_p=drop_p, seed=seed)
+            aggs = [_ops.spmm_rows(adj_t, p, out_rows, reduce="sum") for p in parts]
+            return _ops.fused_linear(aggs, ws, self.bias, act, drop_p, seed)
         live = sum(p.size(1) for p in parts if not _is_const(p))
         if REASSOCIATE and live < self.out_channels:
             # A_hat (x W^T) = (A_hat x) W^T.  The aggregation is the HBM-bound half of the layer, so run it on
