@@ -385,7 +385,7 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(cfg, steps=args.cpu_steps)
+        cpu = cpu_baseline_guarded(args.workload, args.cpu_steps)
 
     if rank == 0:
         line = {"metric": "pos+neg pairs/s (train step)", "value": value, "unit": "pairs/s", "n_gpus": world,
@@ -408,11 +408,34 @@ def run_ours(args):
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_baseline(cfg, steps=2):
+def cpu_baseline_guarded(workload, steps, timeout_s=420):
+    """``cpu_baseline`` in a CHILD interpreter with a time limit.  A fresh process keeps the host-thread pool of
+    the CPU arm apart from the CUDA process (one such run stalled indefinitely inside the bench process on a
+    GPU box), and a stall can then cost at most ``timeout_s``: the run is retried once with 8 threads and
+    otherwise reported as unavailable instead of taking the whole bench line with it."""
+    import subprocess
+    code = ("import json, sys, bench; "
+            "print('CPU_BASELINE ' + json.dumps(bench.cpu_baseline(dict(bench.WORKLOADS[sys.argv[1]]), "
+            "steps=int(sys.argv[2]), threads=int(sys.argv[3]) or None)))")
+    last = "no attempt"
+    for threads in (0, 8):
+        try:
+            r = subprocess.run([sys.executable, "-c", code, workload, str(steps), str(threads)], cwd=ROOT,
+                               capture_output=True, text=True, timeout=timeout_s)
+            for ln in r.stdout.splitlines():
+                if ln.startswith("CPU_BASELINE "):
+                    return json.loads(ln[len("CPU_BASELINE "):])
+            last = f"child exited {r.returncode}: {r.stderr.strip()[-300:]}"
+        except subprocess.TimeoutExpired:
+            last = f"timed out after {timeout_s} s with {'all' if not threads else threads} threads"
+    return {"unavailable": last, "kind": "port"}
+
+
+def cpu_baseline(cfg, steps=2, threads=None):
     """the oracle restatement of the reference's train step (torch CPU, all host threads) on a bounded
     sample: `steps` optimisation steps of the same workload (full-graph encode each)."""
     from oracle import plnlp_ref, sparse
-    threads = os.cpu_count() or 1
+    threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     cpu = torch.device("cpu")
     data, split = build_workload(cfg, cpu, _OracleGraph, sparse.gcn_normalization)
@@ -459,7 +482,10 @@ def run_reference(args):
     cfg = dict(WORKLOADS[args.workload])
     K, W = args.steps, args.warmup
     steps = max(1, min(K, args.cpu_steps))
-    cpu = cpu_baseline(cfg, steps=steps)
+    cpu = cpu_baseline_guarded(args.workload, steps)
+    if "unavailable" in cpu:
+        emit({"impl": "reference", "unavailable": cpu["unavailable"]})
+        return
     B, k = cfg["batch"], cfg["num_neg"]
     line = {"impl": "reference", "metric": "pos+neg pairs/s (train step)", "value": cpu["value"], "unit": "pairs/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": 1,

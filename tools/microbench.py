@@ -20,7 +20,7 @@ except Exception:
 HBM = PEAKS.get("hbm_gbs", 6650.0)
 
 
-def timeit(fn, warm=3, iters=10, flush=None):
+def timeit(fn, warm=2, iters=10, flush=None):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -172,15 +172,47 @@ def collab_dot():
 
 
 def sweep():
-    """BASELINE config 5 (subset): power-law graphs, source matrix >= 4x L2, fp32 SpMM forward"""
-    for E, N in ((10_000_000, 2_000_000), (50_000_000, 4_000_000)):
+    """BASELINE config 5: directed power-law graphs 10 M - 200 M edges, source matrix >= 4x L2, hidden 64-512,
+    fp32 and bf16 storage: SpMM forward and backward (the transposed plan), edge-score DOT forward + backward,
+    edge-score MLP forward (fused tcgen05 kernel), each against the HBM roofline of SURVEY 8d's byte model."""
+    P = 1 << 20
+    for E, N in ((10_000_000, 2_000_000), (50_000_000, 4_000_000), (100_000_000, 4_000_000), (200_000_000, 4_000_000)):
         ei = powerlaw_graph(N, E, 5)
         adj = CSRGraph.from_edge_index(ei, None, N)
+        del ei
+        st = structure_of(adj)
+        torch.cuda.synchronize()
+        tag = f"powerlaw E={E // 1_000_000}M N={N // 1_000_000}M"
         for F in (64, 128, 256, 512):
-            if N * F * 4 > 12e9:
-                continue
-            bench_spmm(f"powerlaw E={E//1_000_000}M N={N//1_000_000}M", adj, F, "sum", None)
-        del adj
+            x32 = torch.randn(N, F, device=DEV)
+            for dt in (torch.float32, torch.bfloat16):
+                x = x32.to(dt)
+                es = x.element_size()
+                for name, plan in (("fwd", st.fwd), ("bwd", st.bwd)):
+                    ms = timeit(lambda: _ops.spmm_raw(plan, x, use_val=False, div_rows=False), iters=5)
+                    by = plan.alg_bytes(F, es)
+                    print(f"[spmm {name}] {tag} F={F} {str(dt)[6:]}: {ms:.3f} ms  {by / ms / 1e6:.0f} GB/s "
+                          f"({by / ms / 1e6 / HBM * 100:.0f}% of HBM)", flush=True)
+                del x
+            if E == 50_000_000:         # edge scoring does not depend on the graph: once per width
+                edges = torch.randint(0, N, (P, 2), device=DEV)
+                ds = torch.randn(P, device=DEV)
+                ms = timeit(lambda: _ops.edge_dot_raw(x32, edges), iters=5)
+                by = P * (2 * F * 4 + 12)
+                print(f"[edge_dot fwd] N={N // 1_000_000}M P={P} H={F}: {ms:.4f} ms  {by / ms / 1e6:.0f} GB/s "
+                      f"({by / ms / 1e6 / HBM * 100:.0f}% of HBM)", flush=True)
+                ms = timeit(lambda: _ops.edge_scatter_raw(x32, edges, dscore=ds, mode="atomic"), iters=5)
+                by = P * (4 * F * 4 + 20) + N * F * 4
+                print(f"[edge_dot bwd atomic] H={F}: {ms:.4f} ms  {by / ms / 1e6:.0f} GB/s "
+                      f"({by / ms / 1e6 / HBM * 100:.0f}% of HBM, incl. the dense grad_h zero-fill + write)", flush=True)
+                W1, b1 = torch.randn(F, F, device=DEV) / F ** 0.5, torch.randn(F, device=DEV)
+                w2, b2 = torch.randn(F, device=DEV), torch.randn(1, device=DEV)
+                ms = timeit(lambda: _ops.edge_mlp_fwd_raw(x32, edges, W1, b1, w2, b2, need_a1=False), iters=5)
+                by, fl = P * (2 * F * 4 + 12), 2.0 * P * F * F + 2.0 * P * F
+                print(f"[edge_mlp fwd fused] H={F}: {ms:.4f} ms  gather {by / ms / 1e6:.0f} GB/s "
+                      f"({by / ms / 1e6 / HBM * 100:.0f}% of HBM)  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+            del x32
+        del adj, st
         torch.cuda.empty_cache()
 
 
