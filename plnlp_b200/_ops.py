@@ -98,15 +98,16 @@ def spmm_raw(plan, x, use_val, div_rows, bias=None, relu=False, drop_p=0.0, seed
     if x_index is not None:
         if x_index.dtype != torch.int32 or x_index.numel() != plan.n_cols or not x_index.is_cuda:
             raise RuntimeError("x_index must be a CUDA int32 vector with one entry per column of the adjacency")
-        name += " (row-sparse operand)"     # algorithmic bytes stay those of the dense gather model
+        name += " (row-sparse operand)"
+        alg = 0        # the live share of the entries is data dependent and not known on the host: no GB/s claim
     if getattr(plan, "subset", False):
         name += " (row subset)"
-    with profiling.span(name, alg, 0):
+    with profiling.span(f"{name} F={F}", alg, 0):
         check(fn(ptr(plan.item_ptr), ptr(plan.item_row), ptr(plan.item_slot), plan.n_items,
                  ptr(plan.item_end), ptr(x_index), ptr(plan.col), ptr(val), ptr(plan.row_cnt if div_rows else None), ptr(bias),
                  int(relu), float(drop_p), int(seed), ptr(x), _ld(x), ptr(out), _ld(out), F,
                  ptr(partial), ptr(plan.fix_ptr), ptr(plan.fix_row), plan.n_fix, stream()),
-              "plnlp_" + name)
+              "plnlp_" + name.split(" ")[0])
     return out
 
 

@@ -176,7 +176,10 @@ def sweep():
     fp32 and bf16 storage: SpMM forward and backward (the transposed plan), edge-score DOT forward + backward,
     edge-score MLP forward (fused tcgen05 kernel), each against the HBM roofline of SURVEY 8d's byte model."""
     P = 1 << 20
+    emax = max([int(a[5:]) for a in sys.argv if a.startswith("emax=")] or [200]) * 1_000_000
     for E, N in ((10_000_000, 2_000_000), (50_000_000, 4_000_000), (100_000_000, 4_000_000), (200_000_000, 4_000_000)):
+        if E > emax:
+            continue
         ei = powerlaw_graph(N, E, 5)
         adj = CSRGraph.from_edge_index(ei, None, N)
         del ei
@@ -189,7 +192,7 @@ def sweep():
                 x = x32.to(dt)
                 es = x.element_size()
                 for name, plan in (("fwd", st.fwd), ("bwd", st.bwd)):
-                    ms = timeit(lambda: _ops.spmm_raw(plan, x, use_val=False, div_rows=False), iters=5)
+                    ms = timeit(lambda: _ops.spmm_raw(plan, x, use_val=False, div_rows=False), iters=3)
                     by = plan.alg_bytes(F, es)
                     print(f"[spmm {name}] {tag} F={F} {str(dt)[6:]}: {ms:.3f} ms  {by / ms / 1e6:.0f} GB/s "
                           f"({by / ms / 1e6 / HBM * 100:.0f}% of HBM)", flush=True)
