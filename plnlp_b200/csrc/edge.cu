@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) mlp_out_fwd_kernel(const float* __restric
 }
 
 // dz = dscore * w * mask(a);  per-block partial dw over MLP_RB consecutive rows (fixed order)
-constexpr int MLP_RB = 256;
+constexpr int MLP_RB = 128;
 
 template <int VEC>
 __global__ void __launch_bounds__(128) mlp_out_bwd_kernel(const float* __restrict__ a, int64_t lda,
@@ -96,7 +96,28 @@ __global__ void __launch_bounds__(128) mlp_out_bwd_kernel(const float* __restric
         load_vec<VEC>(wv, w + f);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) acc[e] = 0.0f;
-        for (int64_t r = r0; r < r1; ++r) {
+        // rows are fetched RU at a time (independent loads in flight) and consumed in row order, so the
+        // per-column sums keep their order
+        constexpr int RU = 4;
+        int64_t r = r0;
+        for (; r + RU - 1 < r1; r += RU) {
+            float av[RU][VEC];
+#pragma unroll
+            for (int i = 0; i < RU; ++i) load_vec<VEC>(av[i], a + (r + i) * lda + f);
+#pragma unroll
+            for (int i = 0; i < RU; ++i) {
+                float g[VEC];
+                const float d = ds[r + i - r0];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    acc[e] = fmaf(d, av[i][e], acc[e]);
+                    g[e] = d * wv[e];
+                    if (mask_a) g[e] = av[i][e] > 0.0f ? g[e] * drop_scale : 0.0f;
+                }
+                store_vec<VEC>(dz + (r + i) * lddz + f, g);
+            }
+        }
+        for (; r < r1; ++r) {
             float av[VEC], g[VEC];
             load_vec<VEC>(av, a + r * lda + f);
             const float d = ds[r - r0];
