@@ -408,12 +408,14 @@ def run_ours(args):
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_baseline_guarded(workload, steps, timeout_s=420):
+def cpu_baseline_guarded(workload, steps, timeout_s=None):
     """``cpu_baseline`` in a CHILD interpreter with a time limit.  A fresh process keeps the host-thread pool of
     the CPU arm apart from the CUDA process (one such run stalled indefinitely inside the bench process on a
     GPU box), and a stall can then cost at most ``timeout_s``: the run is retried once with 8 threads and
     otherwise reported as unavailable instead of taking the whole bench line with it."""
     import subprocess
+    if timeout_s is None:       # normal duration: ~15 s (ddi / collab shape), ~90 s (citation2 shape: graph build + steps)
+        timeout_s = 420 if workload == "citation2" else 150
     code = ("import json, sys, bench; "
             "print('CPU_BASELINE ' + json.dumps(bench.cpu_baseline(dict(bench.WORKLOADS[sys.argv[1]]), "
             "steps=int(sys.argv[2]), threads=int(sys.argv[3]) or None)))")
