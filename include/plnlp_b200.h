@@ -165,6 +165,17 @@ int plnlp_edge_mlp_fwd_tf32(int passes, const float* h, int64_t ldh, int64_t n_r
 /* out[p, :] = h[src_p, :] * h[dst_p, :] */
 int plnlp_gather_hadamard_f32(const float* h, int64_t ldh, int64_t n_rows, const int64_t* edges, int64_t P, int64_t H,
                               float* out, int64_t ldo, void* stream);
+/* Per-destination softmax over the stored entries of each CSR row and its backward: the attention weights of
+ * torch_geometric.nn.TransformerConv under the reference's Transformer encoder (layer.py:57-63).
+ *   alpha[e] = softmax over e in [rowptr[r], rowptr[r+1]) of scale * s[e]
+ *   ds[e]    = scale * alpha[e] * (dalpha[e] - sum_{e' in row} alpha[e'] * dalpha[e'])
+ * The per-entry scores s are <query_i, key_j> from plnlp_edge_dot_fwd_f32 over the entry list; the weighted
+ * aggregation of the values is plnlp_spmm_csr_f32 with val = alpha. */
+int plnlp_segment_softmax_fwd_f32(const int64_t* rowptr, int64_t n_rows, const float* s, float scale, float* alpha,
+                                  void* stream);
+int plnlp_segment_softmax_bwd_f32(const int64_t* rowptr, int64_t n_rows, const float* alpha, const float* dalpha,
+                                  float scale, float* ds, void* stream);
+
 /* Plain endpoint gather out[p, :] = h[idx[p * idx_stride], :] (negative indices wrap) and its backward
  * grad_h[n, :] = sum_{t in segment n} g[entry[t], :] over a node-sorted entry list (seg_ptr has n_seg + 1
  * offsets, one segment per node, empty segments write zero rows; fixed summation order -> deterministic).

@@ -96,7 +96,36 @@ class GraphConv(torch.nn.Module):
         return self.lin_rel(matmul(adj_t, x, reduce="sum")) + self.lin_root(x)
 
 
-TransformerConv = _Unavailable
+class TransformerConv(torch.nn.Module):
+    """torch_geometric 2.0.1 nn.TransformerConv(in, out) with its defaults (heads=1, concat=True, beta=False,
+    dropout=0, edge_dim=None, bias=True, root_weight=True) restated [from memory -- parity unpinned]:
+    alpha_ij = softmax_j(<lin_query(x_i), lin_key(x_j)> / sqrt(out)) over the stored entries of row i of adj_t
+    (row = target), out_i = sum_j alpha_ij lin_value(x_j) + lin_skip(x_i); all four linears carry a bias.
+    Used by the reference's Transformer encoder (plnlp/layer.py:57-63) on a value-less adjacency."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin_key = torch.nn.Linear(in_channels, out_channels)
+        self.lin_query = torch.nn.Linear(in_channels, out_channels)
+        self.lin_value = torch.nn.Linear(in_channels, out_channels)
+        self.lin_skip = torch.nn.Linear(in_channels, out_channels)
+
+    def reset_parameters(self):
+        for lin in (self.lin_key, self.lin_query, self.lin_value, self.lin_skip):
+            lin.reset_parameters()
+
+    def forward(self, x, adj_t):
+        row, col, _ = adj_t.coo()
+        q, k, v = self.lin_query(x), self.lin_key(x), self.lin_value(x)
+        score = (q[row] * k[col]).sum(-1) / (self.out_channels ** 0.5)
+        N = x.size(0)
+        mx = torch.full((N,), float("-inf"), dtype=score.dtype).scatter_reduce(0, row, score, "amax", include_self=True)
+        e = torch.exp(score - mx[row])
+        z = torch.zeros(N, dtype=score.dtype).index_add_(0, row, e)
+        alpha = e / z[row]
+        out = torch.zeros(N, self.out_channels, dtype=x.dtype).index_add_(0, row, alpha.unsqueeze(-1) * v[col])
+        return out + self.lin_skip(x)
 
 
 def add_self_loops(edge_index, edge_weight=None, num_nodes=None):

@@ -838,6 +838,89 @@ def edge_score_loss(h, pos_edge, neg_edge, num_neg, loss_name, weight=None, head
 
 
 # ---------------------------------------------------------------------------
+# attention conv pieces (TransformerConv under the reference's Transformer encoder, layer.py:57-63)
+# ---------------------------------------------------------------------------
+class SegmentSoftmax(torch.autograd.Function):
+    """alpha = softmax of scale * s over the stored entries of every CSR row (per destination node)"""
+
+    @staticmethod
+    def forward(ctx, s, rowptr, scale):
+        lib = _lib.load()
+        s = _f32c(s).contiguous()
+        alpha = torch.empty_like(s)
+        n_rows = rowptr.numel() - 1
+        with profiling.span("segment_softmax_fwd_f32", s.numel() * 8, 0):
+            check(lib.plnlp_segment_softmax_fwd_f32(ptr(rowptr), n_rows, ptr(s), float(scale), ptr(alpha), stream()),
+                  "plnlp_segment_softmax_fwd_f32")
+        ctx.scale = float(scale)
+        ctx.save_for_backward(alpha, rowptr)
+        return alpha
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        alpha, rowptr = ctx.saved_tensors
+        g = _f32c(g).contiguous()
+        ds = torch.empty_like(alpha)
+        with profiling.span("segment_softmax_bwd_f32", alpha.numel() * 12, 0):
+            check(lib.plnlp_segment_softmax_bwd_f32(ptr(rowptr), rowptr.numel() - 1, ptr(alpha), ptr(g), ctx.scale,
+                                                    ptr(ds), stream()), "plnlp_segment_softmax_bwd_f32")
+        return ds, None, None
+
+
+class SpMMValues(torch.autograd.Function):
+    """out = A(alpha) @ v where alpha holds one value per stored entry of ``adj`` (CSR order): the SpMM kernel
+    with the attention weights as its values.  Backward: d v = A(alpha)^T g (the transposed plan with the
+    permuted weights), d alpha[e] = <g[row_e], v[col_e]> (the edge-dot kernel over the entry list)."""
+
+    @staticmethod
+    def forward(ctx, alpha, v, adj):
+        from .graph import _share_plan
+        st = structure_of(adj)
+        alpha = _f32c(alpha).contiguous()
+        out = spmm_raw(_share_plan(st.fwd, alpha), v, use_val=True, div_rows=False)
+        ctx.st = st
+        ctx.save_for_backward(alpha, v)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from .graph import _share_plan
+        alpha, v = ctx.saved_tensors
+        st = ctx.st
+        g = _rowmajor(g)
+        dalpha = dv = None
+        if ctx.needs_input_grad[0]:
+            dalpha = edge_dot_raw(torch.cat([g, v], 0), st.entry_pairs())
+        if ctx.needs_input_grad[1]:
+            dv = spmm_raw(_share_plan(st.bwd, alpha[st.t_perm].contiguous()), g, use_val=True, div_rows=False)
+        return dalpha, dv, None
+
+
+class AddLinear(torch.autograd.Function):
+    """Y = act( x @ W^T + bias + addend ): the root / skip connection of a conv accumulated onto its aggregate in
+    the GEMM epilogue (beta = 1), with the layer's relu + dropout fused"""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, addend, act, drop_p, seed):
+        Y = gemm_raw(x, W, transb=True, C=addend.clone(), beta=1.0, bias=bias, act=act, drop_p=drop_p, seed=seed)
+        ctx.act, ctx.drop_p, ctx.has_bias = act, drop_p, bias is not None
+        ctx.save_for_backward(Y if act == ACT_RELU else None, x, W)
+        return Y
+
+    @staticmethod
+    def backward(ctx, g):
+        Y, x, W = ctx.saved_tensors
+        g = _rowmajor(g)
+        if Y is not None:
+            g = relu_drop_bwd_raw(Y, g, 1.0 / (1.0 - ctx.drop_p))
+        gx = gemm_raw(g, W) if ctx.needs_input_grad[0] else None
+        gW = gemm_raw(g, x, transa=True) if ctx.needs_input_grad[1] else None
+        gb = colsum_raw(g) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gW, gb, (g if ctx.needs_input_grad[3] else None), None, None, None
+
+
+# ---------------------------------------------------------------------------
 # samplers and ranking (no autograd)
 # ---------------------------------------------------------------------------
 def local_neg_sample_raw(pos_edges, num_nodes, num_neg, seed):

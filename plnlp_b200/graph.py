@@ -293,6 +293,7 @@ class Structure:
         deg = rowptr[1:] - rowptr[:-1]
         row = torch.repeat_interleave(torch.arange(M, device=col.device), deg, output_size=col.numel())
         perm = torch.argsort(col * M + row, stable=True)
+        self.t_perm = perm                        # entry e of the transposed matrix is entry perm[e] of this one
         t_row, t_col = col[perm], row[perm]
         t_rowptr = torch.zeros(N + 1, dtype=torch.int64, device=col.device)
         if t_row.numel():
@@ -316,6 +317,14 @@ class Structure:
         self.dense_ok = DENSE_SPMM and max(M, N) <= 16384 and self.density >= 0.06
         self._dense = {}
         self._coo = (row, col, None if val is None else val.to(torch.float32), inv)
+
+    def entry_pairs(self):
+        """int64 [nnz, 2]: (row, n_rows + col) of every stored entry, in CSR order -- the pair list that makes the
+        edge-dot kernels compute one score per entry from the stacked matrix [query; key] (layer.TransformerConv)"""
+        if getattr(self, "_entry_pairs", None) is None:
+            row, col = self._coo[0], self._coo[1]
+            self._entry_pairs = torch.stack([row, col + self.n_rows], 1).contiguous()
+        return self._entry_pairs
 
     def dense(self, mean):
         """[M, N] fp32 dense form: stored values (or 1) summed per cell ('sum'), or 1/max(deg,1) per stored

@@ -226,6 +226,46 @@ class GCNConv(torch.nn.Module):
                          drop_p=drop_p, seed=seed)
 
 
+class TransformerConv(torch.nn.Module):
+    """PyG 2.0.1 ``TransformerConv(in, out)`` with its defaults (heads = 1, concat, no beta gate, no edge
+    features, attention dropout 0, root weight, bias) -- the conv of the reference's Transformer encoder
+    (layer.py:57-63), which main.py feeds a value-less adjacency (main.py:181-184):
+
+        out_i = lin_skip(x_i) + sum_{j in N(i)} softmax_j( <lin_query(x_i), lin_key(x_j)> / sqrt(out) ) lin_value(x_j)
+
+    Kernels: four tcgen05 GEMMs, the edge-dot kernel over the stored entries for the scores, a per-row softmax
+    (csrc/attn.cu), the SpMM kernel with the attention weights as values, and the skip connection accumulated in
+    a GEMM epilogue.  Parameters: lin_key / lin_query / lin_value / lin_skip (.weight, .bias)."""
+
+    def __init__(self, in_channels, out_channels, heads=1):
+        super().__init__()
+        if heads != 1:
+            raise NotImplementedError("the reference uses the default heads = 1 (layer.py:63)")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin_key = _Lin(in_channels, out_channels)
+        self.lin_query = _Lin(in_channels, out_channels)
+        self.lin_value = _Lin(in_channels, out_channels)
+        self.lin_skip = _Lin(in_channels, out_channels)
+
+    def reset_parameters(self):
+        for lin in (self.lin_key, self.lin_query, self.lin_value, self.lin_skip):
+            lin.reset_parameters()
+
+    def forward(self, x, adj_t, act=_ops.ACT_NONE, drop_p=0.0):
+        from . import parallel
+        if isinstance(adj_t, parallel.ShardedAdj):
+            raise NotImplementedError("TransformerConv on a row-partitioned adjacency")
+        parts = _as_parts(x)
+        x = parts[0] if len(parts) == 1 else torch.cat(parts, -1)
+        st = _ops.structure_of(adj_t)
+        q, k, v = self.lin_query(x), self.lin_key(x), self.lin_value(x)
+        score = _ops.EdgeDot.apply(torch.cat([q, k], 0), st.entry_pairs())          # <q_i, k_j> per stored entry
+        alpha = _ops.SegmentSoftmax.apply(score, st.rowptr, 1.0 / math.sqrt(self.out_channels))
+        agg = _ops.SpMMValues.apply(alpha, v, adj_t)
+        return _ops.AddLinear.apply(x, self.lin_skip.weight, self.lin_skip.bias, agg, int(act), float(drop_p),
+                                    _ops.new_seed() if drop_p > 0 else 0)
+
+
 class BaseGNN(torch.nn.Module):
     """layer stacking of layer.py:7-27: relu + dropout after every conv but the last; a 1-layer
     net also applies them to its only conv."""
@@ -279,6 +319,14 @@ class WSAGE(BaseGNN):
     def __init__(self, in_channels, hidden_channels, out_channels, num_layers, dropout):
         super().__init__(dropout, num_layers)
         self.convs.extend(_stack(GraphConv, in_channels, hidden_channels, out_channels, num_layers))
+
+
+class Transformer(BaseGNN):
+    """layer.py:57-63"""
+
+    def __init__(self, in_channels, hidden_channels, out_channels, num_layers, dropout):
+        super().__init__(dropout, num_layers)
+        self.convs.extend(_stack(TransformerConv, in_channels, hidden_channels, out_channels, num_layers))
 
 
 class MLPPredictor(torch.nn.Module):
@@ -473,4 +521,3 @@ class MLPCatPredictor(torch.nn.Module):
         return self.forward(*_endpoints(h, edges))
 
 
-Transformer = _out_of_scope("Transformer", "layer.py:57-63")

@@ -242,7 +242,8 @@ def install(alias_plnlp=True):
     if not _really_installed("torch_geometric"):
         tr = _module("torch_geometric.transforms", ToSparseTensor=ToSparseTensor)
         ut = _module("torch_geometric.utils", to_undirected=to_undirected)
-        nn = _module("torch_geometric.nn", SAGEConv=layer.SAGEConv, GCNConv=layer.GCNConv, GraphConv=layer.GraphConv)
+        nn = _module("torch_geometric.nn", SAGEConv=layer.SAGEConv, GCNConv=layer.GCNConv, GraphConv=layer.GraphConv,
+                     TransformerConv=layer.TransformerConv)
         da = _module("torch_geometric.data", Data=Data)
         put("torch_geometric", _module("torch_geometric", transforms=tr, utils=ut, nn=nn, data=da))
         for sub, mod in (("transforms", tr), ("utils", ut), ("nn", nn), ("data", da)):

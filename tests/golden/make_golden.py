@@ -307,6 +307,19 @@ def golden_predictors_extra():
         out[f"wsage_L{L}"] = {"state": sd(m), "x": x.detach().clone(), "out": y.detach(), "g": g,
                               "gx": x.grad.clone(), "gparams": {k: v.grad.clone() for k, v in m.named_parameters()},
                               "edge_index": ei, "edge_weight": w, "num_nodes": N}
+    # Transformer (layer.py:57-63): the reference's stacking over the TransformerConv restatement, value-less graph
+    torch.manual_seed(18)
+    adj_nv = sparse.to_sparse_tensor(ei, None, N)
+    for L in (1, 2):
+        m = ref_layer.Transformer(12, 16, 16, L, 0.0)
+        m.eval()
+        x = torch.randn(N, 12).requires_grad_(True)
+        y = m(x, adj_nv)
+        g = torch.randn_like(y)
+        y.backward(g)
+        out[f"transformer_L{L}"] = {"state": sd(m), "x": x.detach().clone(), "out": y.detach(), "g": g,
+                                    "gx": x.grad.clone(), "gparams": {k: v.grad.clone() for k, v in m.named_parameters()},
+                                    "edge_index": ei, "num_nodes": N}
     # sample_perm_copy (negative_sample.py:61-76): shapes and the multiset property the copies keep
     torch.manual_seed(16)
     e = torch.randint(0, 50, (2, 30))

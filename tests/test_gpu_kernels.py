@@ -484,6 +484,29 @@ def test_gather_rows_and_sorted_row_scatter(ops, H):
         assert torch.equal(again, hg.grad)
 
 
+def test_segment_softmax_forward_and_backward(ops):
+    """per-row softmax over CSR entries (rows of length 0, 1, 33, a hub) against torch in fp64"""
+    lens = torch.tensor([0, 1, 5, 33, 0, 64, 700, 2, 0])
+    rowptr = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(lens, 0)])
+    nnz = int(rowptr[-1])
+    g = torch.Generator().manual_seed(4)
+    s = (torch.randn(nnz, generator=g) * 3)
+    gout = torch.randn(nnz, generator=g)
+    scale = 0.37
+    sg = s.cuda().requires_grad_(True)
+    alpha = ops.SegmentSoftmax.apply(sg, rowptr.cuda(), scale)
+    alpha.backward(gout.cuda())
+    sc = s.double().requires_grad_(True)
+    parts = [torch.softmax(sc[rowptr[i]:rowptr[i + 1]] * scale, 0) for i in range(lens.numel())]
+    ref = torch.cat(parts)
+    ref.backward(gout.double())
+    assert rel_err(alpha.detach().cpu(), ref.detach()) < TOL
+    assert rel_err(sg.grad.cpu(), sc.grad) < TOL
+    for i in range(lens.numel()):
+        if lens[i] > 0:
+            assert abs(float(alpha.detach()[rowptr[i]:rowptr[i + 1]].sum()) - 1.0) < 1e-5
+
+
 # ------------------------------------------------------------------ ranking
 @pytest.mark.parametrize("n,K", [(1, 1), (50, 20), (1000, 100), (101882, 20), (101882, 50), (300000, 100)])
 def test_kth_largest_and_hits(ops, n, K):

@@ -263,6 +263,48 @@ def test_wsage_against_reference_golden(golden_dir):
             graph.DENSE_SPMM = True
 
 
+@pytest.mark.xfail(strict=False, reason="round 1 ended with 0 GPU minutes: on the last run forward and d/dx matched at 1e-5 "
+                   "and the only failing tensor was lin_key.bias, whose exact gradient is 0 (see below); the floor "
+                   "criterion was added afterwards and could not be re-run.  Remove this mark after the next GPU run.")
+def test_transformer_against_reference_golden(golden_dir):
+    """Transformer (layer.py:57-63; PyG TransformerConv = per-destination softmax attention): the reference's
+    stacking over the restated conv, forward and every gradient, 1 and 2 layers.
+
+    lin_key.bias shifts every score of a destination row by the same <q_i, b_k>, which the softmax ignores: its
+    exact gradient is 0 and the reference's own fp32 value is rounding noise (~1e-7 next to gradients of ~10), so
+    parameter gradients are compared with an absolute floor of 2e-5 x the largest gradient tensor, like the
+    predictor biases under the AUC loss elsewhere in this file."""
+    from plnlp_b200.layer import Transformer
+    G = torch.load(os.path.join(golden_dir, "predictors_extra.pt"))
+    for L in (1, 2):
+        rec = G[f"transformer_L{L}"]
+        N = rec["num_nodes"]
+        o = sparse.to_sparse_tensor(rec["edge_index"], None, N)
+        rowptr, col, val = o.csr()
+        g = _gpu_graph(rowptr, col, val, N)
+        m = Transformer(12, 16, 16, L, 0.0).cuda()
+        assert sorted(k for k, _ in m.named_parameters()) == sorted(rec["state"])
+        _load_module(m, rec["state"])
+        m.eval()
+        x = rec["x"].cuda().requires_grad_(True)
+        y = m(x, g)
+        assert rel_err(y.detach().cpu(), rec["out"]) < TOL
+        y.backward(rec["g"].cuda())
+        assert rel_err(x.grad.cpu(), rec["gx"]) < 2 * TOL
+        floor = 2 * TOL * max(float(v.abs().max()) for v in rec["gparams"].values())
+        for name, p in m.named_parameters():
+            want = rec["gparams"][name]
+            err = float((p.grad.cpu() - want).abs().max())
+            assert err <= 2 * TOL * float(want.abs().max()) or err <= floor, (name, err)
+    # training mode: relu + dropout fused into the skip GEMM's epilogue, deterministic given the seed stream
+    m.train(); m.dropout = 0.5
+    torch.manual_seed(1)
+    a = m(x.detach(), g)
+    torch.manual_seed(1)
+    b = m(x.detach(), g)
+    assert torch.equal(a, b) and a.shape == y.shape
+
+
 def test_extra_predictors_against_reference_golden(golden_dir):
     """BIL / MLPDOT / MLPBIL / MLPCAT (layer.py:90-189): forward and every gradient against
     outputs of the real reference modules; the edge-level entry ``score_edges`` (node-level transform where no
@@ -271,7 +313,7 @@ def test_extra_predictors_against_reference_golden(golden_dir):
     G = torch.load(os.path.join(golden_dir, "predictors_extra.pt"))
     H = 20
     for key, rec in G.items():
-        if key.startswith(("perm_copy", "wsage")):
+        if key.startswith(("perm_copy", "wsage", "transformer")):
             continue
         L = int(key.split("_L")[1]) if "_L" in key else 0
         if key == "bil":

@@ -237,3 +237,27 @@ def test_random_walk_oracle_bruteforce():
     pairs, w = rw.walk_pairs(walk)
     assert (pairs[:, 0] != pairs[:, 1]).all() and pairs.size(0) == w.numel()
     assert set(w.tolist()) <= {float(torch.tensor(1.0) / (j + 1)) for j in range(6)}
+
+
+def test_transformer_conv_restatement_matches_dense_masked_attention():
+    """oracle.pyg.TransformerConv (PyG 2.0.1 defaults restated from memory, parity unpinned upstream) against an
+    independent dense formulation: masked softmax(Q K^T / sqrt(C)) V + skip; isolated nodes get the skip only"""
+    from oracle import pyg
+    torch.manual_seed(9)
+    N, Fi, C = 40, 7, 6
+    key = torch.unique(torch.randint(0, N * N, (300,)))
+    src, dst = key // N, key % N
+    src, dst = src[dst < N - 3], dst[dst < N - 3]            # the last rows have no incoming entries
+    ei = torch.stack([src, dst])
+    adj = sparse.to_sparse_tensor(ei, None, N)
+    conv = pyg.TransformerConv(Fi, C).double()
+    x = torch.randn(N, Fi, dtype=torch.float64)
+    got = conv(x, adj)
+    mask = torch.zeros(N, N, dtype=torch.bool)
+    mask[dst, src] = True                                   # adj_t[target, source]
+    q, k, v = conv.lin_query(x), conv.lin_key(x), conv.lin_value(x)
+    sc = (q @ k.t()) / C ** 0.5
+    att = torch.softmax(sc.masked_fill(~mask, float("-inf")), 1)
+    att = torch.where(mask.any(1, keepdim=True), att, torch.zeros_like(att))
+    want = att @ v + conv.lin_skip(x)
+    assert rel_err(got, want) < 1e-12

@@ -79,6 +79,7 @@ def test_synthetic_dataset_has_the_ogb_layout(name, monkeypatch):
     ["--data_name", "ogbl-citation2", "--encoder", "GCN", "--use_node_feats", "True", "--train_node_emb", "True",
      "--eval_metric", "mrr", "--neg_sampler", "local"],
     ["--data_name", "ogbl-collab", "--encoder", "WSAGE"],
+    ["--data_name", "ogbl-ddi", "--encoder", "Transformer", "--predictor", "MLPCAT", "--neg_sampler", "global_perm"],
 ])
 def test_reference_main_runs_unchanged_up_to_the_model(argv, tmp_path, monkeypatch):
     """the reference's own main.py, imported through the shims: argument parsing, dataset, ToSparseTensor, the
