@@ -390,15 +390,6 @@ class DotPredictor(torch.nn.Module):
         return []
 
 
-def _out_of_scope(name, where):
-    class _Stub(torch.nn.Module):
-        def __init__(self, *args, **kwargs):
-            raise NotImplementedError(
-                f"{name} ({where}) is outside the hot-path scope of plnlp_b200 (SURVEY.md section 8f)")
-    _Stub.__name__ = _Stub.__qualname__ = name
-    return _Stub
-
-
 def _endpoints(h, edges):
     """x_i = h[edge[0]], x_j = h[edge[1]] (model.py:155-156) as two [P, H] matrices"""
     return _ops.GatherRows.apply(h, edges, 0), _ops.GatherRows.apply(h, edges, 1)
