@@ -415,7 +415,7 @@ def cpu_baseline_guarded(workload, steps, timeout_s=None):
     otherwise reported as unavailable instead of taking the whole bench line with it."""
     import subprocess
     if timeout_s is None:       # normal duration: ~15 s (ddi / collab shape), ~90 s (citation2 shape: graph build + steps)
-        timeout_s = 420 if workload == "citation2" else 150
+        timeout_s = 420 if workload == "citation2" else 240
     code = ("import json, sys, bench; "
             "print('CPU_BASELINE ' + json.dumps(bench.cpu_baseline(dict(bench.WORKLOADS[sys.argv[1]]), "
             "steps=int(sys.argv[2]), threads=int(sys.argv[3]) or None)))")
@@ -517,9 +517,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ddi", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--cpu-steps", type=int, default=None,
+                    help="steps of the CPU arm's bounded sample (default: ~10-20 s of CPU work: one 17-batch epoch of "
+                         "the ddi / collab shape, 2 steps of the citation2 shape)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.cpu_steps is None:
+        args.cpu_steps = 2 if args.workload == "citation2" else 17
     # the contract is ONE JSON line on stdout: keep a private handle to the real stdout and point fd 1
     # at stderr so that library banners (e.g. "NCCL version ...") cannot pollute it
     global _OUT
