@@ -101,7 +101,7 @@ def gcn_normalization(adj_t):
 
 
 def adj_normalization(adj_t):
-    """utils.py:92-97 (used only by the out-of-scope WSAGE encoder; kept importable for main.py:13)."""
+    """utils.py:92-97: row-normalise the adjacency, D^-1 A (main.py applies it for the WSAGE encoder, :179-180)."""
     deg = adj_t.sum(dim=1).to(torch.float)
     inv = deg.pow(-1)
     inv[inv == float('inf')] = 0
