@@ -192,10 +192,13 @@ class GCNConv(torch.nn.Module):
         torch.nn.init.zeros_(self.bias)
 
     def can_restrict(self, x, adj_t):
-        """whether ``forward(..., out_rows=)`` can compute just those output rows: a single-device sparse
-        adjacency (the row-partitioned run and the dense tensor-core path compute every row)"""
+        """whether ``forward(..., out_rows=)`` can compute just those output rows: a sparse adjacency (the dense
+        tensor-core path computes every row); on a row-partitioned adjacency only when
+        ``parallel.RESTRICT_LAST`` is on (``out_rows`` are then LOCAL row ids of this rank's block)"""
         from . import parallel
-        return not (isinstance(adj_t, parallel.ShardedAdj) or _ops.structure_of(adj_t).dense_ok)
+        if isinstance(adj_t, parallel.ShardedAdj):
+            return parallel.RESTRICT_LAST and not _ops.structure_of(adj_t.local).dense_ok
+        return not _ops.structure_of(adj_t).dense_ok
 
     def forward(self, x, adj_t, act=_ops.ACT_NONE, drop_p=0.0, out_rows=None):
         parts = _as_parts(x)
@@ -206,7 +209,11 @@ class GCNConv(torch.nn.Module):
             # Aggregating first keeps the linear map and both of its backward GEMMs at T rows instead of N.
             if not self.can_restrict(x, adj_t):
                 raise RuntimeError("out_rows: this layer / adjacency cannot restrict its output rows")
-            aggs = [_ops.spmm_rows(adj_t, p, out_rows, reduce="sum") for p in parts]
+            from . import parallel
+            if isinstance(adj_t, parallel.ShardedAdj):
+                aggs = [parallel.pspmm_rows(adj_t, p, out_rows, reduce="sum") for p in parts]
+            else:
+                aggs = [_ops.spmm_rows(adj_t, p, out_rows, reduce="sum") for p in parts]
             return _ops.fused_linear(aggs, ws, self.bias, act, drop_p, seed)
         live = sum(p.size(1) for p in parts if not _is_const(p))
         if REASSOCIATE and live < self.out_channels:

@@ -137,6 +137,10 @@ class BaseModel(object):
         # layer cannot restrict itself (row-partitioned run) only the backward skips the all-zero rows.
         touched = 2 * (pos_edge.size(0) + neg_edge.size(0)) * max(self.world_size if self.partitioned else 1, 1)
         sparse_rows = ROW_SPARSE_GRAD and touched < 0.5 * self.num_nodes
+        restrict_part = False
+        if self.partitioned:
+            from . import parallel
+            restrict_part = sparse_rows and parallel.RESTRICT_LAST and parallel.EXCHANGE == "rows"
         if sparse_rows and not self.partitioned:
             ids, inv = torch.unique(torch.cat([pos_edge, neg_edge], 0), return_inverse=True)
             h, restricted = self.encoder(self.input_parts(data), data.adj_t, out_rows=ids)
@@ -144,15 +148,23 @@ class BaseModel(object):
                 pos_edge, neg_edge = inv[:pos_edge.size(0)], inv[pos_edge.size(0):]
             else:
                 h = _ops.row_sparse_grad(h)
+        elif restrict_part:
+            # row-partitioned run, requests first (parallel.exchange_row_requests): every owner learns which of its
+            # rows any rank's batch reads, computes the last conv for exactly those and serves them
+            ids, inv = torch.unique(torch.cat([pos_edge, neg_edge], 0), return_inverse=True)
+            req = parallel.exchange_row_requests(ids, data.adj_t.blk, data.adj_t.group)
+            rows_local, where = torch.unique(req.want, return_inverse=True)
+            h, restricted = self.encoder(self.input_parts(data), data.adj_t, out_rows=rows_local)
+            h = parallel.serve_rows(h, where if restricted else req.want, req, data.adj_t.group)
+            pos_edge, neg_edge = inv[:pos_edge.size(0)], inv[pos_edge.size(0):]
         else:
             h = self.encoder(self.input_parts(data), data.adj_t)
             if sparse_rows:
                 h = _ops.row_sparse_grad(h)
-        if self.partitioned:
+        if self.partitioned and not restrict_part:
             # row-partitioned encoder: h is this rank's row block and scoring needs arbitrary
             # endpoints.  Fetch just the distinct endpoint rows of this rank's batch from their owners
             # (parallel.FetchRows; gradients return the same way) and score on that compact table.
-            from . import parallel
             if parallel.EXCHANGE == "rows":
                 ids, inv = torch.unique(torch.cat([pos_edge, neg_edge], 0), return_inverse=True)
                 h = parallel.fetch_rows(h, ids)

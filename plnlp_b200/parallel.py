@@ -27,6 +27,10 @@ import torch.distributed as dist
 # how the scoring step of the row-partitioned model gets its endpoint embeddings: "rows" = only the distinct
 # endpoint rows of the batch, by all_to_all (FetchRows); "allgather" = the whole matrix
 EXCHANGE = os.environ.get("PLNLP_EXCHANGE", "rows")
+# row-partitioned run: exchange the row requests BEFORE the last conv and let every owner compute only the rows
+# that were requested (DESIGN.md 4a item 3 for the partitioned encoder).  Bookkeeping verified on CPU (gloo,
+# tests/test_parallel_cpu.py); OFF by default until it has been through the 2-rank NCCL parity test on GPUs.
+RESTRICT_LAST = os.environ.get("PLNLP_PARTITIONED_RESTRICT", "0") == "1"
 
 
 def world():
@@ -164,6 +168,71 @@ def fetch_rows(h_local, ids, group=None, gather_fn=None, scatter_fn=None):
     return FetchRows.apply(h_local, ids, group, gather_fn, scatter_fn)
 
 
+class RowRequests:
+    """result of ``exchange_row_requests``: ``want`` = the local row ids other ranks (and this one) asked THIS
+    rank for, concatenated in requester order; the split sizes of the exchange in both directions"""
+
+    def __init__(self, want, send_split, recv_split, n_ids):
+        self.want, self.send_split, self.recv_split, self.n_ids = want, send_split, recv_split, n_ids
+
+
+def exchange_row_requests(ids, blk, group=None):
+    """phase 1 of the endpoint-row exchange on its own: every rank sends the sorted distinct global row ids it
+    needs to their owners.  Knowing ``want`` BEFORE the last conv runs lets the owner compute only the requested
+    rows (``pspmm_rows``) and then serve them (``serve_rows``).  One host read (the split sizes)."""
+    _, ws = world()
+    dev = ids.device
+    bounds = torch.arange(ws + 1, device=dev, dtype=ids.dtype) * blk
+    cut = torch.searchsorted(ids, bounds)
+    send_cnt = (cut[1:] - cut[:-1]).to(torch.int64)
+    recv_cnt = torch.empty_like(send_cnt)
+    dist.all_to_all_single(recv_cnt, send_cnt, group=group)
+    both = torch.stack([send_cnt, recv_cnt]).tolist()
+    send_split, recv_split = both[0], both[1]
+    owner = torch.repeat_interleave(torch.arange(ws, device=dev, dtype=ids.dtype), send_cnt, output_size=ids.numel())
+    want = torch.empty(sum(recv_split), dtype=ids.dtype, device=dev)
+    dist.all_to_all_single(want, ids - owner * blk, recv_split, send_split, group=group)
+    return RowRequests(want, send_split, recv_split, ids.numel())
+
+
+class ServeRows(torch.autograd.Function):
+    """phase 2: ``rows[i] = src[pos[j]]`` for every request j this rank received, delivered to the requester.
+    ``src`` is whatever table the owner holds the requested rows in -- its whole block (pos = want) or the compact
+    output of a row-restricted last conv (pos = position of want in the sorted distinct requested rows).
+    Backward: gradient rows return to the owner and are summed into ``src``'s rows in a fixed order."""
+
+    @staticmethod
+    def forward(ctx, src, pos, req, group, gather_fn, scatter_fn):
+        rank, _ = world()
+        served = gather_fn(src, pos)
+        rows = torch.empty(req.n_ids, src.size(1), dtype=src.dtype, device=src.device)
+        from . import profiling
+        with profiling.span("nccl all_to_all (endpoint rows)", (req.n_ids - req.send_split[rank]) * src.size(1) * 4, 0):
+            dist.all_to_all_single(rows, served, req.send_split, req.recv_split, group=group)
+        ctx.group, ctx.n_src, ctx.scatter_fn, ctx.req = group, src.size(0), scatter_fn, req
+        ctx.save_for_backward(pos)
+        return rows
+
+    @staticmethod
+    def backward(ctx, g):
+        (pos,) = ctx.saved_tensors
+        req = ctx.req
+        rank, _ = world()
+        back = torch.empty(pos.numel(), g.size(1), dtype=g.dtype, device=g.device)
+        from . import profiling
+        with profiling.span("nccl all_to_all (endpoint row grads)", (g.size(0) - req.send_split[rank]) * g.size(1) * 4, 0):
+            dist.all_to_all_single(back, g.contiguous(), req.recv_split, req.send_split, group=ctx.group)
+        return ctx.scatter_fn(back, pos, ctx.n_src), None, None, None, None, None
+
+
+def serve_rows(src, pos, req, group=None, gather_fn=None, scatter_fn=None):
+    if gather_fn is None or scatter_fn is None:
+        from . import _ops
+        gather_fn = gather_fn or _ops.gather_rows_idx_raw
+        scatter_fn = scatter_fn or _ops.row_scatter_raw
+    return ServeRows.apply(src, pos, req, group, gather_fn, scatter_fn)
+
+
 class ShardedAdj:
     """Rows ``[lo, hi)`` of an adjacency, columns in the padded global index space ``[0, R*blk)``."""
 
@@ -196,6 +265,17 @@ def pad_rows(x, blk):
         return x
     pad = torch.zeros(blk - x.size(0), x.size(1), dtype=x.dtype, device=x.device)
     return torch.cat([x, pad], 0)
+
+
+def pspmm_rows(sadj, x_local, rows_local, reduce="sum", local_op=None):
+    """row-partitioned SpMM restricted to the output rows ``rows_local`` (local ids, sorted, distinct) of this
+    rank's block, written compactly: (A[lo:hi, :] @ all_gather(x_local))[rows_local].  ``local_op(adj, x, rows,
+    reduce)`` defaults to the CUDA row-subset SpMM (``_ops.spmm_rows``)."""
+    if local_op is None:
+        from . import _ops
+        local_op = _ops.spmm_rows
+    x_full = gather_rows(pad_rows(x_local, sadj.blk), sadj.group)
+    return local_op(sadj.local, x_full, rows_local, reduce)
 
 
 def pspmm(sadj, x_local, reduce="sum", local_op=None, **epilogue):

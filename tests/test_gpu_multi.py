@@ -124,3 +124,73 @@ def test_partitioned_matches_single_gpu_nccl_ws2():
             # for the AUC loss: heavy cancellation, and the two runs add the pairs in different orders
             tol = 2e-3 if ".pred." in k else 2e-5
             assert v < tol, (r, k, v)
+
+
+def _restricted_worker(rank, ws, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=ws, device_id=dev)
+    try:
+        from plnlp_b200 import graph, parallel
+        from plnlp_b200.graph import CSRGraph
+        from plnlp_b200.utils import gcn_normalization
+        graph.DENSE_SPMM = False
+        N = 301
+        ei, _ = rand_graph(N, 3000, seed=9, hub=True)
+        ei = ei[:, ei[0] != ei[1]]
+        adj = gcn_normalization(CSRGraph.from_edge_index(torch.cat([ei, ei.flip(0)], 1).to(dev), None, N).to_symmetric())
+        lo, hi = parallel.row_block(N, rank, ws)
+        blk = parallel.block_size(N, ws)
+        sadj = parallel.shard_graph(adj, rank, ws, CSRGraph)
+        B, k = 16, 2                                    # few pairs: the batches touch a small part of the nodes
+        gg = torch.Generator().manual_seed(2)
+        pos_all = torch.randint(0, N, (ws * B, 2), generator=gg).to(dev)
+        neg_all = torch.randint(0, N, (ws * B, k, 2), generator=gg).to(dev)
+        feats = torch.randn(N, 8, generator=gg).to(dev)
+        single = _model(N, 8, dev, "GCN")
+        d1 = Data(); d1.adj_t, d1.x, d1.edge_index = adj, feats, None
+        single.encoder.train(); single.predictor.train()
+        single.optimizer = torch.optim.SGD(single.para_list, lr=0.0)
+        loss1 = single.train_batch(d1, pos_all, neg_all.reshape(-1, 2), k)
+        part = _model(blk, 8, dev, "GCN")
+        with torch.no_grad():
+            for a, b in zip(part.encoder.parameters(), single.encoder.parameters()):
+                a.copy_(b)
+            for a, b in zip(part.predictor.parameters(), single.predictor.parameters()):
+                a.copy_(b)
+            part.emb.weight.zero_()
+            part.emb.weight[: hi - lo].copy_(single.emb.weight[lo:hi])
+        part.world_size, part.rank, part.partitioned = ws, rank, True
+        part.num_nodes = 10 ** 9                         # "a batch touches a small part of the node set"
+        part.optimizer = torch.optim.SGD(part.para_list, lr=0.0)
+        d2 = Data(); d2.adj_t, d2.x, d2.edge_index = sadj, parallel.pad_rows(feats[lo:hi].contiguous(), blk), None
+        part.encoder.train(); part.predictor.train()
+        parallel.RESTRICT_LAST, parallel.EXCHANGE = True, "rows"
+        loss2 = part.train_batch(d2, pos_all[rank * B:(rank + 1) * B], neg_all[rank * B:(rank + 1) * B].reshape(-1, 2), k)
+        tot = loss2.clone()
+        dist.all_reduce(tot)
+        errs = {"loss": abs(float(tot) - float(loss1)) / abs(float(loss1)),
+                "emb": rel_err(part.emb.weight.grad[: hi - lo], single.emb.weight.grad[lo:hi])}
+        for (n1, a), b in zip(part.encoder.named_parameters(), single.encoder.parameters()):
+            errs["enc." + n1] = rel_err(a.grad, b.grad)
+        for (n1, a), b in zip(part.predictor.named_parameters(), single.predictor.parameters()):
+            errs["pred." + n1] = rel_err(a.grad, b.grad)
+        ret[rank] = errs
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.xfail(strict=False, reason="PLNLP_PARTITIONED_RESTRICT (off by default) was written after the round's GPU "
+                   "minutes were spent: bookkeeping verified with gloo on CPU only; remove this mark after a 2-GPU run")
+def test_partitioned_restricted_last_layer_nccl_ws2():
+    """requests first, then every owner computes the last conv only for the requested rows
+    (parallel.exchange_row_requests / pspmm_rows / serve_rows) vs the single-GPU step"""
+    ws = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_restricted_worker, args=(ws, _free_port(), ret), nprocs=ws, join=True)
+    for r in range(ws):
+        for k, v in ret[r].items():
+            tol = 2e-3 if k.startswith("pred.") else 2e-5
+            assert v < tol, (r, k, v)
