@@ -44,17 +44,24 @@ def test_gcn_normalization_matches_oracle():
     _same(a, b)
 
 
-def _emulate(plan, x, use_val, div):
-    """python emulation of csrc/spmm.cu driven by the plan arrays"""
+def _emulate(plan, x, use_val, div, x_index=None):
+    """python emulation of csrc/spmm.cu driven by the plan arrays (explicit item ends of row-subset plans and the
+    x_index of a row-sparse operand included)"""
     F = x.size(1)
     out = torch.full((plan.n_rows, F), float("nan"))
     partial = torch.zeros(max(plan.n_partial, 1), F)
     for i in range(plan.n_items):
-        b, e = int(plan.item_ptr[i]), int(plan.item_ptr[i + 1])
+        b = int(plan.item_ptr[i])
+        e = int(plan.item_end[i]) if plan.item_end is not None else int(plan.item_ptr[i + 1])
         acc = torch.zeros(F)
         for p in range(b, e):
             v = plan.val[p] if (use_val and plan.val is not None) else 1.0
-            acc = acc + v * x[int(plan.col[p])]
+            c = int(plan.col[p])
+            if x_index is not None:
+                c = int(x_index[c])
+                if c < 0:
+                    continue
+            acc = acc + v * x[c]
         s = int(plan.item_slot[i])
         if s >= 0:
             partial[s] = acc
@@ -116,6 +123,35 @@ def test_subset_plan_covers_exactly_the_selected_rows():
             assert int(slot[sel][0]) == -1
     assert p.nnz == int((rowptr[rows + 1] - rowptr[rows]).sum())
     assert p.n_fix == int(((rowptr[rows + 1] - rowptr[rows]) > 32).sum()) and p.n_partial == int((slot >= 0).sum())
+
+
+def test_subset_plan_and_row_sparse_operand_emulated():
+    """the two plan-level tricks behind the last conv, emulated on the CPU from the plan
+    arrays exactly as csrc/spmm.cu walks them: a row-subset plan yields the selected rows of the full product,
+    and an x_index with -1 entries yields the full product of the operand with those rows zeroed"""
+    from plnlp_b200.graph import build_subset_plan
+    N, F = 90, 5
+    ei, w = rand_graph(N, 700, seed=21, weighted=True, hub=True)
+    o = sparse.to_sparse_tensor(ei, w, N)
+    rowptr, col, val = o.csr()
+    parent = build_plan(rowptr, col, val, N, N, chunk=16)
+    x = torch.randn(N, F)
+    full = _emulate(parent, x, True, False)
+    assert rel_err(full, sparse.matmul(o, x, "sum")) < 1e-5
+    rows = torch.unique(torch.cat([torch.randint(0, N, (25,)), torch.tensor([2, N - 1])]))
+    sub = build_subset_plan(parent, rowptr, rows)
+    assert torch.equal(_emulate(sub, x, True, False), full[rows])            # same per-row order: same bits
+    keep = torch.rand(N) < 0.3
+    x_index = torch.where(keep, torch.arange(N), torch.full((N,), -1)).to(torch.int32)
+    xz = x.clone()
+    xz[~keep] = 0
+    assert torch.equal(_emulate(parent, x, True, False, x_index=x_index), _emulate(parent, xz, True, False))
+    # compact operand: x_index maps a source row to its position in a [T, F] matrix
+    live = torch.nonzero(keep).reshape(-1)
+    compact_index = torch.full((N,), -1, dtype=torch.int32)
+    compact_index[live] = torch.arange(live.numel(), dtype=torch.int32)
+    assert torch.equal(_emulate(parent, x[live], True, False, x_index=compact_index),
+                       _emulate(parent, xz, True, False))
 
 
 def test_adjust_lr_and_loss_dispatch():
