@@ -31,6 +31,21 @@ def conv_forward(kind, p, x, adj_t):
     if kind == "GCN":
         z = F.linear(x, p["lin.weight"])
         return sparse.matmul(adj_t, z, reduce="sum") + p["bias"]
+    if kind == "WSAGE":          # layer.py:48-54: PyG GraphConv, weighted-sum aggregation
+        agg = sparse.matmul(adj_t, x, reduce="sum")
+        return F.linear(agg, p["lin_rel.weight"], p["lin_rel.bias"]) + F.linear(x, p["lin_root.weight"])
+    if kind == "TRANSFORMER":    # layer.py:57-63: PyG TransformerConv with its defaults (see oracle/pyg.py)
+        row, col, _ = adj_t.coo()
+        q = F.linear(x, p["lin_query.weight"], p["lin_query.bias"])
+        k = F.linear(x, p["lin_key.weight"], p["lin_key.bias"])
+        v = F.linear(x, p["lin_value.weight"], p["lin_value.bias"])
+        score = (q[row] * k[col]).sum(-1) / math.sqrt(q.size(1))
+        n = x.size(0)
+        mx = torch.full((n,), float("-inf"), dtype=score.dtype).scatter_reduce(0, row, score, "amax", include_self=True)
+        e = torch.exp(score - mx[row])
+        alpha = e / torch.zeros(n, dtype=score.dtype).index_add_(0, row, e)[row]
+        agg = torch.zeros(n, q.size(1), dtype=x.dtype).index_add_(0, row, alpha.unsqueeze(-1) * v[col])
+        return agg + F.linear(x, p["lin_skip.weight"], p["lin_skip.bias"])
     raise NotImplementedError(kind)
 
 
@@ -66,6 +81,38 @@ def mlp_score(lins, x_i, x_j, keep_masks=None, p_drop=0.0):
 def dot_score(x_i, x_j):
     """layer.py:174-176; output [P]."""
     return (x_i * x_j).sum(-1)
+
+
+def _node_mlp(lins, x):
+    """the shared loop of MLPDotPredictor / MLPBilPredictor (layer.py:132-137, 157-162) in eval mode: EVERY linear
+    is followed by relu (dropout is the identity without training)"""
+    for W, b in lins:
+        x = torch.relu(F.linear(x, W, b))
+    return x
+
+
+def bil_score(W, x_i, x_j):
+    """BilinearPredictor, layer.py:179-189: sum(bilin(x_i) * x_j, -1); output [P]."""
+    return (F.linear(x_i, W) * x_j).sum(-1)
+
+
+def mlpdot_score(lins, x_i, x_j):
+    """MLPDotPredictor, layer.py:119-139; output [P]."""
+    return (_node_mlp(lins, x_i) * _node_mlp(lins, x_j)).sum(-1)
+
+
+def mlpbil_score(lins, W, x_i, x_j):
+    """MLPBilPredictor, layer.py:142-164; output [P]."""
+    return (F.linear(_node_mlp(lins, x_i), W) * _node_mlp(lins, x_j)).sum(-1)
+
+
+def mlpcat_score(lins, x_i, x_j):
+    """MLPCatPredictor, layer.py:90-116: the MLP on [x_i | x_j] and on [x_j | x_i], averaged; output [P, out]."""
+    x1, x2 = torch.cat([x_i, x_j], -1), torch.cat([x_j, x_i], -1)
+    for W, b in lins[:-1]:
+        x1, x2 = torch.relu(F.linear(x1, W, b)), torch.relu(F.linear(x2, W, b))
+    W, b = lins[-1]
+    return (F.linear(x1, W, b) + F.linear(x2, W, b)) / 2
 
 
 # ---------------------------------------------------------------------------

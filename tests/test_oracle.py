@@ -261,3 +261,47 @@ def test_transformer_conv_restatement_matches_dense_masked_attention():
     att = torch.where(mask.any(1, keepdim=True), att, torch.zeros_like(att))
     want = att @ v + conv.lin_skip(x)
     assert rel_err(got, want) < 1e-12
+
+
+def test_extra_predictors_and_encoders_match_reference(golden_dir):
+    """the restatements of layer.py:48-63, 90-189 (WSAGE, Transformer stacking; BIL / MLPDOT / MLPBIL / MLPCAT) against
+    the outputs and gradients of the REAL reference modules (tests/golden/predictors_extra.pt)"""
+    G = torch.load(os.path.join(golden_dir, "predictors_extra.pt"))
+
+    def lins_of(state):
+        n = len([k for k in state if k.startswith("lins.") and k.endswith(".weight")])
+        return [(state[f"lins.{i}.weight"].clone().requires_grad_(True), state[f"lins.{i}.bias"].clone().requires_grad_(True))
+                for i in range(n)]
+
+    for key, rec in G.items():
+        if key.startswith(("perm_copy", "wsage", "transformer")):
+            continue
+        xi, xj = rec["xi"].clone().requires_grad_(True), rec["xj"].clone().requires_grad_(True)
+        st = rec["state"]
+        lins = lins_of(st)
+        W = st["bilin.weight"].clone().requires_grad_(True) if "bilin.weight" in st else None
+        if key == "bil":
+            out = plnlp_ref.bil_score(W, xi, xj)
+        elif key.startswith("mlpdot"):
+            out = plnlp_ref.mlpdot_score(lins, xi, xj)
+        elif key.startswith("mlpbil"):
+            out = plnlp_ref.mlpbil_score(lins, W, xi, xj)
+        else:
+            out = plnlp_ref.mlpcat_score(lins, xi, xj)
+        assert out.shape == rec["out"].shape and rel_err(out.detach(), rec["out"]) < 1e-6, key
+        out.backward(rec["g"])
+        assert rel_err(xi.grad, rec["gxi"]) < 1e-5 and rel_err(xj.grad, rec["gxj"]) < 1e-5, key
+        for i, (Wl, bl) in enumerate(lins):
+            assert rel_err(Wl.grad, rec["gparams"][f"lins.{i}.weight"]) < 1e-5, key
+        if W is not None:
+            assert rel_err(W.grad, rec["gparams"]["bilin.weight"]) < 1e-5, key
+    for kind, prefix, weighted in (("WSAGE", "wsage", True), ("TRANSFORMER", "transformer", False)):
+        for L in (1, 2):
+            rec = G[f"{prefix}_L{L}"]
+            adj = sparse.to_sparse_tensor(rec["edge_index"], rec.get("edge_weight") if weighted else None, rec["num_nodes"])
+            layers = []
+            for i in range(L):
+                pre = f"convs.{i}."
+                layers.append({k[len(pre):]: v for k, v in rec["state"].items() if k.startswith(pre)})
+            out = plnlp_ref.encoder_forward(kind, layers, rec["x"], adj)
+            assert rel_err(out, rec["out"]) < 1e-6, (kind, L)
