@@ -215,11 +215,13 @@ class BaseModel(object):
         self.encoder.train()
         self.predictor.train()
         if self.world_size > 1 and neg_edges is None:
-            # data-parallel edge batches: rank r trains on edges r, r+R, r+2R, ... (equal counts on every
-            # rank so the per-step collectives line up)
+            # data-parallel edge batches: rank r trains on the r-th contiguous block of the epoch's edges (equal
+            # counts on every rank so the per-step collectives line up).  A contiguous block is a VIEW of the
+            # caller's (pinned host) tensor, so only this rank's share is copied to the device; a strided pick
+            # r, r+R, ... would first gather on the host, inside the epoch.
             tr = split_edge['train']
             n_each = next(iter(tr.values())).size(0) // self.world_size
-            tr = {k: v[self.rank::self.world_size][:n_each] for k, v in tr.items()}
+            tr = {k: v[self.rank * n_each:(self.rank + 1) * n_each] for k, v in tr.items()}
             split_edge = dict(split_edge, train=tr)
         if neg_edges is None:
             pos_train_edge, neg_train_edge = get_pos_neg_edges(
