@@ -182,8 +182,10 @@ def _restricted_worker(rank, ws, port, ret):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-@pytest.mark.xfail(strict=False, reason="PLNLP_PARTITIONED_RESTRICT (off by default) was written after the round's GPU "
-                   "minutes were spent: bookkeeping verified with gloo on CPU only; remove this mark after a 2-GPU run")
+@pytest.mark.skipif(os.environ.get("PLNLP_RUN_STAGED") != "1",
+                    reason="PLNLP_PARTITIONED_RESTRICT (off by default) was written after the round's GPU minutes were "
+                           "spent: bookkeeping verified with gloo on CPU only.  Run with PLNLP_RUN_STAGED=1 on 2 GPUs "
+                           "(under a timeout: a mismatch in the collective sequence would hang), then drop this mark")
 def test_partitioned_restricted_last_layer_nccl_ws2():
     """requests first, then every owner computes the last conv only for the requested rows
     (parallel.exchange_row_requests / pspmm_rows / serve_rows) vs the single-GPU step"""
