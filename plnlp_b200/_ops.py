@@ -168,41 +168,6 @@ def row_nonzero_index_raw(x):
     return index
 
 
-# Row-sparsity hints for gradients.  The gradient of the embeddings w.r.t. the scoring loss is non-zero only at
-# the endpoint rows of the edge batch; ``row_sparse_grad(h)`` (an identity in forward) measures that on the
-# incoming gradient and leaves an index vector here, keyed by the gradient's storage, for the backward of the
-# layer that produced h: its A^T g product then skips the all-zero rows (spmm_raw(x_index=)).  Ops that map zero
-# rows to zero rows (relu mask, g @ W) hand the hint on to their result.
-_ROW_HINTS = {}
-
-
-def _put_hint(t, mask):
-    if len(_ROW_HINTS) > 4:
-        _ROW_HINTS.clear()
-    _ROW_HINTS[t.data_ptr()] = (t.size(0), mask)
-
-
-def _take_hint(t):
-    hit = _ROW_HINTS.pop(t.data_ptr(), None)
-    return hit[1] if hit is not None and hit[0] == t.size(0) else None
-
-
-class RowSparseGrad(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x):
-        return x.view_as(x)
-
-    @staticmethod
-    def backward(ctx, g):
-        g = _rowmajor(g)
-        _put_hint(g, row_nonzero_index_raw(g))
-        return g
-
-
-def row_sparse_grad(x):
-    return RowSparseGrad.apply(x)
-
-
 def colsum_raw(x, scale=1.0):
     lib = _lib.load()
     x = _rowmajor(x)
@@ -445,9 +410,10 @@ class SpMM(torch.autograd.Function):
     cached transposed structure."""
 
     @staticmethod
-    def forward(ctx, x, bias, adj, reduce, relu, drop_p, seed):
+    def forward(ctx, x, bias, adj, reduce, relu, drop_p, seed, sparse_grad=False):
         st = structure_of(adj)
         mean = reduce == "mean"
+        ctx.sparse_grad = bool(sparse_grad)
         ctx.dense = st.dense_ok and GEMM_BACKEND != "ffma" and x.size(1) >= 32
         if ctx.dense:
             # small, dense-ish adjacency (graph.Structure.dense_ok): multiply it as a dense matrix on the
@@ -467,7 +433,6 @@ class SpMM(torch.autograd.Function):
     def backward(ctx, g):
         (out,) = ctx.saved_tensors
         g = _rowmajor(g)
-        hint = _take_hint(g)
         if out is not None:
             g = relu_drop_bwd_raw(out, g, 1.0 / (1.0 - ctx.drop_p))      # zero rows stay zero rows
         gb = colsum_raw(g) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
@@ -476,20 +441,28 @@ class SpMM(torch.autograd.Function):
             if ctx.dense:
                 gx = gemm_raw(ctx.st.dense(ctx.mean), g, transa=True)          # A^T g on the tensor cores
             else:
+                # sparse_grad (set by the layer in forward): the caller reads this conv's output only at the
+                # endpoint rows of the edge batch, so most rows of g are exactly zero.  The index of the live
+                # rows is measured HERE, on this node's own incoming gradient (one pass over g) -- never
+                # handed between autograd nodes, whose gradient buffers autograd may accumulate into in place.
+                x_index = row_nonzero_index_raw(g) if ctx.sparse_grad else None
                 plan = ctx.st.bwd_mean if ctx.mean else ctx.st.bwd
                 gx = spmm_raw(plan, g, use_val=True if ctx.mean else ctx.st.has_value, div_rows=False,
-                              x_index=hint)
-        return gx, gb, None, None, None, None, None
+                              x_index=x_index)
+        return gx, gb, None, None, None, None, None, None
 
 
-def spmm(adj, x, reduce="sum", bias=None, relu=False, drop_p=0.0, seed=0):
+def spmm(adj, x, reduce="sum", bias=None, relu=False, drop_p=0.0, seed=0, sparse_grad=False):
+    """``sparse_grad``: the gradient arriving at the output will be non-zero only at a few rows (the endpoint
+    rows of an edge batch); the backward then gathers only those (see SpMM.backward)."""
     if reduce == "add":
         reduce = "sum"
     if isinstance(adj, parallel.ShardedAdj):      # row-partitioned encoder (citation2-shape, SURVEY 8e)
-        return parallel.pspmm(adj, x, reduce, bias=bias, relu=relu, drop_p=drop_p, seed=seed)
+        return parallel.pspmm(adj, x, reduce, bias=bias, relu=relu, drop_p=drop_p, seed=seed,
+                              sparse_grad=sparse_grad)
     if reduce not in ("sum", "mean"):
         raise NotImplementedError(f"reduce={reduce!r}")
-    return SpMM.apply(x, bias, adj, reduce, bool(relu), float(drop_p), int(seed))
+    return SpMM.apply(x, bias, adj, reduce, bool(relu), float(drop_p), int(seed), bool(sparse_grad))
 
 
 class SpMMRows(torch.autograd.Function):
@@ -566,15 +539,12 @@ class FusedLinear(torch.autograd.Function):
         Y, n = saved[0], ctx.n
         xs, ws = saved[1:1 + n], saved[1 + n:]
         g = _rowmajor(g)
-        hint = _take_hint(g)
         if Y is not None:
             g = relu_drop_bwd_raw(Y, g, 1.0 / (1.0 - ctx.drop_p))
         gb = colsum_raw(g) if (ctx.has_bias and ctx.needs_input_grad[0]) else None
         gxs, gws = [], []
         for i in range(n):
             gx = gemm_raw(g, ws[i]) if ctx.needs_input_grad[5 + i] else None          # dX = dY @ W
-            if gx is not None and hint is not None:
-                _put_hint(gx, hint)                                                   # zero rows of dY -> zero rows of dX
             gw = gemm_raw(g, xs[i], transa=True) if ctx.needs_input_grad[5 + n + i] else None  # dW = dY^T @ X
             gxs.append(gx)
             gws.append(gw)
@@ -597,15 +567,17 @@ def aggregate_into(adj, x, out):
     return spmm_raw(st.fwd, x, use_val=st.has_value, div_rows=False, out=out)
 
 
-def aggregate_t(adj, g):
+def aggregate_t(adj, g, sparse_rows=False):
     """A^T @ g through the raw kernel; row-partitioned: the transposed product over all columns is
-    reduce-scattered to the owners of the rows"""
+    reduce-scattered to the owners of the rows.  ``sparse_rows``: most rows of g are exactly zero -- measure
+    which (one pass over g) and gather only the live ones."""
+    x_index = row_nonzero_index_raw(g) if sparse_rows else None
     if isinstance(adj, parallel.ShardedAdj):
         st = structure_of(adj.local)
-        full = spmm_raw(st.bwd, g, use_val=st.has_value, div_rows=False)
+        full = spmm_raw(st.bwd, g, use_val=st.has_value, div_rows=False, x_index=x_index)
         return parallel._reduce_scatter_rows(full, adj.blk, adj.group)
     st = structure_of(adj)
-    return spmm_raw(st.bwd, g, use_val=st.has_value, div_rows=False)
+    return spmm_raw(st.bwd, g, use_val=st.has_value, div_rows=False, x_index=x_index)
 
 
 class AggLinear(torch.autograd.Function):
@@ -619,7 +591,8 @@ class AggLinear(torch.autograd.Function):
     the live blocks are recomputed first.  Works on a row-partitioned adjacency too (``aggregate_into``)."""
 
     @staticmethod
-    def forward(ctx, W, bias, adj, buf, holder, offs, act, drop_p, seed, *xs):
+    def forward(ctx, W, bias, adj, buf, holder, offs, act, drop_p, seed, sparse_grad, *xs):
+        ctx.sparse_grad = bool(sparse_grad)
         for off, x in zip(offs, xs):
             aggregate_into(adj, x, buf[:, off:off + x.size(1)])
         holder["stamp"] = holder.get("stamp", 0) + 1
@@ -645,16 +618,17 @@ class AggLinear(torch.autograd.Function):
         gb = colsum_raw(g) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
         gxs = []
         for i, (off, x) in enumerate(zip(ctx.offs, xs)):
-            if not ctx.needs_input_grad[9 + i]:
+            if not ctx.needs_input_grad[10 + i]:
                 gxs.append(None)
                 continue
             gu = gemm_raw(g, W[:, off:off + x.size(1)])                                      # d(A x_i) = dY W_i
-            gxs.append(aggregate_t(ctx.adj, gu)[: x.size(0)])                                 # A^T .
-        return (gW, gb, None, None, None, None, None, None, None, *gxs)
+            gxs.append(aggregate_t(ctx.adj, gu, ctx.sparse_grad)[: x.size(0)])                # A^T .
+        return (gW, gb, None, None, None, None, None, None, None, None, *gxs)
 
 
-def agg_linear(adj, buf, holder, offs, xs, W, bias, act=ACT_NONE, drop_p=0.0, seed=0):
-    return AggLinear.apply(W, bias, adj, buf, holder, tuple(offs), int(act), float(drop_p), int(seed), *xs)
+def agg_linear(adj, buf, holder, offs, xs, W, bias, act=ACT_NONE, drop_p=0.0, seed=0, sparse_grad=False):
+    return AggLinear.apply(W, bias, adj, buf, holder, tuple(offs), int(act), float(drop_p), int(seed),
+                           bool(sparse_grad), *xs)
 
 
 class GatherHadamard(torch.autograd.Function):

@@ -27,11 +27,16 @@ def random_walk(row, col, start, walk_length, num_nodes=None, rand=None, rowptr=
         raise RuntimeError("plnlp_b200.augment runs on the GPU; there is no CPU path")
     lib = _lib.load()
     if rowptr is None:
-        n = int(num_nodes) if num_nodes is not None else int(torch.max(torch.stack([row.max(), col.max()]))) + 1
+        # torch_cluster sizes the graph from row, col AND start (main.py --walk_start_type=node passes
+        # arange(num_nodes): trailing isolated nodes are legal start points that simply stay where they are)
+        n = int(num_nodes) if num_nodes is not None else \
+            int(torch.max(torch.stack([row.max(), col.max(), start.max()]))) + 1
         rowptr = _rowptr_of(row, n)
     rowptr, col = rowptr.to(torch.int64).contiguous(), col.to(torch.int64).contiguous()
     start = start.to(torch.int64).contiguous()
     W = start.numel()
+    if W and (int(start.max()) >= rowptr.numel() - 1 or int(start.min()) < 0):
+        raise RuntimeError(f"random_walk: start node out of range for a graph of {rowptr.numel() - 1} nodes")
     walk = torch.empty(W, walk_length + 1, dtype=torch.int64, device=col.device)
     if rand is not None:
         rand = rand.to(torch.float32).contiguous()

@@ -300,6 +300,7 @@ class Structure:
             t_rowptr[1:] = torch.cumsum(torch.bincount(t_row, minlength=N), 0)
         t_val = None if val is None else val.to(torch.float32)[perm]
         self.bwd = build_plan(t_rowptr, t_col, t_val, N, M, chunk)
+        self.t_rowptr = t_rowptr                  # int64 row pointers of the transposed matrix (TransposedStructure)
         # mean backward: A^T D^-1 g  ->  transposed entries carry 1/max(deg_row,1) of their source row
         inv = 1.0 / torch.clamp(deg, min=1).to(torch.float32)
         self.bwd_mean = _share_plan(self.bwd, inv[t_col].contiguous())
@@ -338,6 +339,36 @@ class Structure:
         return self._dense[mean]
 
 
+class TransposedStructure:
+    """``Structure`` of A^T as a VIEW of the structure of A: forward and backward plans swapped, nothing copied.
+    Used by the row-partitioned encoder: the COLUMN block A[:, block] a rank multiplies its own activation rows
+    with is the transpose of the row block of A^T it already holds (``parallel.ShardedAdj.local_t``).
+    'sum' products only (the mean divisor of the transposed matrix is not kept)."""
+
+    def __init__(self, st):
+        if st.symmetric:
+            raise RuntimeError("a symmetric structure shares its index arrays: use it directly")
+        self.base = st
+        self.n_rows, self.n_cols = st.n_cols, st.n_rows
+        self.has_value = st.has_value
+        self.fwd, self.bwd = st.bwd, st.fwd
+        self.fwd_noval = st.bwd if st.bwd.val is None else _share_plan(st.bwd, None)
+        self.bwd_mean = None
+        self.rowptr, self.t_rowptr = st.t_rowptr, st.rowptr
+        self.symmetric, self.dense_ok, self.density = False, False, st.density
+
+
+class TransposedAdj:
+    """adjacency handle whose ``structure_of`` is the transposed view of ``base``'s (no data of its own)"""
+
+    def __init__(self, base):
+        self.base = base
+        self._plnlp_structure = None
+
+    def size(self, dim):
+        return self.base.size(1 - dim)
+
+
 def _share_plan(plan, val):
     q = SpmmPlan()
     for s in SpmmPlan.__slots__:
@@ -351,6 +382,10 @@ _CACHE = {}
 
 def structure_of(adj):
     """Cached ``Structure`` of an adjacency object (CSRGraph or torch_sparse.SparseTensor)."""
+    if isinstance(adj, TransposedAdj):
+        if adj._plnlp_structure is None:
+            adj._plnlp_structure = TransposedStructure(structure_of(adj.base))
+        return adj._plnlp_structure
     key = id(adj)
     hit = _CACHE.get(key)
     if hit is not None and hit[0] is adj:

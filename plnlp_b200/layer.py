@@ -139,10 +139,10 @@ class SAGEConv(torch.nn.Module):
         self.lin_l.reset_parameters()
         self.lin_r.reset_parameters()
 
-    def forward(self, x, adj_t, act=_ops.ACT_NONE, drop_p=0.0):
+    def forward(self, x, adj_t, act=_ops.ACT_NONE, drop_p=0.0, sparse_grad=False):
         parts = _as_parts(x)
-        aggs = [_const_aggregate(adj_t, p, "mean") if _is_const(p) else _ops.spmm(adj_t, p, reduce="mean")
-                for p in parts]
+        aggs = [_const_aggregate(adj_t, p, "mean") if _is_const(p)
+                else _ops.spmm(adj_t, p, reduce="mean", sparse_grad=sparse_grad) for p in parts]
         wl, wr = _split_cols(self.lin_l.weight, parts), _split_cols(self.lin_r.weight, parts)
         return _ops.fused_linear(aggs + parts, wl + wr, self.lin_l.bias, act, drop_p,
                                  _ops.new_seed() if drop_p > 0 else 0)
@@ -164,10 +164,10 @@ class GraphConv(torch.nn.Module):
         self.lin_rel.reset_parameters()
         self.lin_root.reset_parameters()
 
-    def forward(self, x, adj_t, act=_ops.ACT_NONE, drop_p=0.0):
+    def forward(self, x, adj_t, act=_ops.ACT_NONE, drop_p=0.0, sparse_grad=False):
         parts = _as_parts(x)
-        aggs = [_const_aggregate(adj_t, p, "sum") if _is_const(p) else _ops.spmm(adj_t, p, reduce="sum")
-                for p in parts]
+        aggs = [_const_aggregate(adj_t, p, "sum") if _is_const(p)
+                else _ops.spmm(adj_t, p, reduce="sum", sparse_grad=sparse_grad) for p in parts]
         wl, wr = _split_cols(self.lin_rel.weight, parts), _split_cols(self.lin_root.weight, parts)
         return _ops.fused_linear(aggs + parts, wl + wr, self.lin_rel.bias, act, drop_p,
                                  _ops.new_seed() if drop_p > 0 else 0)
@@ -193,14 +193,14 @@ class GCNConv(torch.nn.Module):
 
     def can_restrict(self, x, adj_t):
         """whether ``forward(..., out_rows=)`` can compute just those output rows: a sparse adjacency (the dense
-        tensor-core path computes every row); on a row-partitioned adjacency only when
-        ``parallel.RESTRICT_LAST`` is on (``out_rows`` are then LOCAL row ids of this rank's block)"""
+        tensor-core path computes every row).  On a row-partitioned adjacency ``out_rows`` are GLOBAL row ids, the
+        same list on every rank, and every rank returns all of those rows (``parallel.pspmm_rows``)."""
         from . import parallel
         if isinstance(adj_t, parallel.ShardedAdj):
             return parallel.RESTRICT_LAST and not _ops.structure_of(adj_t.local).dense_ok
         return not _ops.structure_of(adj_t).dense_ok
 
-    def forward(self, x, adj_t, act=_ops.ACT_NONE, drop_p=0.0, out_rows=None):
+    def forward(self, x, adj_t, act=_ops.ACT_NONE, drop_p=0.0, out_rows=None, sparse_grad=False):
         parts = _as_parts(x)
         ws = _split_cols(self.lin.weight, parts)
         seed = _ops.new_seed() if drop_p > 0 else 0
@@ -224,13 +224,14 @@ class GCNConv(torch.nn.Module):
             # reference's order by a few ulp (inside the 1e-5 bar, tests/test_gpu_model.py).
             if _agg_buffer_ok(adj_t, parts):
                 buf, holder, offs, xs = _agg_buffer(adj_t, parts)
-                return _ops.agg_linear(adj_t, buf, holder, offs, xs, self.lin.weight, self.bias, act, drop_p, seed)
-            aggs = [_const_aggregate(adj_t, p, "sum") if _is_const(p) else _ops.spmm(adj_t, p, reduce="sum")
-                    for p in parts]
+                return _ops.agg_linear(adj_t, buf, holder, offs, xs, self.lin.weight, self.bias, act, drop_p, seed,
+                                       sparse_grad=sparse_grad)
+            aggs = [_const_aggregate(adj_t, p, "sum") if _is_const(p)
+                    else _ops.spmm(adj_t, p, reduce="sum", sparse_grad=sparse_grad) for p in parts]
             return _ops.fused_linear(aggs, ws, self.bias, act, drop_p, seed)
         z = _ops.fused_linear(parts, ws)
         return _ops.spmm(adj_t, z, reduce="sum", bias=self.bias, relu=(act == _ops.ACT_RELU),
-                         drop_p=drop_p, seed=seed)
+                         drop_p=drop_p, seed=seed, sparse_grad=sparse_grad)
 
 
 class TransformerConv(torch.nn.Module):
@@ -258,7 +259,7 @@ class TransformerConv(torch.nn.Module):
         for lin in (self.lin_key, self.lin_query, self.lin_value, self.lin_skip):
             lin.reset_parameters()
 
-    def forward(self, x, adj_t, act=_ops.ACT_NONE, drop_p=0.0):
+    def forward(self, x, adj_t, act=_ops.ACT_NONE, drop_p=0.0, sparse_grad=False):
         from . import parallel
         if isinstance(adj_t, parallel.ShardedAdj):
             raise NotImplementedError("TransformerConv on a row-partitioned adjacency")
@@ -287,10 +288,12 @@ class BaseGNN(torch.nn.Module):
         for conv in self.convs:
             conv.reset_parameters()
 
-    def forward(self, x, adj_t, out_rows=None):
+    def forward(self, x, adj_t, out_rows=None, sparse_grad=False):
         """``out_rows`` (extension; sorted distinct node ids): the caller only reads these rows of the output.
         Returns ``(h, restricted)``: when the last conv can restrict itself, h is the compact [len(out_rows), H]
-        matrix of just those rows (restricted = True), otherwise the full output (restricted = False)."""
+        matrix of just those rows (restricted = True), otherwise the full output (restricted = False) -- and
+        the last conv is then told (``sparse_grad``) that its output gradient will be zero outside a few rows,
+        so its backward measures and skips them."""
         p = self.dropout if self.training else 0.0
         last = len(self.convs) - 1
         restricted = False
@@ -299,6 +302,8 @@ class BaseGNN(torch.nn.Module):
             kw = {}
             if i == last and out_rows is not None and getattr(conv, "can_restrict", None) and conv.can_restrict(x, adj_t):
                 kw["out_rows"], restricted = out_rows, True
+            elif i == last and (sparse_grad or out_rows is not None):
+                kw["sparse_grad"] = True
             x = conv(x, adj_t, act=_ops.ACT_RELU if fused else _ops.ACT_NONE, drop_p=p if fused else 0.0, **kw)
         return x if out_rows is None else (x, restricted)
 

@@ -133,35 +133,32 @@ class BaseModel(object):
         self.optimizer.zero_grad(set_to_none=True)
         # Scoring reads h only at the endpoint rows of the batch, and d loss / d h is non-zero only there.  When
         # those are a small part of the node set (citation2-shape: ~10 %) the last conv computes just those
-        # rows (compact h, edges renumbered) and its backward gathers just their gradient rows; where the
-        # layer cannot restrict itself (row-partitioned run) only the backward skips the all-zero rows.
-        touched = 2 * (pos_edge.size(0) + neg_edge.size(0)) * max(self.world_size if self.partitioned else 1, 1)
-        sparse_rows = ROW_SPARSE_GRAD and touched < 0.5 * self.num_nodes
-        restrict_part = False
+        # rows (compact h, edges renumbered) and its backward gathers just their gradient rows; a conv that cannot
+        # restrict itself is told that its output gradient is row-sparse (``sparse_grad``) and skips the zero rows
+        # in its backward.
+        n_touch = 2 * (pos_edge.size(0) + neg_edge.size(0)) * (self.world_size if self.partitioned else 1)
+        sparse_rows = ROW_SPARSE_GRAD and n_touch < 0.5 * self.num_nodes
+        restricted = False
         if self.partitioned:
             from . import parallel
-            restrict_part = sparse_rows and parallel.RESTRICT_LAST and parallel.EXCHANGE == "rows"
         if sparse_rows and not self.partitioned:
             ids, inv = torch.unique(torch.cat([pos_edge, neg_edge], 0), return_inverse=True)
             h, restricted = self.encoder(self.input_parts(data), data.adj_t, out_rows=ids)
             if restricted:
                 pos_edge, neg_edge = inv[:pos_edge.size(0)], inv[pos_edge.size(0):]
-            else:
-                h = _ops.row_sparse_grad(h)
-        elif restrict_part:
-            # row-partitioned run, requests first (parallel.exchange_row_requests): every owner learns which of its
-            # rows any rank's batch reads, computes the last conv for exactly those and serves them
-            ids, inv = torch.unique(torch.cat([pos_edge, neg_edge], 0), return_inverse=True)
-            req = parallel.exchange_row_requests(ids, data.adj_t.blk, data.adj_t.group)
-            rows_local, where = torch.unique(req.want, return_inverse=True)
-            h, restricted = self.encoder(self.input_parts(data), data.adj_t, out_rows=rows_local)
-            h = parallel.serve_rows(h, where if restricted else req.want, req, data.adj_t.group)
-            pos_edge, neg_edge = inv[:pos_edge.size(0)], inv[pos_edge.size(0):]
+        elif sparse_rows and parallel.RESTRICT_LAST:
+            # row-partitioned run: the union of every rank's endpoint rows (the same sorted list everywhere) is
+            # what the last conv computes -- as partial products over each rank's column block, summed by one
+            # all-reduce (parallel.pspmm_rows) -- so every rank holds the compact h of ALL batches and scores its own
+            mine = torch.cat([pos_edge, neg_edge], 0)
+            ids = parallel.union_ids(mine.reshape(-1), data.adj_t.group)
+            h, restricted = self.encoder(self.input_parts(data), data.adj_t, out_rows=ids)
+            if restricted:
+                inv = torch.searchsorted(ids, mine)
+                pos_edge, neg_edge = inv[:pos_edge.size(0)], inv[pos_edge.size(0):]
         else:
-            h = self.encoder(self.input_parts(data), data.adj_t)
-            if sparse_rows:
-                h = _ops.row_sparse_grad(h)
-        if self.partitioned and not restrict_part:
+            h = self.encoder(self.input_parts(data), data.adj_t, sparse_grad=sparse_rows)
+        if self.partitioned and not restricted:
             # row-partitioned encoder: h is this rank's row block and scoring needs arbitrary
             # endpoints.  Fetch just the distinct endpoint rows of this rank's batch from their owners
             # (parallel.FetchRows; gradients return the same way) and score on that compact table.
@@ -205,7 +202,17 @@ class BaseModel(object):
             # the reduce-scatter of the gathers (owner computes) -> no all-reduce
             own = {id(p) for p in self.emb.parameters()}
             params = [p for p in params if id(p) not in own]
-        parallel.allreduce_grads(params)
+        # AUC-family losses are SUMS over pairs (loss.py:8,14,21,28,35,42): the summed gradient is the gradient of
+        # the global batch.  CE / LogRank / InfoNCE are MEANS (loss.py:48,52-53,62): average over ranks, so the
+        # step (and what the clip sees) does not depend on the number of GPUs.
+        parallel.allreduce_grads(params, average=self._loss_is_mean())
+        if self._loss_is_mean() and self.partitioned and self.emb is not None:
+            for p in self.emb.parameters():
+                if p.grad is not None:
+                    p.grad.div_(self.world_size)
+
+    def _loss_is_mean(self):
+        return self.loss_func_name in ('CE', 'InfoNCE', 'LogRank')
 
     def train(self, data, split_edge, batch_size, neg_sampler_name, num_neg, perms=None, neg_edges=None,
               max_batches=None):
@@ -251,7 +258,15 @@ class BaseModel(object):
             total_loss += loss.double() * perm.numel()
             total_examples += perm.numel()
         self.last_epoch_stats = {'batches': it + 1 if total_examples else 0, 'examples': total_examples}
-        return (total_loss / max(total_examples, 1)).item()   # the one host sync of the epoch
+        value = total_loss / max(total_examples, 1)
+        if self.world_size > 1:
+            # every rank scored 1/R of each batch: the global-batch value of model.py:169-173 is the SUM of the
+            # ranks' values for the sum-type losses and their average for the mean-type ones
+            import torch.distributed as dist
+            dist.all_reduce(value)
+            if self._loss_is_mean():
+                value = value / self.world_size
+        return value.item()   # the one host sync of the epoch
 
     def _train_pos(self, split_edge):
         tr = split_edge['train']
@@ -272,6 +287,11 @@ class BaseModel(object):
     def encode_for_test(self, data):
         """model.py:189-194: eval-mode encoding plus the mean row that index -1 resolves to."""
         h = self.encoder(self.input_parts(data), data.adj_t)
+        if self.partitioned:
+            # row-partitioned encoder: every rank evaluates against the whole matrix (all-gather of the blocks,
+            # padding rows dropped) -- scoring and ranking are then the single-GPU code
+            from . import parallel
+            h = parallel.all_gather_rows(h.contiguous(), data.adj_t.group)[: data.adj_t.n_global]
         mean_h = _ops.colsum_raw(h, 1.0 / h.size(0)).reshape(1, -1)
         return torch.cat([h, mean_h], dim=0)
 

@@ -27,10 +27,9 @@ import torch.distributed as dist
 # how the scoring step of the row-partitioned model gets its endpoint embeddings: "rows" = only the distinct
 # endpoint rows of the batch, by all_to_all (FetchRows); "allgather" = the whole matrix
 EXCHANGE = os.environ.get("PLNLP_EXCHANGE", "rows")
-# row-partitioned run: exchange the row requests BEFORE the last conv and let every owner compute only the rows
-# that were requested (DESIGN.md 4a item 3 for the partitioned encoder).  Bookkeeping verified on CPU (gloo,
-# tests/test_parallel_cpu.py); OFF by default until it has been through the 2-rank NCCL parity test on GPUs.
-RESTRICT_LAST = os.environ.get("PLNLP_PARTITIONED_RESTRICT", "0") == "1"
+# row-partitioned run: the last conv computes only the rows some rank's edge batch reads (DESIGN.md 4a item 3 for
+# the partitioned encoder, ``pspmm_rows``).  PLNLP_PARTITIONED_RESTRICT=0 switches it off.
+RESTRICT_LAST = os.environ.get("PLNLP_PARTITIONED_RESTRICT", "1") != "0"
 
 
 def world():
@@ -50,9 +49,10 @@ def row_block(n, rank, world_size):
     return lo, min(lo + blk, n)
 
 
-def allreduce_grads(params, group=None):
-    """sum the gradients of ``params`` over ranks with ONE flat all-reduce (weak-scaling edge batches:
-    the loss is a sum over pairs, so the summed gradient is the gradient of the global batch)."""
+def allreduce_grads(params, group=None, average=False):
+    """sum (``average``: mean) the gradients of ``params`` over ranks with ONE flat all-reduce.  Data-parallel
+    edge batches: for a loss that is a SUM over pairs the summed gradient is the gradient of the global batch;
+    for a MEAN loss (CE / LogRank / InfoNCE) it is the average."""
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
         return
@@ -60,6 +60,8 @@ def allreduce_grads(params, group=None):
     from . import profiling
     with profiling.span("nccl all_reduce (grads)", flat.numel() * 4, 0):
         dist.all_reduce(flat, group=group)
+    if average:
+        flat.div_(dist.get_world_size(group))
     off = 0
     for g in grads:
         g.copy_(flat[off:off + g.numel()].view_as(g))
@@ -168,96 +170,110 @@ def fetch_rows(h_local, ids, group=None, gather_fn=None, scatter_fn=None):
     return FetchRows.apply(h_local, ids, group, gather_fn, scatter_fn)
 
 
-class RowRequests:
-    """result of ``exchange_row_requests``: ``want`` = the local row ids other ranks (and this one) asked THIS
-    rank for, concatenated in requester order; the split sizes of the exchange in both directions"""
-
-    def __init__(self, want, send_split, recv_split, n_ids):
-        self.want, self.send_split, self.recv_split, self.n_ids = want, send_split, recv_split, n_ids
-
-
-def exchange_row_requests(ids, blk, group=None):
-    """phase 1 of the endpoint-row exchange on its own: every rank sends the sorted distinct global row ids it
-    needs to their owners.  Knowing ``want`` BEFORE the last conv runs lets the owner compute only the requested
-    rows (``pspmm_rows``) and then serve them (``serve_rows``).  One host read (the split sizes)."""
-    _, ws = world()
-    dev = ids.device
-    bounds = torch.arange(ws + 1, device=dev, dtype=ids.dtype) * blk
-    cut = torch.searchsorted(ids, bounds)
-    send_cnt = (cut[1:] - cut[:-1]).to(torch.int64)
-    recv_cnt = torch.empty_like(send_cnt)
-    dist.all_to_all_single(recv_cnt, send_cnt, group=group)
-    both = torch.stack([send_cnt, recv_cnt]).tolist()
-    send_split, recv_split = both[0], both[1]
-    owner = torch.repeat_interleave(torch.arange(ws, device=dev, dtype=ids.dtype), send_cnt, output_size=ids.numel())
-    want = torch.empty(sum(recv_split), dtype=ids.dtype, device=dev)
-    dist.all_to_all_single(want, ids - owner * blk, recv_split, send_split, group=group)
-    return RowRequests(want, send_split, recv_split, ids.numel())
-
-
-class ServeRows(torch.autograd.Function):
-    """phase 2: ``rows[i] = src[pos[j]]`` for every request j this rank received, delivered to the requester.
-    ``src`` is whatever table the owner holds the requested rows in -- its whole block (pos = want) or the compact
-    output of a row-restricted last conv (pos = position of want in the sorted distinct requested rows).
-    Backward: gradient rows return to the owner and are summed into ``src``'s rows in a fixed order."""
+class AllReduceSum(torch.autograd.Function):
+    """y = sum over ranks of x (every rank gets y).  Used where every rank holds a PARTIAL value of a replicated
+    quantity and then continues with its own share of the loss: the total loss is the sum of the ranks' losses,
+    so d loss / d x on every rank is the sum of the ranks' gradients w.r.t. y -- the backward is an all-reduce
+    too."""
 
     @staticmethod
-    def forward(ctx, src, pos, req, group, gather_fn, scatter_fn):
-        rank, _ = world()
-        served = gather_fn(src, pos)
-        rows = torch.empty(req.n_ids, src.size(1), dtype=src.dtype, device=src.device)
+    def forward(ctx, x, group):
+        ctx.group = group
+        y = x.contiguous()
+        if y.data_ptr() == x.data_ptr():
+            ctx.mark_dirty(x)
         from . import profiling
-        with profiling.span("nccl all_to_all (endpoint rows)", (req.n_ids - req.send_split[rank]) * src.size(1) * 4, 0):
-            dist.all_to_all_single(rows, served, req.send_split, req.recv_split, group=group)
-        ctx.group, ctx.n_src, ctx.scatter_fn, ctx.req = group, src.size(0), scatter_fn, req
-        ctx.save_for_backward(pos)
-        return rows
+        _, ws = world()
+        with profiling.span("nccl all_reduce (restricted rows)", 2 * (ws - 1) * y.numel() * 4 // max(ws, 1), 0):
+            dist.all_reduce(y, group=group)
+        return y
 
     @staticmethod
     def backward(ctx, g):
-        (pos,) = ctx.saved_tensors
-        req = ctx.req
-        rank, _ = world()
-        back = torch.empty(pos.numel(), g.size(1), dtype=g.dtype, device=g.device)
+        g = g.contiguous().clone()
         from . import profiling
-        with profiling.span("nccl all_to_all (endpoint row grads)", (g.size(0) - req.send_split[rank]) * g.size(1) * 4, 0):
-            dist.all_to_all_single(back, g.contiguous(), req.recv_split, req.send_split, group=ctx.group)
-        return ctx.scatter_fn(back, pos, ctx.n_src), None, None, None, None, None
+        _, ws = world()
+        with profiling.span("nccl all_reduce (restricted row grads)", 2 * (ws - 1) * g.numel() * 4 // max(ws, 1), 0):
+            dist.all_reduce(g, group=ctx.group)
+        return g, None
 
 
-def serve_rows(src, pos, req, group=None, gather_fn=None, scatter_fn=None):
-    if gather_fn is None or scatter_fn is None:
-        from . import _ops
-        gather_fn = gather_fn or _ops.gather_rows_idx_raw
-        scatter_fn = scatter_fn or _ops.row_scatter_raw
-    return ServeRows.apply(src, pos, req, group, gather_fn, scatter_fn)
+def all_reduce_sum(x, group=None):
+    return AllReduceSum.apply(x, group)
+
+
+def union_ids(ids_local, group=None):
+    """sorted distinct union over ranks of every rank's id list (all ranks must pass the same count -- the
+    data-parallel edge batches have equal sizes) -> the same tensor on every rank.  One all-gather of the raw ids;
+    ``torch.unique`` is the one host read (the size of the union)."""
+    _, ws = world()
+    ids_local = ids_local.contiguous()
+    if ws == 1:
+        return torch.unique(ids_local)
+    allv = torch.empty(ws * ids_local.numel(), dtype=ids_local.dtype, device=ids_local.device)
+    dist.all_gather_into_tensor(allv, ids_local, group=group)
+    return torch.unique(allv)
 
 
 class ShardedAdj:
-    """Rows ``[lo, hi)`` of an adjacency, columns in the padded global index space ``[0, R*blk)``."""
+    """Rows ``[lo, hi)`` of an adjacency A, columns in the padded global index space ``[0, R*blk)`` (``local``),
+    plus the same rows of A^T (``local_t``; the SAME object when A is symmetric, as every prepared OGB graph
+    is).  ``cols()`` is the COLUMN block A[:, lo:hi] = local_t^T as a transposed view."""
 
-    def __init__(self, local_adj, n_global, rank, world_size, group=None):
+    def __init__(self, local_adj, n_global, rank, world_size, group=None, local_t=None):
         self.local = local_adj                  # CSRGraph-like, shape [blk, R*blk]
+        self.local_t = local_t if local_t is not None else local_adj
         self.n_global, self.rank, self.world_size, self.group = n_global, rank, world_size, group
         self.blk = block_size(n_global, world_size)
+        self._cols = None
 
     def size(self, dim):
         return self.local.size(dim)
 
+    def cols(self):
+        if self._cols is None:
+            from .graph import TransposedAdj
+            self._cols = TransposedAdj(self.local_t)
+        return self._cols
 
-def shard_graph(adj, rank, world_size, graph_cls, group=None):
-    """slice a full adjacency (``csr()`` / ``size()``) into this rank's ``ShardedAdj``.  Index work only;
-    entries keep their order, so every local row is bit-identical to the corresponding global row."""
-    rowptr, col, val = adj.csr()
-    n = adj.size(0)
+
+def _row_slice(rowptr, col, val, n, rank, world_size, graph_cls):
     blk = block_size(n, world_size)
     lo, hi = row_block(n, rank, world_size)
     e0, e1 = int(rowptr[lo]), int(rowptr[hi])
     lptr = torch.full((blk + 1,), e1 - e0, dtype=torch.int64, device=rowptr.device)
     lptr[: hi - lo + 1] = rowptr[lo:hi + 1] - e0
-    local = graph_cls(lptr, col[e0:e1].clone(), None if val is None else val[e0:e1].clone(),
-                      (blk, blk * world_size))
-    return ShardedAdj(local, n, rank, world_size, group)
+    return graph_cls(lptr, col[e0:e1].clone(), None if val is None else val[e0:e1].clone(),
+                     (blk, blk * world_size))
+
+
+def transpose_csr(rowptr, col, val, n):
+    """CSR arrays of A^T for a square [n, n] CSR matrix (entries of a column keep their row order)"""
+    deg = rowptr[1:] - rowptr[:-1]
+    row = torch.repeat_interleave(torch.arange(n, device=col.device), deg, output_size=col.numel())
+    perm = torch.argsort(col * n + row, stable=True)
+    t_rowptr = torch.zeros(n + 1, dtype=torch.int64, device=col.device)
+    if col.numel():
+        t_rowptr[1:] = torch.cumsum(torch.bincount(col, minlength=n), 0)
+    return t_rowptr, row[perm], None if val is None else val[perm], perm
+
+
+def shard_graph(adj, rank, world_size, graph_cls, group=None, symmetric=None):
+    """slice a full adjacency (``csr()`` / ``size()``) into this rank's ``ShardedAdj``.  Index work only;
+    entries keep their order, so every local row is bit-identical to the corresponding global row.
+    ``symmetric`` (None = check): A == A^T, entry for entry -- then the row block doubles as the row block of A^T."""
+    rowptr, col, val = adj.csr()
+    n = adj.size(0)
+    local = _row_slice(rowptr, col, val, n, rank, world_size, graph_cls)
+    local_t = None
+    if symmetric is not True and adj.size(0) == adj.size(1):
+        t_rowptr, t_col, t_val, _ = transpose_csr(rowptr, col, val, n)
+        if symmetric is None:
+            symmetric = bool(torch.equal(t_rowptr, rowptr) and torch.equal(t_col, col)
+                             and (val is None or torch.equal(t_val, val)))
+        if not symmetric:
+            local_t = _row_slice(t_rowptr, t_col, t_val, n, rank, world_size, graph_cls)
+    return ShardedAdj(local, n, rank, world_size, group, local_t=local_t)
 
 
 def pad_rows(x, blk):
@@ -267,15 +283,25 @@ def pad_rows(x, blk):
     return torch.cat([x, pad], 0)
 
 
-def pspmm_rows(sadj, x_local, rows_local, reduce="sum", local_op=None):
-    """row-partitioned SpMM restricted to the output rows ``rows_local`` (local ids, sorted, distinct) of this
-    rank's block, written compactly: (A[lo:hi, :] @ all_gather(x_local))[rows_local].  ``local_op(adj, x, rows,
-    reduce)`` defaults to the CUDA row-subset SpMM (``_ops.spmm_rows``)."""
+def pspmm_rows(sadj, x_local, rows, reduce="sum", local_op=None):
+    """(A @ X)[rows] on a row-partitioned X, for GLOBAL row ids ``rows`` (sorted, distinct, the SAME list on every
+    rank -- ``union_ids``), returned in full, compactly, on every rank.
+
+    The last conv's output is read only at the endpoint rows of the edge batches.  Gathering the operand to the
+    rows (all-gather of X: 2.05 GB received per rank for citation2-shape's [N, 200] activations) would move ten
+    times more than the result is worth, so the product is formed the other way round: rank r multiplies the
+    COLUMN block it owns the operand rows of, ``A[rows, lo:hi] @ X[lo:hi]`` -- a row-subset SpMM on the transposed
+    view of its block of A^T -- and the [len(rows), F] partial results are summed over ranks (all-reduce:
+    ~0.23 GB).  Backward: all-reduce of the compact gradient, then ``A[rows, lo:hi]^T @ g`` with the compact
+    gradient as a row-sparse operand of the rank's own row block.  ``local_op(adj, x, rows, reduce)`` defaults to
+    the CUDA row-subset SpMM (``_ops.spmm_rows``)."""
+    if reduce not in ("sum", "add"):
+        raise NotImplementedError("row-restricted partitioned products are sums (GCNConv)")
     if local_op is None:
         from . import _ops
         local_op = _ops.spmm_rows
-    x_full = gather_rows(pad_rows(x_local, sadj.blk), sadj.group)
-    return local_op(sadj.local, x_full, rows_local, reduce)
+    partial = local_op(sadj.cols(), pad_rows(x_local, sadj.blk), rows, "sum")
+    return all_reduce_sum(partial, sadj.group)
 
 
 def pspmm(sadj, x_local, reduce="sum", local_op=None, **epilogue):

@@ -58,10 +58,12 @@ def hits_at_k(pos_pred, neg_pred, K):
 
 
 def mrr_list(pos_pred, neg_pred):
-    """per-row reciprocal rank; rank = 1 + #{neg > pos} (ties resolved optimistically; ogb 1.3.2's
-    argsort-based rank is implementation defined under exact ties)."""
-    gt, _ = _ops.mrr_counts_raw(pos_pred, neg_pred)
-    return 1.0 / (gt.to(torch.float32) + 1.0)
+    """per-row reciprocal rank.  Without ties rank = 1 + #{neg > pos}, which is what ogb 1.3.2's argsort gives.
+    Under exact ties (a collapsed model, relu outputs that are all zero) that argsort is implementation defined;
+    the rank used here is the mean of the optimistic and the pessimistic one, 1 + (#{neg > pos} + #{neg >= pos}) / 2
+    -- the rule of current ogb -- so a constant-score model reports MRR ~ 2/K, not 1."""
+    gt, ge = _ops.mrr_counts_raw(pos_pred, neg_pred)
+    return 1.0 / (0.5 * (gt.to(torch.float32) + ge.to(torch.float32)) + 1.0)
 
 
 def _cuda_f32(t):

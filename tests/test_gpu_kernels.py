@@ -80,7 +80,8 @@ def test_spmm_split_rows(ops, chunk):
 def test_spmm_row_sparse_operand_mask(ops, F, monkeypatch):
     """x_index < 0 skips the gathers of all-zero rows of x: identical bits to the dense kernel (the skipped terms are
     exact zeros, the surviving ones keep their CSR order), valued and value-less, hub rows included; and the
-    autograd hint path (row_sparse_grad -> SpMM.backward) gives the same gradient as the plain path"""
+    autograd path (spmm(..., sparse_grad=True): SpMM.backward measures the live rows of its own incoming gradient)
+    gives the same gradient as the plain path"""
     from plnlp_b200 import graph
     from plnlp_b200.graph import Structure
     monkeypatch.setattr(graph, "DENSE_SPMM", False)       # CSR kernels also for the autograd part below
@@ -110,13 +111,10 @@ def test_spmm_row_sparse_operand_mask(ops, F, monkeypatch):
     grads = []
     for hinted in (False, True):
         z = torch.randn(N, F, generator=torch.Generator().manual_seed(1)).cuda().requires_grad_(True)
-        y = ops.spmm(g, z, "sum", relu=True)
-        if hinted:
-            y = ops.row_sparse_grad(y)
+        y = ops.spmm(g, z, "sum", relu=True, sparse_grad=hinted)
         (y[idx] * wgt).sum().backward()
         grads.append(z.grad.clone())
     assert torch.equal(grads[0], grads[1])
-    assert not ops._ROW_HINTS                          # the hint was consumed
 
 
 @pytest.mark.parametrize("F", [3, 50, 200])
@@ -536,7 +534,13 @@ def test_mrr_counts(ops):
     gt, ge = ops.mrr_counts_raw(pos.cuda(), neg.cuda())
     ogt, oge = ogb_eval.mrr_ranks(pos, neg)
     assert torch.equal(gt.cpu().long() + 1, ogt) and torch.equal(ge.cpu().long() + 1, oge)
-    assert torch.equal(mrr_list(pos.cuda(), neg.cuda()).cpu(), 1.0 / ogt.float())
+    # ties: the mean of the optimistic and the pessimistic rank (current ogb), not the optimistic one
+    assert torch.equal(mrr_list(pos.cuda(), neg.cuda()).cpu(), 1.0 / (0.5 * (ogt + oge).float()))
+    pos2, neg2 = torch.randn(S, generator=g), torch.randn(S, K, generator=g)       # no ties: ogb 1.3.2's rank
+    o2, p2 = ogb_eval.mrr_ranks(pos2, neg2)
+    assert torch.equal(o2, p2) and torch.equal(mrr_list(pos2.cuda(), neg2.cuda()).cpu(), 1.0 / o2.float())
+    flat = torch.zeros(S)                                        # a collapsed model does not report MRR = 1
+    assert float(mrr_list(flat.cuda(), torch.zeros(S, K).cuda()).max()) < 0.01
 
 
 def test_eval_glue_against_reference_golden(ops, golden_dir):

@@ -103,13 +103,23 @@ def _setup_run(R):
 
 
 @pytest.mark.parametrize("tag", ["ddi_like", "collab_like", "citation_like", "hinge_like"])
-@pytest.mark.parametrize("scatter", ["sorted", "atomic"])
-def test_first_step_gradients_match_reference(golden_dir, tag, scatter):
+@pytest.mark.parametrize("scatter", ["sorted", "atomic", "sorted+sparse_rows"])
+def test_first_step_gradients_match_reference(golden_dir, tag, scatter, monkeypatch):
     """one step from the reference's initial state with its first shuffle + negatives: loss and every
-    parameter gradient against the oracle (itself pinned to the reference by tests/test_oracle.py)"""
+    parameter gradient against the oracle (itself pinned to the reference by tests/test_oracle.py).
+
+    ``+sparse_rows``: the model is told its node set is huge, so the batch counts as touching a small part of it
+    and the CSR kernels run the row-restricted last conv (GCN) or the full conv with a row-sparse backward
+    (SAGE: ddi_like is the 2-layer SAGE whose FIRST layer then receives a dense gradient through the root weight
+    plus A^T g -- the case a pointer-keyed sparsity hint got wrong in round 1)."""
     from plnlp_b200 import _ops
     R = torch.load(os.path.join(golden_dir, "train_runs.pt"))[tag]
     cfg, model, data = _setup_run(R)
+    if scatter.endswith("+sparse_rows"):
+        from plnlp_b200 import graph
+        monkeypatch.setattr(graph, "DENSE_SPMM", False)
+        model.num_nodes = 10 ** 9
+        scatter = "sorted"
     _ops.SCATTER_MODE = scatter
     try:
         pos = plnlp_ref.train_pos_edges(R["split"])
@@ -263,9 +273,6 @@ def test_wsage_against_reference_golden(golden_dir):
             graph.DENSE_SPMM = True
 
 
-@pytest.mark.xfail(strict=False, reason="round 1 ended with 0 GPU minutes: on the last run forward and d/dx matched at 1e-5 "
-                   "and the only failing tensor was lin_key.bias, whose exact gradient is 0 (see below); the floor "
-                   "criterion was added afterwards and could not be re-run.  Remove this mark after the next GPU run.")
 def test_transformer_against_reference_golden(golden_dir):
     """Transformer (layer.py:57-63; PyG TransformerConv = per-destination softmax attention): the reference's
     stacking over the restated conv, forward and every gradient, 1 and 2 layers.

@@ -5,6 +5,7 @@ the flat gradient all-reduce.  Parity target: the single-process result (SURVEY.
 import os
 import socket
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -138,52 +139,58 @@ def test_fetch_rows_exchange_gloo_ws3():
         assert torch.all(grad_local[hi - lo:] == 0)               # padding rows receive nothing
 
 
-def _restricted_worker(rank, world_size, port, N, F, ret):
+def _restricted_worker(rank, world_size, port, N, F, symmetric, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world_size)
     try:
-        ei, w = rand_graph(N, 500, seed=4, weighted=True, hub=True)
-        full = sparse.to_sparse_tensor(ei, w, N)
+        full = _restricted_graph(N, symmetric)
         g = torch.Generator().manual_seed(6)
         X = torch.randn(N, F, generator=g)
-        blk = parallel.block_size(N, world_size)
         lo, hi = parallel.row_block(N, rank, world_size)
         sadj = parallel.shard_graph(full, rank, world_size, _oracle_graph)
+        assert (sadj.local_t is sadj.local) == symmetric          # a symmetric matrix shares its row block
         x_local = X[lo:hi].clone().requires_grad_(True)
         gr = torch.Generator().manual_seed(200 + rank)
-        ids = torch.unique(torch.cat([torch.randint(0, N, (7 + 3 * rank,), generator=gr), torch.tensor([1, N - 1])]))
-        # requests first, then the owner computes only the requested rows of A @ X and serves them
-        req = parallel.exchange_row_requests(ids, blk)
-        rows_local, where = torch.unique(req.want, return_inverse=True)
-        assert rows_local.numel() <= req.want.numel() and int(rows_local.max()) < blk
-        h_c = parallel.pspmm_rows(sadj, x_local, rows_local, "sum",
-                                  local_op=lambda adj, x, rows, reduce: sparse.matmul(adj, x, reduce)[rows])
-        assert h_c.shape == (rows_local.numel(), F)
-        rows = parallel.serve_rows(h_c, where, req, gather_fn=lambda s, i: s[i],
-                                   scatter_fn=lambda gg, i, n: torch.zeros(n, gg.size(1)).index_add_(0, i, gg))
+        mine = torch.cat([torch.randint(0, N, (8,), generator=gr), torch.tensor([1, N - 1])])   # equal counts
+        ids = parallel.union_ids(mine)
+        # every rank multiplies the COLUMN block it owns the operand rows of; the partial rows are all-reduced
+        rows = parallel.pspmm_rows(
+            sadj, x_local, ids, "sum",
+            local_op=lambda adj, x, r, reduce: sparse.matmul(adj.base.t(), x, reduce)[r])
         want_rows = sparse.matmul(full, X, "sum")[ids]
-        assert rel_err(rows.detach(), want_rows) < 1e-6
-        gout = torch.randn(ids.numel(), F, generator=gr)
-        rows.backward(gout)
-        ret[rank] = (ids, gout, x_local.grad.clone(), lo, hi)
+        assert rows.shape == (ids.numel(), F) and rel_err(rows.detach(), want_rows) < 1e-6
+        # each rank's loss reads its own endpoints only
+        pos = torch.searchsorted(ids, mine)
+        gout = torch.randn(mine.numel(), F, generator=gr)
+        (rows[pos] * gout).sum().backward()
+        ret[rank] = (ids, mine, gout, x_local.grad.clone(), lo, hi)
     finally:
         dist.destroy_process_group()
 
 
-def test_requests_first_then_restricted_rows_gloo_ws3():
-    """the row-partitioned form of 'the last conv computes only the rows the batches read'
-    (parallel.exchange_row_requests -> pspmm_rows -> serve_rows, PLNLP_PARTITIONED_RESTRICT): every rank receives
-    exactly (A @ X)[ids], and the gradient w.r.t. every rank's block of X equals the single-process gradient"""
+def _restricted_graph(N, symmetric):
+    ei, w = rand_graph(N, 500, seed=4, weighted=True, hub=True)
+    if symmetric:       # the prepared citation2 graph: symmetrised, unit diagonal, D^-1/2 A D^-1/2 (bit-symmetric values)
+        return sparse.gcn_normalization(sparse.to_sparse_tensor(ei, None, N).to_symmetric())
+    return sparse.to_sparse_tensor(ei, w, N)
+
+
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_restricted_rows_column_block_products_gloo_ws3(symmetric):
+    """the row-partitioned form of 'the last conv computes only the rows the batches read' (parallel.union_ids ->
+    pspmm_rows): every rank ends up with exactly (A @ X)[ids] for the union of all ranks' endpoints, and the
+    gradient w.r.t. every rank's block of X equals the single-process gradient of the summed losses"""
     N, F, ws = 31, 4, 3
     port = _free_port()
     ret = mp.Manager().dict()
-    mp.spawn(_restricted_worker, args=(ws, port, N, F, ret), nprocs=ws, join=True)
-    ei, w = rand_graph(N, 500, seed=4, weighted=True, hub=True)
-    full = sparse.to_sparse_tensor(ei, w, N)
+    mp.spawn(_restricted_worker, args=(ws, port, N, F, symmetric, ret), nprocs=ws, join=True)
+    full = _restricted_graph(N, symmetric)
     X = torch.randn(N, F, generator=torch.Generator().manual_seed(6)).requires_grad_(True)
     Y = sparse.matmul(full, X, "sum")
-    total = sum((Y[ret[r][0]] * ret[r][1]).sum() for r in range(ws))
+    total = sum((Y[ret[r][1]] * ret[r][2]).sum() for r in range(ws))
     total.backward()
+    ids0 = ret[0][0]
     for r in range(ws):
-        _, _, grad_local, lo, hi = ret[r]
+        ids, _, _, grad_local, lo, hi = ret[r]
+        assert torch.equal(ids, ids0)                              # the same sorted union on every rank
         assert rel_err(grad_local, X.grad[lo:hi]) < 1e-5

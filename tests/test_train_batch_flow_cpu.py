@@ -1,5 +1,5 @@
 """CPU test (-m "not gpu") of BaseModel.train_batch's CONTROL FLOW with the kernels replaced by torch stand-ins:
-which branch runs (plain / row-restricted last conv / row-sparse hint), that edges are renumbered consistently
+which branch runs (plain / row-restricted last conv / full output with a row-sparse gradient), that edges are renumbered consistently
 with the compact table, and that the loss and gradients equal the plain path's.  The arithmetic itself is covered
 by the GPU parity tests; this pins the Python glue that sits between them."""
 import pytest
@@ -16,10 +16,10 @@ class _Enc(torch.nn.Module):
         self.w = torch.nn.Parameter(torch.randn(f, f) * 0.3)
         self.restrict, self.calls = restrict, []
 
-    def forward(self, x, adj_t, out_rows=None):
+    def forward(self, x, adj_t, out_rows=None, sparse_grad=False):
         h = torch.relu(x[0] @ self.w)
         if out_rows is None:
-            self.calls.append("full")
+            self.calls.append("full+sparse_grad" if sparse_grad else "full")
             return h
         self.calls.append("rows" if self.restrict else "full+flag")
         return (h[out_rows], True) if self.restrict else (h, False)
@@ -55,8 +55,6 @@ def test_train_batch_branches_agree(restrict, monkeypatch):
     torch.manual_seed(0)
     n, f, B, k = 200, 6, 8, 2
     monkeypatch.setattr(_ops, "edge_score_loss", _fake_edge_score_loss)
-    hints = []
-    monkeypatch.setattr(_ops, "row_sparse_grad", lambda h: (hints.append(1), h)[1])
 
     class D:
         adj_t, x, edge_index = None, None, None
@@ -75,7 +73,6 @@ def test_train_batch_branches_agree(restrict, monkeypatch):
         results.append((float(loss), [p.grad.clone() for p in m.para_list], enc_state, emb_state, list(m.encoder.calls)))
     (l0, g0, _, _, c0), (l1, g1, _, _, c1) = results
     assert c0 == ["full"] and c1 == (["rows"] if restrict else ["full+flag"])
-    assert len(hints) == (0 if restrict else 1)            # the hint is the fallback of a conv that cannot restrict
     assert abs(l0 - l1) <= 1e-5 * abs(l0)
     for a, b in zip(g0, g1):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
