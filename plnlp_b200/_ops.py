@@ -61,6 +61,14 @@ def _ld(t):
     return t.stride(0) if t.size(0) > 1 else max(t.size(1), t.stride(0))
 
 
+# SpMM operands of <= 64 columns whose rows sit on a 16-byte aligned pitch run on the two-rows-per-warp kernel
+# (csrc/spmm.cu, spmm_csr_narrow_kernel; the library picks it from the layout it is handed).  Measured on the
+# citation2-shape graph (profiles/r02_spmm_narrow_ab.txt): F = 64 53 % -> 71 % of the HBM copy peak, F = 32
+# 30 % -> 41 %.  A width that is not a multiple of 4 (the 50-wide embedding) is NOT re-pitched: at <= 256 B per
+# gathered row the kernel is bound by the rate of random DRAM row fetches (~17 G rows/s whatever the width
+# between 16 and 64 floats), the generic kernel already reaches it, and the copy would cost more than it gains.
+
+
 def new_seed():
     """64-bit Philox seed drawn from torch's CPU generator (reproducible under manual_seed,
     never touches the device)."""

@@ -254,6 +254,111 @@ __global__ void __launch_bounds__(256, (NB * U * VEC <= 8) ? 8 : (NB * U * VEC <
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Narrow rows (F <= 64 floats on a 16-byte aligned pitch): TWO work items per warp.
+//
+// With one warp per row a 50-wide row keeps 25 lanes busy with 8-byte loads and 800 B in flight per warp; the
+// kernel is latency bound (see above), so rows this short run at ~50 % of the HBM roof.  Here each half-warp owns
+// one item: 16 lanes x one 16-byte load cover a row of up to 64 floats (the last vector of a row whose width is not
+// a multiple of 4 reads pitch padding, which is never stored), NB neighbours per half are in flight, so a warp
+// keeps 2 x NB x 16 B x 16 lanes in flight with the same register footprint.  Accumulation order per output
+// element is still the CSR order of its row (bit-identical results).  Measured on the citation2-shape graph:
+// F = 64 5.07 -> 3.78 ms (53 % -> 71 % of the HBM copy peak), F = 32 4.63 -> 3.38 ms.  Below ~256 B per gathered
+// row the time no longer falls with the width (3.0 ms at F = 16): the bound is the rate of random DRAM row
+// fetches, not bytes.
+// ---------------------------------------------------------------------------------------------------------
+template <bool HAS_VAL, int NB>
+__global__ void __launch_bounds__(256, 8) spmm_csr_narrow_kernel(const SpmmParams p) {
+    const int lane = threadIdx.x & 31;
+    const int half = lane >> 4, hl = lane & 15;
+    const int64_t warp_id = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t item = warp_id * 2 + half;
+    const bool valid = item < p.n_items;
+    const int f = hl * 4;
+    const bool act = f < p.F;
+
+    int beg = 0, end = 0;
+    if (valid) {
+        beg = __ldg(p.item_ptr + item);
+        end = p.item_end ? __ldg(p.item_end + item) : __ldg(p.item_ptr + item + 1);
+    }
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const float* __restrict__ xb = p.x + f;
+    const int src0 = half << 4;                        // first lane of this half
+    for (int base = beg; __any_sync(0xffffffffu, base < end); base += 16) {
+        const int n = max(0, min(16, end - base));
+        int c = 0;
+        float v = 0.0f;
+        if (hl < n) {
+            c = __ldg(p.col + base + hl);
+            if (HAS_VAL) v = __ldg(p.val + base + hl);
+        }
+        const int n_other = __shfl_xor_sync(0xffffffffu, n, 16);
+        const int nmax = max(n, n_other);              // warp-uniform trip count
+#pragma unroll 1
+        for (int j = 0; j < nmax; j += NB) {
+            float t[NB][4];
+            float vv[NB];
+            bool ok[NB];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const int jj = j + b;
+                const int cj = __shfl_sync(0xffffffffu, c, src0 | (jj & 15));
+                vv[b] = HAS_VAL ? __shfl_sync(0xffffffffu, v, src0 | (jj & 15)) : 1.0f;
+                ok[b] = jj < n;
+                if (ok[b] && act) {
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(xb + static_cast<int64_t>(cj) * p.ldx));
+                    t[b][0] = q.x; t[b][1] = q.y; t[b][2] = q.z; t[b][3] = q.w;
+                } else {
+                    t[b][0] = t[b][1] = t[b][2] = t[b][3] = 0.0f;
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                if (ok[b]) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        acc[e] = HAS_VAL ? __fadd_rn(acc[e], __fmul_rn(vv[b], t[b][e])) : __fadd_rn(acc[e], t[b][e]);
+                }
+            }
+        }
+    }
+    if (!valid || !act) return;
+    const int row = __ldg(p.item_row + item);
+    const int slot = __ldg(p.item_slot + item);
+    const int live = min(4, p.F - f);                  // columns of this lane that exist
+    if (slot >= 0) {
+        float* dst = p.partial + static_cast<int64_t>(slot) * p.F + f;
+        for (int e = 0; e < live; ++e) dst[e] = acc[e];
+        return;
+    }
+    if (p.row_div) {
+        const float d = __ldg(p.row_div + row);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] = acc[e] / d;
+    }
+    if (p.bias) {
+        for (int e = 0; e < live; ++e) acc[e] += __ldg(p.bias + f + e);
+    }
+    if (p.relu) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] = fmaxf(acc[e], 0.0f);
+    }
+    if (p.drop_p > 0.0f) {
+        const float s = 1.0f / (1.0f - p.drop_p);
+        for (int e = 0; e < live; ++e) {
+            const uint64_t idx = static_cast<uint64_t>(row) * static_cast<uint64_t>(p.F) + (f + e);
+            acc[e] = dropout_keep(p.seed, idx, p.drop_p) ? acc[e] * s : 0.0f;
+        }
+    }
+    float* dst = p.out + static_cast<int64_t>(row) * p.ldo + f;
+    if (live == 4 && (p.ldo % 4 == 0) && (reinterpret_cast<uintptr_t>(p.out) % 16 == 0)) {
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else {
+        for (int e = 0; e < live; ++e) dst[e] = acc[e];
+    }
+}
+
 // second pass for split (hub) rows: sum the partial slots in slot order, then the epilogue
 template <typename T, int VEC, int U>
 __global__ void __launch_bounds__(256) spmm_fix_kernel(const SpmmParamsT<T> p) {
@@ -281,6 +386,41 @@ __global__ void __launch_bounds__(256) spmm_fix_kernel(const SpmmParamsT<T> p) {
 }
 
 template <typename T, int VEC, int U>
+static int launch_fix(const SpmmParamsT<T>& p, cudaStream_t st) {
+    if (p.n_fix > 0) {
+        const int per = 32 * VEC * U;
+        const dim3 grid(static_cast<unsigned>(ceil_div(p.n_fix, 8)), static_cast<unsigned>(ceil_div(p.F, per)));
+        spmm_fix_kernel<T, VEC, U><<<grid, 256, 0, st>>>(p);
+        PLNLP_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+// narrow rows: see spmm_csr_narrow_kernel.  PLNLP_SPMM_NARROW=0 switches the path off (tuning / A-B runs).
+static bool narrow_ok(const SpmmParams& p) {
+    static const bool on = [] { const char* e = getenv("PLNLP_SPMM_NARROW"); return !(e && e[0] == '0'); }();
+    return on && p.F <= 64 && p.x_index == nullptr && (p.ldx % 4 == 0) && p.ldx >= ((p.F + 3) / 4) * 4 &&
+           aligned(p.x, 16);
+}
+
+static int launch_narrow(const SpmmParams& p, cudaStream_t st) {
+    static const int nb_env = [] { const char* e = getenv("PLNLP_SPMM_NB"); return e ? atoi(e) : 0; }();
+    // two neighbours per half in flight: measured best (F = 64: 3.78 ms vs 3.86 at four; eight spills)
+    const int nb = nb_env ? nb_env : 2;
+    const dim3 grid(static_cast<unsigned>(ceil_div(ceil_div(p.n_items, 2), 8)));
+#define PLNLP_NARROW_LAUNCH(NBV)                                                          \
+    do {                                                                                  \
+        if (p.val) spmm_csr_narrow_kernel<true, NBV><<<grid, 256, 0, st>>>(p);            \
+        else       spmm_csr_narrow_kernel<false, NBV><<<grid, 256, 0, st>>>(p);           \
+    } while (0)
+    if (nb >= 4) PLNLP_NARROW_LAUNCH(4);
+    else PLNLP_NARROW_LAUNCH(2);
+#undef PLNLP_NARROW_LAUNCH
+    PLNLP_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename T, int VEC, int U>
 static int launch_spmm(const SpmmParamsT<T>& p, cudaStream_t st) {
     const int per = 32 * VEC * U;
     const unsigned slabs = static_cast<unsigned>(ceil_div(p.F, per));
@@ -305,12 +445,7 @@ static int launch_spmm(const SpmmParamsT<T>& p, cudaStream_t st) {
         PLNLP_LAUNCH_CHECK();
     }
 #undef PLNLP_SPMM_LAUNCH
-    if (p.n_fix > 0) {
-        const dim3 grid(static_cast<unsigned>(ceil_div(p.n_fix, 8)), slabs);
-        spmm_fix_kernel<T, VEC, U><<<grid, block, 0, st>>>(p);
-        PLNLP_LAUNCH_CHECK();
-    }
-    return 0;
+    return launch_fix<T, VEC, U>(p, st);
 }
 
 template <typename T, int VEC>
@@ -343,6 +478,16 @@ extern "C" int plnlp_spmm_csr_f32(const int32_t* item_ptr, const int32_t* item_r
                     (!partial || aligned(partial, 16));
     const bool v2 = (F % 2 == 0) && (ldx % 2 == 0) && (ldo % 2 == 0) && aligned(x, 8) && aligned(out, 8) &&
                     (!partial || aligned(partial, 8));
+    if (narrow_ok(p)) {
+        int rc = launch_narrow(p, st);
+        if (rc != 0) return rc;
+        // hub rows: the fixed-order combine of the partial slots (any vector width the partial buffer allows)
+        const bool f4 = (F % 4 == 0) && (ldo % 4 == 0) && aligned(out, 16) && (!partial || aligned(partial, 16));
+        const bool f2 = (F % 2 == 0) && (ldo % 2 == 0) && aligned(out, 8) && (!partial || aligned(partial, 8));
+        if (f4) return launch_fix<float, 4, 1>(p, st);
+        if (f2) return launch_fix<float, 2, 1>(p, st);
+        return launch_fix<float, 1, 2>(p, st);
+    }
     if (v4) return dispatch_u<float, 4>(p, st);
     if (v2) return dispatch_u<float, 2>(p, st);
     return dispatch_u<float, 1>(p, st);

@@ -60,6 +60,57 @@ def test_spmm_unsplit_rows_are_bit_exact(ops):
         assert torch.equal(got, cspmm.spmm(rowptr, col, val, x, reduce))
 
 
+@pytest.mark.parametrize("F", [1, 3, 17, 32, 50, 52, 63, 64])
+@pytest.mark.parametrize("layout", ["auto_pad", "pitch64", "slice_of_wide"])
+def test_spmm_narrow_rows_two_per_warp(ops, F, layout):
+    """operands of <= 64 columns run on the two-rows-per-warp kernel (16 lanes x 16-byte loads per row): rows that
+    fit one work item keep the bits of the in-order CPU loop (valued, value-less, mean), hub rows are combined in
+    fixed order, the epilogue (bias / relu / dropout) is the generic kernel's, and the output may be a column slice
+    of a wider buffer (the [A emb | A x] aggregate buffer of the GCN layer)"""
+    from plnlp_b200 import _lib
+    from plnlp_b200.graph import Structure
+    N = 333                                                   # odd item count: the last warp has one idle half
+    ei, w = rand_graph(N, 5000, seed=100 + F, weighted=True, hub=True)
+    gen = torch.Generator().manual_seed(F)
+    x = torch.randn(N, F, generator=gen)
+    if layout == "auto_pad":
+        xg = x.cuda()                                         # contiguous [N, F]: narrow kernel iff F % 4 == 0
+    elif layout == "pitch64":
+        xg = torch.full((N, 64), float("nan")).cuda()[:, :F]   # pitch padding is garbage and must never leak
+        xg.copy_(x)
+    else:
+        xg = torch.full((N, 136), float("nan")).cuda()[:, 8:8 + F]    # 32-byte column offset inside a wide matrix
+        xg.copy_(x)
+    for weights, reduce, chunk in ((w, "sum", 1024), (None, "mean", 1024), (None, "sum", 1024), (w, "sum", 64)):
+        o = sparse.to_sparse_tensor(ei, weights, N)
+        st = Structure(_to_gpu_graph(o), chunk=chunk)
+        rowptr, col, val = o.csr()
+        wide = torch.full((N, 96), -7.0).cuda()
+        out = wide[:, 5:5 + F]                                # unaligned column slice as the output
+        n0 = _lib.launch_count()
+        ops.spmm_raw(st.fwd, xg, use_val=weights is not None, div_rows=(reduce == "mean"), out=out)
+        assert _lib.launch_count() - n0 == (1 if st.fwd.n_fix == 0 else 2)
+        want = cspmm.spmm(rowptr, col, val, x, reduce)
+        if st.fwd.n_fix == 0:
+            assert torch.equal(out.cpu(), want)
+        else:
+            assert rel_err(out.cpu(), cspmm.spmm(rowptr, col, val, x, reduce, f64=True)) < TOL
+            fixed = st.fwd.fix_row.cpu().long()
+            keep = torch.ones(N, dtype=torch.bool)
+            keep[fixed] = False
+            assert torch.equal(out.cpu()[keep], want[keep])  # unsplit rows stay bit-exact next to split ones
+        assert torch.all(wide[:, :5] == -7.0) and torch.all(wide[:, 5 + F:] == -7.0)     # nothing outside the slice
+    # fused epilogue = the generic kernel's (same Philox indexing): compare with the wide kernel on the same plan
+    o = sparse.to_sparse_tensor(ei, w, N)
+    st = Structure(_to_gpu_graph(o), chunk=1024)
+    bias = torch.randn(F, generator=gen).cuda()
+    a = ops.spmm_raw(st.fwd, xg, use_val=True, div_rows=False, bias=bias, relu=True, drop_p=0.3, seed=99)
+    x1 = torch.zeros(N, F + 1).cuda()[:, :F]                 # odd pitch: the generic warp-per-row kernel
+    x1.copy_(x)
+    b = ops.spmm_raw(st.fwd, x1, use_val=True, div_rows=False, bias=bias, relu=True, drop_p=0.3, seed=99)
+    assert torch.equal(a, b) and not torch.isnan(a).any()
+
+
 @pytest.mark.parametrize("chunk", [32, 64])
 def test_spmm_split_rows(ops, chunk):
     from plnlp_b200.graph import Structure
