@@ -146,6 +146,20 @@ int plnlp_gemm_tf32_2cta(int passes, int transa, int transb, int64_t M, int64_t 
                          const float* aux, int64_t ldaux, float drop_p, uint64_t seed,
                          float* workspace, int64_t workspace_bytes, int split_k, void* stream);
 
+/* TMA-fed persistent variant for the TALL-SKINNY dense layers of the full-graph encoder (csrc/gemm_tma.cu;
+ * layer.py:20,23 at citation2 shape: 2.9 M x 200 x 178, 2.9 M x 50 x 200): A tiles arrive by cp.async.bulk.tensor
+ * (128-byte swizzle) into a deep ring, the weight is split once per call into tf32 hi / lo copies in the caller's
+ * workspace (plnlp_gemm_tf32_tma_workspace_bytes) and TMA-loaded as well, the TMEM accumulator is double buffered
+ * so the epilogue of one tile overlaps the main loop of the next.  A is [M, K] row-major (lda % 4 == 0, 16-byte
+ * aligned); transb = 1: B is [N, K] (y = x W^T), transb = 0: B is [K, N] (dX = dY W).  32 <= K, N <= 512, no split-k;
+ * anything else returns PLNLP_E_UNSUPPORTED (-4) and the caller picks another kernel.  Same epilogue contract. */
+int64_t plnlp_gemm_tf32_tma_workspace_bytes(int64_t N, int64_t K);
+int plnlp_gemm_tf32_tma(int passes, int transb, int64_t M, int64_t N, int64_t K,
+                        const float* A, int64_t lda, const float* B, int64_t ldb,
+                        float* C, int64_t ldc, float beta, const float* bias, int act,
+                        const float* aux, int64_t ldaux, float drop_p, uint64_t seed,
+                        float* workspace, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Edge scoring (replaces h[edge[0]], h[edge[1]] advanced indexing + MLPPredictor /
  * DotPredictor, model.py:152-156,180 and layer.py:80-87,174-176).

@@ -32,6 +32,11 @@ GEMM_BACKEND = os.environ.get("PLNLP_GEMM", "tf32x3c2")
 # 296 resident CTA slots instead of 5 splits = 1.15 waves (0.167 -> 0.127 ms per aggregation).
 TF32X3_KCAP = int(os.environ.get("PLNLP_GEMM_KCAP", "1088"))
 
+# TMA-fed persistent GEMM (csrc/gemm_tma.cu) for tall-skinny products A[M, K] @ W^T / A @ W with a huge M and
+# N, K of a few hundred: "auto" = when M >= 16 384, N <= 256 and K <= 512 (the encoder's dense layers on the big
+# graphs; the large-K predictor GEMMs of the ddi shape stay on the CTA-pair kernel), "1" = whenever legal, "0" = off
+GEMM_TMA = os.environ.get("PLNLP_GEMM_TMA", "auto")
+
 # fused edge scoring for the MLP head (gather + Hadamard + layer 1 + out layer in one tcgen05 kernel)
 FUSED_EDGE_MLP = os.environ.get("PLNLP_FUSED_EDGE", "1") != "0"
 
@@ -67,6 +72,15 @@ def _ld(t):
 # 30 % -> 41 %.  A width that is not a multiple of 4 (the 50-wide embedding) is NOT re-pitched: at <= 256 B per
 # gathered row the kernel is bound by the rate of random DRAM row fetches (~17 G rows/s whatever the width
 # between 16 and 64 floats), the generic kernel already reaches it, and the copy would cost more than it gains.
+
+
+def _rows_for_spmm(rows, F, device):
+    """uninitialised fp32 [rows, F] for a GEMM output that an SpMM gathers next: for F <= 64 the rows sit on a
+    64-float (256-byte) pitch -- the GEMM epilogue then writes whole 16-byte vectors and the gather runs on the
+    two-rows-per-warp kernel with every row inside one 256-byte window (F = 50: 3.91 -> 3.75 ms)"""
+    if F <= 64 and F % 4:
+        return torch.empty(rows, 64, dtype=torch.float32, device=device)[:, :F]
+    return torch.empty(rows, F, dtype=torch.float32, device=device)
 
 
 def new_seed():
@@ -150,6 +164,17 @@ def gemm_raw(A, B, transa=False, transb=False, C=None, beta=0.0, bias=None, act=
     if split_k > 1:
         ws_bytes = split_k * M * N * 4
         ws = workspace.get("gemm_splitk", ws_bytes, A.device)
+    if (backend in ("tf32x3c2", "tf32c2", "tf32x3", "tf32") and GEMM_TMA != "0" and not transa and split_k == 1
+            and K >= 32 and N <= 512 and _ld(A) % 4 == 0 and A.data_ptr() % 16 == 0
+            and (GEMM_TMA == "1" or (M >= 16384 and N <= 256 and K <= 512))):
+        nbytes = lib.plnlp_gemm_tf32_tma_workspace_bytes(N, K)
+        wsb = workspace.get("gemm_tma_b", nbytes, A.device)
+        passes = 3 if backend.startswith("tf32x3") else 1
+        with profiling.span(f"gemm_tf32x{passes}_tma {M}x{N}x{K}", 0, 2 * M * N * K):
+            check(lib.plnlp_gemm_tf32_tma(passes, int(transb), M, N, K, ptr(A), _ld(A), ptr(B), _ld(B), ptr(C), _ld(C),
+                                          float(beta), ptr(bias), int(act), ptr(aux), _ld(aux) if aux is not None else 0,
+                                          float(drop_p), int(seed), ptr(wsb), nbytes, stream()), "plnlp_gemm_tf32_tma")
+        return C
     tail = (int(transa), int(transb), M, N, K, ptr(A), _ld(A), ptr(B), _ld(B), ptr(C), _ld(C),
             float(beta), ptr(bias), int(act), ptr(aux), _ld(aux) if aux is not None else 0,
             float(drop_p), int(seed), ptr(ws), ws_bytes, int(split_k), stream())
@@ -487,7 +512,8 @@ class SpMMRows(torch.autograd.Function):
         st = structure_of(adj)
         mean = reduce == "mean"
         parent = st.fwd_noval if mean else st.fwd
-        plan = build_subset_plan(parent, st.rowptr, rows)
+        with profiling.span("torch: row-subset plan (index ops, 3 host reads)"):
+            plan = build_subset_plan(parent, st.rowptr, rows)
         out = spmm_raw(plan, x, use_val=not mean, div_rows=mean, bias=bias, relu=relu, drop_p=drop_p, seed=seed)
         ctx.st, ctx.mean, ctx.drop_p, ctx.has_bias = st, mean, drop_p, bias is not None
         ctx.save_for_backward(rows, out if (relu or drop_p > 0) else None)
@@ -503,8 +529,9 @@ class SpMMRows(torch.autograd.Function):
         gb = colsum_raw(g) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
         gx = None
         if ctx.needs_input_grad[0]:
-            x_index = torch.full((st.n_rows,), -1, dtype=torch.int32, device=g.device)
-            x_index[rows] = torch.arange(rows.numel(), dtype=torch.int32, device=g.device)
+            with profiling.span("torch: x_index of the compact gradient"):
+                x_index = torch.full((st.n_rows,), -1, dtype=torch.int32, device=g.device)
+                x_index[rows] = torch.arange(rows.numel(), dtype=torch.int32, device=g.device)
             plan = st.bwd_mean if ctx.mean else st.bwd
             gx = spmm_raw(plan, g, use_val=True if ctx.mean else st.has_value, div_rows=False, x_index=x_index)
         return gx, gb, None, None, None, None, None, None
@@ -622,14 +649,22 @@ class AggLinear(torch.autograd.Function):
             for off, x in zip(ctx.offs, xs):
                 aggregate_into(ctx.adj, x, buf[:, off:off + x.size(1)])
             ctx.holder["stamp"] += 1
-        gW = gemm_raw(g, buf, transa=True) if ctx.needs_input_grad[0] else None             # dW = dY^T [A x]
-        gb = colsum_raw(g) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
+        gW = gb = None
+        ext = ctx.holder.get("ext")
+        want_b = ctx.has_bias and ctx.needs_input_grad[1]
+        if ctx.needs_input_grad[0] and want_b and ext is not None:
+            # dY^T [A x | 1]: the weight gradient and, in the last column, the bias gradient (column sums of dY)
+            gWe = gemm_raw(g, ext, transa=True)
+            gW, gb = gWe[:, :-1].contiguous(), gWe[:, -1].contiguous()
+        else:
+            gW = gemm_raw(g, buf, transa=True) if ctx.needs_input_grad[0] else None         # dW = dY^T [A x]
+            gb = colsum_raw(g) if want_b else None
         gxs = []
         for i, (off, x) in enumerate(zip(ctx.offs, xs)):
             if not ctx.needs_input_grad[10 + i]:
                 gxs.append(None)
                 continue
-            gu = gemm_raw(g, W[:, off:off + x.size(1)])                                      # d(A x_i) = dY W_i
+            gu = gemm_raw(g, W[:, off:off + x.size(1)], C=_rows_for_spmm(g.size(0), x.size(1), g.device))   # d(A x_i) = dY W_i
             gxs.append(aggregate_t(ctx.adj, gu, ctx.sparse_grad)[: x.size(0)])                # A^T .
         return (gW, gb, None, None, None, None, None, None, None, None, *gxs)
 

@@ -249,13 +249,60 @@ __device__ __forceinline__ float tc_epilogue_one(const TcGemmParams& p, int64_t 
 }
 
 
+// beta*C + bias -> relu -> dropout / relu-grad mask for the 32 columns c0 .. c0+31 of row r held in v
+// (bias_s: optional copy of the bias vector in shared memory, indexed by global column -- gemm_tma.cu)
+__device__ __forceinline__ void tc_epi_apply32(const TcGemmParams& p, int64_t r, int64_t c0, float (&v)[32], bool vec_epi,
+                                               float keep_scale, const float* bias_s = nullptr) {
+    if (vec_epi && c0 + 31 < p.N) {
+        // 4 columns at a time: 16-byte loads of C / bias / aux, one Philox block per
+        // group (element r*N + c uses word c%4 of block (r*N + c)/4 -- the same
+        // stream as dropout_keep, a quarter of the hashing)
+        const float* crow = p.C + r * p.ldc + c0;
+        const float* arow = p.aux ? p.aux + r * p.ldaux + c0 : nullptr;
+        const uint64_t ebase = static_cast<uint64_t>(r) * p.N + c0;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+            float x[4] = {v[e], v[e + 1], v[e + 2], v[e + 3]};
+            if (p.beta != 0.0f) {
+                const float4 c4 = *reinterpret_cast<const float4*>(crow + e);
+                x[0] += p.beta * c4.x; x[1] += p.beta * c4.y;
+                x[2] += p.beta * c4.z; x[3] += p.beta * c4.w;
+            }
+            if (p.bias) {
+                const float4 b4 = bias_s ? *reinterpret_cast<const float4*>(bias_s + c0 + e)
+                                         : __ldg(reinterpret_cast<const float4*>(p.bias + c0 + e));
+                x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w;
+            }
+            if (p.act == PLNLP_ACT_RELU) {
+                bool keep[4] = {true, true, true, true};
+                if (p.drop_p > 0.0f) dropout_keep4(p.seed, ebase + e, p.drop_p, keep);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) x[t] = keep[t] ? fmaxf(x[t], 0.0f) * keep_scale : 0.0f;
+            } else if (p.act == PLNLP_ACT_RELU_GRAD) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(arow + e));
+                x[0] = a4.x > 0.0f ? x[0] * keep_scale : 0.0f;
+                x[1] = a4.y > 0.0f ? x[1] * keep_scale : 0.0f;
+                x[2] = a4.z > 0.0f ? x[2] * keep_scale : 0.0f;
+                x[3] = a4.w > 0.0f ? x[3] * keep_scale : 0.0f;
+            }
+            v[e] = x[0]; v[e + 1] = x[1]; v[e + 2] = x[2]; v[e + 3] = x[3];
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+            if (c0 + e < p.N) v[e] = tc_epilogue_one(p, r, c0 + e, v[e]);
+    }
+}
+
+
 // Epilogue of one CTA tile, executed by warps 0-7 after the accumulator barrier: thread (warp q = w%4,
 // lane) owns accumulator row q*32 + lane; warps 0-3 / 4-7 take the two column halves.  Split-k partial
 // store, or beta*C + bias -> relu -> dropout / relu-grad mask.
-template <int BN>
+// HALVES = 1: four warps (one per TMEM lane quarter) each take all BN columns (gemm_tma.cu).
+template <int BN, int HALVES = 2>
 __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t tmem_d, int64_t m0, int64_t n0,
                                                  int n_mma, int n_iter, int warp, int lane) {
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, half = HALVES == 2 ? (warp >> 2) : 0;
     const int64_t r = m0 + q * 32 + lane;
     const bool split = p.split_k > 1;
     const bool plain = p.beta == 0.0f && p.bias == nullptr && p.act == PLNLP_ACT_NONE;
@@ -265,7 +312,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
                          (!p.bias || reinterpret_cast<uintptr_t>(p.bias) % 16 == 0) &&
                          (!p.aux || ((p.ldaux % 4 == 0) && reinterpret_cast<uintptr_t>(p.aux) % 16 == 0));
     float* wsz = split ? p.ws + static_cast<int64_t>(blockIdx.z) * p.M * p.N : nullptr;
-    for (int cb = half * (BN / 2); cb < (half + 1) * (BN / 2); cb += 32) {
+    for (int cb = half * (BN / HALVES); cb < (half + 1) * (BN / HALVES); cb += 32) {
         if (cb >= n_mma) break;                                   // warp-uniform
         float v[32];
         if (n_iter > 0) {
@@ -288,46 +335,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcGemmParams& p, uint32_t
                         if (c0 + e < p.N) dst[e] = v[e];
                 }
             } else {
-                if (!plain) {
-                    if (vec_epi && c0 + 31 < p.N) {
-                        // 4 columns at a time: 16-byte loads of C / bias / aux, one Philox block per
-                        // group (element r*N + c uses word c%4 of block (r*N + c)/4 -- the same
-                        // stream as dropout_keep, a quarter of the hashing)
-                        const float* crow = p.C + r * p.ldc + c0;
-                        const float* arow = p.aux ? p.aux + r * p.ldaux + c0 : nullptr;
-                        const uint64_t ebase = static_cast<uint64_t>(r) * p.N + c0;
-#pragma unroll
-                        for (int e = 0; e < 32; e += 4) {
-                            float x[4] = {v[e], v[e + 1], v[e + 2], v[e + 3]};
-                            if (p.beta != 0.0f) {
-                                const float4 c4 = *reinterpret_cast<const float4*>(crow + e);
-                                x[0] += p.beta * c4.x; x[1] += p.beta * c4.y;
-                                x[2] += p.beta * c4.z; x[3] += p.beta * c4.w;
-                            }
-                            if (p.bias) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + e));
-                                x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w;
-                            }
-                            if (p.act == PLNLP_ACT_RELU) {
-                                bool keep[4] = {true, true, true, true};
-                                if (p.drop_p > 0.0f) dropout_keep4(p.seed, ebase + e, p.drop_p, keep);
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) x[t] = keep[t] ? fmaxf(x[t], 0.0f) * keep_scale : 0.0f;
-                            } else if (p.act == PLNLP_ACT_RELU_GRAD) {
-                                const float4 a4 = __ldg(reinterpret_cast<const float4*>(arow + e));
-                                x[0] = a4.x > 0.0f ? x[0] * keep_scale : 0.0f;
-                                x[1] = a4.y > 0.0f ? x[1] * keep_scale : 0.0f;
-                                x[2] = a4.z > 0.0f ? x[2] * keep_scale : 0.0f;
-                                x[3] = a4.w > 0.0f ? x[3] * keep_scale : 0.0f;
-                            }
-                            v[e] = x[0]; v[e + 1] = x[1]; v[e + 2] = x[2]; v[e + 3] = x[3];
-                        }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e)
-                            if (c0 + e < p.N) v[e] = tc_epilogue_one(p, r, c0 + e, v[e]);
-                    }
-                }
+                if (!plain) tc_epi_apply32(p, r, c0, v, vec_epi, keep_scale);
                 if (p.w_out) {     // fused out_channels = 1 layer: this thread's share of a[r, :] . w_out
 #pragma unroll
                     for (int e = 0; e < 32; ++e)

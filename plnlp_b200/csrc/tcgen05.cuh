@@ -82,6 +82,22 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// the same load WITHOUT the wait: the registers may only be read after tmem_ld_wait() (lets the load of the next
+// chunk fly while the current one is processed)
+__device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // ---------------------------------------------------------------- descriptors + MMA
 // shared-memory matrix descriptor, no swizzle ("interleaved" canonical layout of 8x16B core matrices)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -186,6 +202,36 @@ __device__ __forceinline__ void mma_commit_2cta(uint64_t* bar, uint16_t cta_mask
             smem_u32(bar)),
         "h"(cta_mask)
         : "memory");
+}
+
+// ---------------------------------------------------------------- TMA (cp.async.bulk.tensor) + 128-byte swizzle
+// arm the barrier with the byte count the bulk copies of this phase will deliver, and arrive (count 1)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 2-D tiled load global -> shared through a CUtensorMap (c0 = innermost coordinate, in elements); completion is
+// signalled on `bar` as transaction bytes.  Out-of-bounds parts of the box are filled with zeros.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+// K-major operand tile written by TMA with CU_TENSOR_MAP_SWIZZLE_128B: rows of 128 bytes (32 tf32 of K), 8-row
+// groups 1024 bytes apart (SBO), 16-byte chunks of a row XOR-ed with (row % 8).  The tile base must be 1024-byte
+// aligned; a k-step of 8 tf32 inside the 128-byte row advances the start address by 32 bytes.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>(1) << 16;             // LBO: unused for swizzled K-major layouts (canonical value 1)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;     // SBO = 1024 bytes
+    d |= static_cast<uint64_t>(1) << 46;             // descriptor version for sm_100
+    d |= static_cast<uint64_t>(2) << 61;             // layout type SWIZZLE_128B
+    return d;
 }
 
 // round-to-nearest fp32 -> tf32 (result is an fp32 bit pattern with the low 13 mantissa bits zero)

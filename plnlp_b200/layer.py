@@ -62,14 +62,21 @@ def _agg_buffer(adj_t, parts):
     holder = adj_t.__dict__.setdefault("_plnlp_agg_buffer", {})
     if holder.get("key") != key:
         holder.clear()
-        buf = torch.empty(adj_t.size(0), sum(p.size(1) for p in parts), dtype=torch.float32, device=parts[0].device)
+        # rows on a 16-byte pitch (the TMA-fed GEMM, csrc/gemm_tma.cu, reads this matrix as its A operand) with one
+        # spare column that holds 1.0: the weight-gradient GEMM  dY^T [A x | 1]  then delivers the bias gradient
+        # (the column sums of dY) in its last column for free -- no separate pass over dY (_ops.AggLinear.backward)
+        width = sum(p.size(1) for p in parts)
+        full = torch.empty(adj_t.size(0), (width + 1 + 3) // 4 * 4, dtype=torch.float32, device=parts[0].device)
+        full[:, width:] = 0.0
+        full[:, width] = 1.0
+        buf = full[:, :width]
         off = 0
         with torch.no_grad():
             for p in parts:
                 if _is_const(p):
                     _ops.aggregate_into(adj_t, p, buf[:, off:off + p.size(1)])
                 off += p.size(1)
-        holder.update(key=key, buf=buf, stamp=0)
+        holder.update(key=key, buf=buf, ext=full[:, :width + 1], stamp=0)
     offs, xs, off = [], [], 0
     for p in parts:
         if not _is_const(p):

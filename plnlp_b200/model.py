@@ -17,7 +17,7 @@ import os
 
 import torch
 
-from . import _ops
+from . import _ops, profiling
 from .layer import *  # noqa: F401,F403
 from .layer import (GCN, SAGE, WSAGE, BilinearPredictor, DotPredictor, MLPBilPredictor, MLPCatPredictor,
                     MLPDotPredictor, MLPPredictor, mark_constant)
@@ -142,7 +142,8 @@ class BaseModel(object):
         if self.partitioned:
             from . import parallel
         if sparse_rows and not self.partitioned:
-            ids, inv = torch.unique(torch.cat([pos_edge, neg_edge], 0), return_inverse=True)
+            with profiling.span("torch: unique endpoint ids + renumber"):
+                ids, inv = torch.unique(torch.cat([pos_edge, neg_edge], 0), return_inverse=True)
             h, restricted = self.encoder(self.input_parts(data), data.adj_t, out_rows=ids)
             if restricted:
                 pos_edge, neg_edge = inv[:pos_edge.size(0)], inv[pos_edge.size(0):]
@@ -151,7 +152,8 @@ class BaseModel(object):
             # what the last conv computes -- as partial products over each rank's column block, summed by one
             # all-reduce (parallel.pspmm_rows) -- so every rank holds the compact h of ALL batches and scores its own
             mine = torch.cat([pos_edge, neg_edge], 0)
-            ids = parallel.union_ids(mine.reshape(-1), data.adj_t.group)
+            with profiling.span("torch + nccl: union of endpoint ids (all_gather + unique)"):
+                ids = parallel.union_ids(mine.reshape(-1), data.adj_t.group)
             h, restricted = self.encoder(self.input_parts(data), data.adj_t, out_rows=ids)
             if restricted:
                 inv = torch.searchsorted(ids, mine)
@@ -183,12 +185,13 @@ class BaseModel(object):
         loss.backward()
         if getattr(self, 'world_size', 1) > 1:
             self._allreduce_grads()
-        if self.clip_norm >= 0:
-            torch.nn.utils.clip_grad_norm_(self.encoder.parameters(), self.clip_norm)
-            pp = list(self.predictor.parameters())
-            if pp:
-                torch.nn.utils.clip_grad_norm_(pp, self.clip_norm)
-        self.optimizer.step()
+        with profiling.span("torch: clip_grad_norm + fused Adam step"):
+            if self.clip_norm >= 0:
+                torch.nn.utils.clip_grad_norm_(self.encoder.parameters(), self.clip_norm)
+                pp = list(self.predictor.parameters())
+                if pp:
+                    torch.nn.utils.clip_grad_norm_(pp, self.clip_norm)
+            self.optimizer.step()
         return loss.detach()
 
     def _allreduce_grads(self):

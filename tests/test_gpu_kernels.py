@@ -665,6 +665,62 @@ def test_gemm_tf32x3_2cta_layouts(ops, M, N, K, ta, tb):
     assert rel_err(got, want) < TOL, rel_err(got, want)
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 200, 178), (1000, 50, 200), (257, 512, 96), (129, 16, 32), (4096, 256, 512),
+                                   (130, 208, 1000), (20000, 200, 178), (70000, 64, 200), (5000, 300, 40)])
+@pytest.mark.parametrize("tb", [True, False])
+def test_gemm_tma_tall_skinny(ops, M, N, K, tb, monkeypatch):
+    """TMA-fed persistent kernel (csrc/gemm_tma.cu): ragged M / N / K (zero fill by the tensor map), both layouts of
+    the weight, more tiles than SMs (persistent loop, both TMEM accumulators, ring wrap-around), two column tiles;
+    the same 3xTF32 bar as the other tensor-core kernels, and bit-identical to the CTA-pair kernel (same split, same
+    MMA order per k-step)"""
+    monkeypatch.setattr(ops, "GEMM_TMA", "1")
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    A = torch.randn(M, (K + 3) // 4 * 4 + 4, generator=g)          # rows on a 16-byte pitch, wider than K
+    B = torch.randn((N, K) if tb else (K, N), generator=g)
+    Ag = A.cuda()[:, :K]
+    n0 = _launches()
+    got = ops.gemm_raw(Ag, B.cuda(), transb=tb, backend="tf32x3c2")
+    if M * N * K >= (1 << 20):                                    # (tiny products go to the FFMA kernel)
+        assert _launches() - n0 == 2                               # weight split + the GEMM: the TMA path ran
+    want = A[:, :K].double() @ (B.t() if tb else B).double()
+    assert rel_err(got.cpu(), want) < TOL, rel_err(got.cpu(), want)
+    monkeypatch.setattr(ops, "GEMM_TMA", "0")
+    old = ops.gemm_raw(Ag, B.cuda(), transb=tb, backend="tf32x3c2")
+    assert rel_err(got, old) < 2e-6
+
+
+def _launches():
+    from plnlp_b200 import _lib
+    return _lib.launch_count()
+
+
+def test_gemm_tma_epilogues(ops, monkeypatch):
+    monkeypatch.setattr(ops, "GEMM_TMA", "1")
+    g = torch.Generator().manual_seed(44)
+    M, N, K = 3000, 200, 180
+    A, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    bias, C0 = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    want = A.double() @ W.double().t()
+    n0 = _launches()
+    C = C0.clone().cuda()
+    ops.gemm_raw(A.cuda(), W.cuda(), transb=True, C=C, beta=1.0, bias=bias.cuda(), act=ops.ACT_RELU)
+    assert rel_err(C.cpu(), torch.relu(want + C0.double() + bias.double())) < TOL
+    aux = torch.randn(M, N, generator=g)
+    G = ops.gemm_raw(A.cuda(), W.cuda(), transb=True, act=ops.ACT_RELU_GRAD, aux=aux.cuda())
+    assert rel_err(G.cpu(), want * (aux > 0)) < TOL
+    d1 = ops.gemm_raw(A.cuda(), W.cuda(), transb=True, act=ops.ACT_RELU, drop_p=0.3, seed=99)
+    assert _launches() - n0 == 6
+    d2 = ops.gemm_raw(A.cuda(), W.cuda(), transb=True, act=ops.ACT_RELU, drop_p=0.3, seed=99, backend="ffma")
+    assert torch.equal(d1 == 0, d2 == 0) and rel_err(d1, d2) < TOL
+    # output into a column slice of a wider matrix (unaligned leading dimension: scalar epilogue stores)
+    wide = torch.full((M, N + 7), -3.0).cuda()
+    ops.gemm_raw(A.cuda(), W.cuda(), transb=True, C=wide[:, 3:3 + N])
+    assert rel_err(wide[:, 3:3 + N].cpu(), want) < TOL and torch.all(wide[:, :3] == -3.0) and torch.all(wide[:, 3 + N:] == -3.0)
+    # plain TF32 (single pass), stated separately
+    fast = ops.gemm_raw(A.cuda(), W.cuda(), transb=True, backend="tf32c2").cpu()
+    assert 1e-5 < rel_err(fast, want) < 5e-3
+
+
 def test_gemm_tf32x3_2cta_epilogues_and_splitk(ops):
     g = torch.Generator().manual_seed(6)
     A, W = torch.randn(1000, 512, generator=g), torch.randn(384, 512, generator=g)
