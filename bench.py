@@ -279,9 +279,9 @@ def measure(args, workload, world, rank, device, full):
         pos, neg = get_pos_neg_edges("train", sub, edge_index=data.edge_index, num_nodes=cfg["N"],
                                      neg_sampler_name=cfg["sampler"], num_neg=k, device=device)
         model.encoder.train(); model.predictor.train()
-        for i in range(n):
-            model.train_batch(data, pos[i * Bl:(i + 1) * Bl], neg[i * Bl:(i + 1) * Bl].reshape(-1, 2), k,
-                              None if wgt is None else wgt[i * Bl:(i + 1) * Bl])
+        # the batch loop of BaseModel.train (index work of batch i + 1 prepared on a side stream while batch i runs)
+        model.run_batches(data, ((pos[i * Bl:(i + 1) * Bl], neg[i * Bl:(i + 1) * Bl].reshape(-1, 2),
+                                  None if wgt is None else wgt[i * Bl:(i + 1) * Bl]) for i in range(n)), k)
 
     out = {"cfg": cfg, "E": E, "partitioned": partitioned, "strong": strong, "K": K, "W": W}
 
@@ -292,11 +292,14 @@ def measure(args, workload, world, rank, device, full):
         out["parity_check"] = {
             "loss_rel": max_over_ranks(errs["loss_rel"]), "max_grad_rel": max_over_ranks(errs["max_grad_rel"]),
             "max_grad_rel_per_tensor": max_over_ranks(errs["max_grad_rel_per_tensor"]),
+            "fp32_noise_floor": max_over_ranks(errs["fp32_noise_floor"]),
             "what": f"one optimisation step of the row-partitioned model on {world} ranks vs the single-GPU model on "
                     "the same parameters, graph (60 000 nodes, GCN 2x32 + MLP head, features + embedding) and global "
                     "batch; max over ranks; max_grad_rel = largest |d - d_single| over every gradient tensor / largest "
                     "gradient magnitude of the model (per_tensor: relative to each tensor's own magnitude, which for "
-                    "the predictor biases is cancellation noise: d loss / d score sums to 0 under the AUC loss)"}
+                    "the predictor biases is cancellation noise: d loss / d score sums to 0 under the AUC loss); "
+                    "fp32_noise_floor = the same quantity between two SINGLE-GPU runs of that step that differ only in "
+                    "the order of the pairs inside the batch -- what a change of summation order alone costs"}
         torch.cuda.empty_cache()
 
     # ---- value: device-resident ------------------------------------------------------------
@@ -416,8 +419,9 @@ def measure(args, workload, world, rank, device, full):
         nccl = [r for r in kernels if r["kernel"].startswith("nccl")]
         if nccl:
             out["nvlink"] = {"peak_gbs_per_direction": NVLINK_PEER_GBS, "peak_source": "measured peer copy (B200_PROFILING.md)",
-                             "collectives": nccl, "exposed_ms_per_step": round(sum(r["ms_total"] for r in nccl) / K, 3),
-                             "share_of_step": round(sum(r["share"] for r in nccl), 4)}
+                             "collectives": nccl, "ms_per_step_run_alone": round(sum(r["ms_total"] for r in nccl) / K, 3),
+                             "note": "durations from the instrumented pass, which runs every collective synchronously; in "
+                                     "the timed passes the layer-1 reduce-scatter overlaps the weight-gradient GEMM"}
     return out
 
 

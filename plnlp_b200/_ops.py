@@ -512,8 +512,13 @@ class SpMMRows(torch.autograd.Function):
         st = structure_of(adj)
         mean = reduce == "mean"
         parent = st.fwd_noval if mean else st.fwd
-        with profiling.span("torch: row-subset plan (index ops, 3 host reads)"):
-            plan = build_subset_plan(parent, st.rowptr, rows)
+        ready = getattr(rows, "_plnlp_prepared", {}).get(id(st)) if not mean else None
+        if ready is not None:                                     # BaseModel.prepare_batch built them ahead of time
+            plan, ctx.x_index = ready
+        else:
+            ctx.x_index = None
+            with profiling.span("torch: row-subset plan (index ops, 3 host reads)"):
+                plan = build_subset_plan(parent, st.rowptr, rows)
         out = spmm_raw(plan, x, use_val=not mean, div_rows=mean, bias=bias, relu=relu, drop_p=drop_p, seed=seed)
         ctx.st, ctx.mean, ctx.drop_p, ctx.has_bias = st, mean, drop_p, bias is not None
         ctx.save_for_backward(rows, out if (relu or drop_p > 0) else None)
@@ -529,9 +534,11 @@ class SpMMRows(torch.autograd.Function):
         gb = colsum_raw(g) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
         gx = None
         if ctx.needs_input_grad[0]:
-            with profiling.span("torch: x_index of the compact gradient"):
-                x_index = torch.full((st.n_rows,), -1, dtype=torch.int32, device=g.device)
-                x_index[rows] = torch.arange(rows.numel(), dtype=torch.int32, device=g.device)
+            x_index = ctx.x_index
+            if x_index is None:
+                with profiling.span("torch: x_index of the compact gradient"):
+                    x_index = torch.full((st.n_rows,), -1, dtype=torch.int32, device=g.device)
+                    x_index[rows] = torch.arange(rows.numel(), dtype=torch.int32, device=g.device)
             plan = st.bwd_mean if ctx.mean else st.bwd
             gx = spmm_raw(plan, g, use_val=True if ctx.mean else st.has_value, div_rows=False, x_index=x_index)
         return gx, gb, None, None, None, None, None, None
@@ -602,17 +609,19 @@ def aggregate_into(adj, x, out):
     return spmm_raw(st.fwd, x, use_val=st.has_value, div_rows=False, out=out)
 
 
-def aggregate_t(adj, g, sparse_rows=False):
+def aggregate_t(adj, g, sparse_rows=False, async_op=False):
     """A^T @ g through the raw kernel; row-partitioned: the transposed product over all columns is
     reduce-scattered to the owners of the rows.  ``sparse_rows``: most rows of g are exactly zero -- measure
-    which (one pass over g) and gather only the live ones."""
+    which (one pass over g) and gather only the live ones.  ``async_op``: -> (result, wait); on a row-partitioned
+    adjacency the reduce-scatter is then in flight until ``wait()`` is called."""
     x_index = row_nonzero_index_raw(g) if sparse_rows else None
     if isinstance(adj, parallel.ShardedAdj):
         st = structure_of(adj.local)
         full = spmm_raw(st.bwd, g, use_val=st.has_value, div_rows=False, x_index=x_index)
-        return parallel._reduce_scatter_rows(full, adj.blk, adj.group)
+        return parallel._reduce_scatter_rows(full, adj.blk, adj.group, async_op=async_op)
     st = structure_of(adj)
-    return spmm_raw(st.bwd, g, use_val=st.has_value, div_rows=False, x_index=x_index)
+    out = spmm_raw(st.bwd, g, use_val=st.has_value, div_rows=False, x_index=x_index)
+    return (out, (lambda: None)) if async_op else out
 
 
 class AggLinear(torch.autograd.Function):
@@ -649,6 +658,17 @@ class AggLinear(torch.autograd.Function):
             for off, x in zip(ctx.offs, xs):
                 aggregate_into(ctx.adj, x, buf[:, off:off + x.size(1)])
             ctx.holder["stamp"] += 1
+        # input gradients first: on a row-partitioned adjacency their reduce-scatter then travels over NVLink while
+        # the weight-gradient GEMM below runs
+        gxs, waits = [], []
+        for i, (off, x) in enumerate(zip(ctx.offs, xs)):
+            if not ctx.needs_input_grad[10 + i]:
+                gxs.append(None)
+                continue
+            gu = gemm_raw(g, W[:, off:off + x.size(1)], C=_rows_for_spmm(g.size(0), x.size(1), g.device))   # d(A x_i) = dY W_i
+            gx, wait = aggregate_t(ctx.adj, gu, ctx.sparse_grad, async_op=True)                 # A^T .
+            gxs.append(gx[: x.size(0)])
+            waits.append(wait)
         gW = gb = None
         ext = ctx.holder.get("ext")
         want_b = ctx.has_bias and ctx.needs_input_grad[1]
@@ -659,13 +679,8 @@ class AggLinear(torch.autograd.Function):
         else:
             gW = gemm_raw(g, buf, transa=True) if ctx.needs_input_grad[0] else None         # dW = dY^T [A x]
             gb = colsum_raw(g) if want_b else None
-        gxs = []
-        for i, (off, x) in enumerate(zip(ctx.offs, xs)):
-            if not ctx.needs_input_grad[10 + i]:
-                gxs.append(None)
-                continue
-            gu = gemm_raw(g, W[:, off:off + x.size(1)], C=_rows_for_spmm(g.size(0), x.size(1), g.device))   # d(A x_i) = dY W_i
-            gxs.append(aggregate_t(ctx.adj, gu, ctx.sparse_grad)[: x.size(0)])                # A^T .
+        for wait in waits:
+            wait()
         return (gW, gb, None, None, None, None, None, None, None, None, *gxs)
 
 

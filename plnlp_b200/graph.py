@@ -274,6 +274,11 @@ def build_subset_plan(parent, rowptr, rows):
     return p
 
 
+def plan_tensors(plan):
+    """the device tensors a plan owns or references (for stream bookkeeping)"""
+    return [t for t in (getattr(plan, s) for s in SpmmPlan.__slots__) if isinstance(t, torch.Tensor)]
+
+
 class Structure:
     """Everything the encoder kernels need about one adjacency, forward and transposed."""
 

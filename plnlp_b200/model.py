@@ -29,6 +29,15 @@ _IN_SCOPE_LOSSES = ('AUC', 'HingeAUC', 'WeightedHingeAUC')
 
 # skip all-zero gradient rows in the backward of the last conv (see train_batch)
 ROW_SPARSE_GRAD = os.environ.get("PLNLP_ROW_SPARSE_GRAD", "1") != "0"
+# do the index work of the next batch on a side stream while the current one runs (BaseModel.prepare_batch)
+PREPARE_AHEAD = os.environ.get("PLNLP_PREPARE_AHEAD", "1") != "0"
+
+
+class PreparedBatch:
+    __slots__ = ("ids", "pos_edge", "neg_edge", "event")
+
+    def __init__(self, ids, pos_edge, neg_edge, event):
+        self.ids, self.pos_edge, self.neg_edge, self.event = ids, pos_edge, neg_edge, event
 
 
 class BaseModel(object):
@@ -127,21 +136,73 @@ class BaseModel(object):
         return _ops.pair_loss(self._loss_name(margin is not None), pos_out, neg_out, num_neg, margin)
 
     # ------------------------------------------------------------------
-    def train_batch(self, data, pos_edge, neg_edge, num_neg, weight_margin=None):
+    def _sparse_rows(self, pos_edge, neg_edge):
+        """does this batch touch a small part of the node set?  (then the last conv computes only the endpoint rows)"""
+        n_touch = 2 * (pos_edge.size(0) + neg_edge.size(0)) * (self.world_size if self.partitioned else 1)
+        return ROW_SPARSE_GRAD and n_touch < 0.5 * self.num_nodes
+
+    def prepare_batch(self, data, pos_edge, neg_edge):
+        """The index work of one step that does not depend on any parameter: the sorted distinct endpoint rows of the
+        batch (on a row-partitioned run: the union over ranks), the edges renumbered into that compact table, the
+        row-subset SpMM plan of the last conv and the index vector of its backward.  It runs on a SIDE stream, so
+        ``run_batches`` can issue it for batch i + 1 while the GPU is still busy with batch i: the host reads it needs
+        (``torch.unique``, the plan's item counts) then cost nothing on the main stream.  Returns None when the batch
+        is not row-sparse or the last conv cannot restrict itself (``train_batch`` then does everything itself)."""
+        if not self._sparse_rows(pos_edge, neg_edge):
+            return None
+        last = self.encoder.convs[-1]
+        parts = self.input_parts(data) if len(self.encoder.convs) == 1 else None
+        if not (getattr(last, "can_restrict", None) and last.can_restrict(parts, data.adj_t)):
+            return None
+        from . import graph
+        main = torch.cuda.current_stream()
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        side = self._side_stream
+        side.wait_stream(main)                                   # the edge tensors were produced on the main stream
+        with torch.cuda.stream(side):
+            mine = torch.cat([pos_edge, neg_edge], 0)
+            if self.partitioned:
+                from . import parallel
+                if not parallel.RESTRICT_LAST:
+                    return None
+                ids = parallel.union_ids(mine.reshape(-1), data.adj_t.group)
+                inv = torch.searchsorted(ids, mine)
+                st = graph.structure_of(data.adj_t.cols())
+            else:
+                ids, inv = torch.unique(mine, return_inverse=True)
+                st = graph.structure_of(data.adj_t)
+            plan = graph.build_subset_plan(st.fwd, st.rowptr, ids)
+            x_index = torch.full((st.n_rows,), -1, dtype=torch.int32, device=ids.device)
+            x_index[ids] = torch.arange(ids.numel(), dtype=torch.int32, device=ids.device)
+            ids._plnlp_prepared = {id(st): (plan, x_index)}      # picked up by _ops.SpMMRows
+            n_pos = pos_edge.size(0)
+            prep = PreparedBatch(ids, inv[:n_pos], inv[n_pos:], torch.cuda.Event())
+            for t in [ids, inv, x_index] + graph.plan_tensors(plan):
+                t.record_stream(main)                            # allocated on the side stream, consumed on the main one
+            prep.event.record(side)
+        return prep
+
+    def train_batch(self, data, pos_edge, neg_edge, num_neg, weight_margin=None, prepared=None):
         """one optimisation step (model.py:148-167).  pos_edge [B,2], neg_edge [B*num_neg,2].
-        Returns the batch loss as a 0-d device tensor (no host sync)."""
+        Returns the batch loss as a 0-d device tensor (no host sync).  ``prepared``: the result of
+        ``prepare_batch`` for these edges (else the same index work is done here, on the main stream)."""
         self.optimizer.zero_grad(set_to_none=True)
         # Scoring reads h only at the endpoint rows of the batch, and d loss / d h is non-zero only there.  When
         # those are a small part of the node set (citation2-shape: ~10 %) the last conv computes just those
         # rows (compact h, edges renumbered) and its backward gathers just their gradient rows; a conv that cannot
         # restrict itself is told that its output gradient is row-sparse (``sparse_grad``) and skips the zero rows
         # in its backward.
-        n_touch = 2 * (pos_edge.size(0) + neg_edge.size(0)) * (self.world_size if self.partitioned else 1)
-        sparse_rows = ROW_SPARSE_GRAD and n_touch < 0.5 * self.num_nodes
+        sparse_rows = self._sparse_rows(pos_edge, neg_edge)
         restricted = False
         if self.partitioned:
             from . import parallel
-        if sparse_rows and not self.partitioned:
+        if prepared is not None:
+            torch.cuda.current_stream().wait_event(prepared.event)
+            h, restricted = self.encoder(self.input_parts(data), data.adj_t, out_rows=prepared.ids)
+            assert restricted
+            pos_edge, neg_edge = prepared.pos_edge, prepared.neg_edge
+        elif sparse_rows and not self.partitioned:
             with profiling.span("torch: unique endpoint ids + renumber"):
                 ids, inv = torch.unique(torch.cat([pos_edge, neg_edge], 0), return_inverse=True)
             h, restricted = self.encoder(self.input_parts(data), data.adj_t, out_rows=ids)
@@ -248,19 +309,16 @@ class BaseModel(object):
         if perms is None:
             order = torch.randperm(E, device=self.device)
             perms = [order[i:i + batch_size] for i in range(0, E, batch_size)]
-        total_loss = torch.zeros((), dtype=torch.float64, device=self.device)
-        total_examples = 0
-        for it, perm in enumerate(perms):
-            if max_batches is not None and it >= max_batches:
-                break
-            perm = perm.to(self.device)
-            pos_edge = pos_train_edge[perm]
-            neg_edge = neg_train_edge[perm].reshape(-1, 2)
-            w = margin[perm] if margin is not None else None
-            loss = self.train_batch(data, pos_edge, neg_edge, num_neg, w)
-            total_loss += loss.double() * perm.numel()
-            total_examples += perm.numel()
-        self.last_epoch_stats = {'batches': it + 1 if total_examples else 0, 'examples': total_examples}
+        def batches():
+            for it, perm in enumerate(perms):
+                if max_batches is not None and it >= max_batches:
+                    break
+                perm = perm.to(self.device)
+                yield (pos_train_edge[perm], neg_train_edge[perm].reshape(-1, 2),
+                       margin[perm] if margin is not None else None)
+
+        total_loss, total_examples, n_batches = self.run_batches(data, batches(), num_neg)
+        self.last_epoch_stats = {'batches': n_batches, 'examples': total_examples}
         value = total_loss / max(total_examples, 1)
         if self.world_size > 1:
             # every rank scored 1/R of each batch: the global-batch value of model.py:169-173 is the SUM of the
@@ -270,6 +328,27 @@ class BaseModel(object):
             if self._loss_is_mean():
                 value = value / self.world_size
         return value.item()   # the one host sync of the epoch
+
+    def run_batches(self, data, batches, num_neg):
+        """the batch loop of model.py:147-171 over an iterable of (pos_edge [B,2], neg_edge [B*num_neg,2], weight or
+        None) device tensors, with the parameter-independent index work of batch i + 1 (``prepare_batch``) issued on
+        a side stream right after the kernels of batch i were enqueued.  -> (sum of loss * B as a 0-d fp64 device
+        tensor, examples, batches); no host read of the loss."""
+        total_loss = torch.zeros((), dtype=torch.float64, device=self.device)
+        total_examples = n_batches = 0
+        it = iter(batches)
+        cur = next(it, None)
+        prep = self.prepare_batch(data, cur[0], cur[1]) if cur is not None and PREPARE_AHEAD else None
+        while cur is not None:
+            pos_edge, neg_edge, w = cur
+            loss = self.train_batch(data, pos_edge, neg_edge, num_neg, w, prepared=prep)
+            nxt = next(it, None)
+            prep = self.prepare_batch(data, nxt[0], nxt[1]) if nxt is not None and PREPARE_AHEAD else None
+            total_loss += loss.double() * pos_edge.size(0)
+            total_examples += pos_edge.size(0)
+            n_batches += 1
+            cur = nxt
+        return total_loss, total_examples, n_batches
 
     def _train_pos(self, split_edge):
         tr = split_edge['train']

@@ -68,18 +68,27 @@ def allreduce_grads(params, group=None, average=False):
         off += g.numel()
 
 
-def _reduce_scatter_rows(full, blk, group=None):
-    """sum ``full`` [R*blk, F] over ranks and return this rank's [blk, F] block."""
+def _reduce_scatter_rows(full, blk, group=None, async_op=False):
+    """sum ``full`` [R*blk, F] over ranks and return this rank's [blk, F] block.  ``async_op``: -> (block, wait)
+    where ``wait()`` must be called before the block is read; the collective then runs beside whatever the caller
+    enqueues in between."""
     rank, ws = world()
     out = torch.empty(blk, full.size(1), dtype=full.dtype, device=full.device)
+    work = None
     if dist.get_backend(group) == "gloo":          # gloo has no reduce_scatter: test-only path
         dist.all_reduce(full, group=group)
         out.copy_(full[rank * blk:(rank + 1) * blk])
     else:
         from . import profiling
+        full = full.contiguous()
         # bytes RECEIVED per rank: (R-1)/R of the full matrix (SURVEY 8d all-gather model)
-        with profiling.span("nccl reduce_scatter (rows)", (ws - 1) * out.numel() * 4, 0):
-            dist.reduce_scatter_tensor(out, full.contiguous(), group=group)
+        if async_op and not profiling.enabled():
+            work = dist.reduce_scatter_tensor(out, full, group=group, async_op=True)
+        else:
+            with profiling.span("nccl reduce_scatter (rows)", (ws - 1) * out.numel() * 4, 0):
+                dist.reduce_scatter_tensor(out, full, group=group)
+    if async_op:
+        return out, ((lambda: work.wait()) if work is not None else (lambda: None))
     return out
 
 

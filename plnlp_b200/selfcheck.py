@@ -115,6 +115,15 @@ def partitioned_step(rank, ws, device, adj=None, n=60000, e=600000, feats=16, em
             if keep:
                 grads["single"][key], grads["part"][key] = b.grad.cpu(), a.grad.cpu()
         errs["max_abs_over_model_scale"] = worst / max(scale, 1e-30)
+        # fp32 noise floor of the comparison: the SAME single-GPU step with the pairs of the batch in another order
+        # (mathematically identical loss and gradients; only the summation order inside the scatter / reduction
+        # kernels changes, as it does between 1 and N ranks)
+        ref = [b.grad.detach().clone() for _, _, b in pairs] + [single.emb.weight.grad.detach().clone()]
+        perm = torch.randperm(pos_all.size(0), generator=torch.Generator().manual_seed(seed + 1)).to(device)
+        single.train_batch(d1, pos_all[perm], neg_all[perm].reshape(-1, 2), k)
+        again = [b.grad for _, _, b in pairs] + [single.emb.weight.grad]
+        errs["noise_floor_over_model_scale"] = max(
+            float((a.double() - b.double()).abs().max()) for a, b in zip(again, ref)) / max(scale, 1e-30)
         if keep:
             grads["single"]["emb"] = single.emb.weight.grad[lo:hi].cpu()
             grads["part"]["emb"] = part.emb.weight.grad[: hi - lo].cpu()
@@ -133,7 +142,9 @@ def partitioned_step(rank, ws, device, adj=None, n=60000, e=600000, feats=16, em
 
 def summarize(errs):
     """the two numbers bench.py prints: loss error and the worst gradient error (on the model-wide scale)"""
-    per_tensor = {k: v for k, v in errs.items() if not k.startswith("_") and k not in ("loss", "max_abs_over_model_scale")}
+    per_tensor = {k: v for k, v in errs.items() if not k.startswith("_")
+                  and k not in ("loss", "max_abs_over_model_scale", "noise_floor_over_model_scale")}
     return {"loss_rel": errs["loss"], "max_grad_rel": errs["max_abs_over_model_scale"],
+            "fp32_noise_floor": errs["noise_floor_over_model_scale"],
             "max_grad_rel_per_tensor": max(per_tensor.values()),
             "worst_tensor": max(per_tensor, key=per_tensor.get)}

@@ -212,6 +212,31 @@ def test_gcn_feature_plus_embedding_layer_orders(golden_dir, mode, monkeypatch):
     assert used_buffer == (mode in ("buffer", "restricted_last_layer", "row_sparse_grad_only"))
 
 
+def test_prepared_batches_equal_unprepared(golden_dir, monkeypatch):
+    """BaseModel.run_batches prepares the index work of batch i + 1 (endpoint ids, renumbered edges, row-subset plan,
+    backward index) on a side stream while batch i runs: same bits as train_batch doing it inline, step after step"""
+    from plnlp_b200 import graph, model as M
+    monkeypatch.setattr(graph, "DENSE_SPMM", False)
+    R = torch.load(os.path.join(golden_dir, "train_runs.pt"))["citation_like"]
+    pos = plnlp_ref.train_pos_edges(R["split"])
+    outs = []
+    for ahead in (False, True):
+        monkeypatch.setattr(M, "PREPARE_AHEAD", ahead)
+        cfg, model, data = _setup_run(R)
+        model.num_nodes = 10 ** 9                                  # every batch counts as row-sparse
+        model.encoder.train(); model.predictor.train()
+        batches = [(pos[p].cuda(), R["negs"][0][p].reshape(-1, 2).cuda(), None) for p in R["perms"][0][:3]]
+        calls = []
+        orig = model.prepare_batch
+        model.prepare_batch = lambda *a: (calls.append(1), orig(*a))[1]
+        tot, n_ex, n_b = model.run_batches(data, iter(batches), cfg["num_neg"])
+        assert n_b == len(batches) and len(calls) == (len(batches) if ahead else 0)
+        outs.append((float(tot), [p.detach().clone() for p in model.para_list]))
+    assert outs[0][0] == outs[1][0]
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(a, b)
+
+
 def test_gcn_aggregate_buffer_survives_interleaved_forwards(monkeypatch):
     """the aggregate buffer is shared by every forward on one adjacency: a backward that runs after a LATER
     forward must first restore its own live block (AggLinear's stamp check)"""
