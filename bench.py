@@ -422,6 +422,36 @@ def measure(args, workload, world, rank, device, full):
                              "collectives": nccl, "ms_per_step_run_alone": round(sum(r["ms_total"] for r in nccl) / K, 3),
                              "note": "durations from the instrumented pass, which runs every collective synchronously; in "
                                      "the timed passes the layer-1 reduce-scatter overlaps the weight-gradient GEMM"}
+    # ---- the stated fast path (N = 1): plain single-pass TF32 dense layers, NOT the parity path ---------------
+    if world == 1 and rank == 0 and not args.no_extra:
+        from plnlp_b200 import _ops
+        with torch.no_grad():
+            model.encoder.eval()
+            h_ref = model.encoder(model.input_parts(data), data.adj_t)
+        was = _ops.GEMM_BACKEND
+        _ops.GEMM_BACKEND = "tf32c2"
+        try:
+            with torch.no_grad():
+                h_fast = model.encoder(model.input_parts(data), data.adj_t)
+            err = float((h_fast - h_ref).abs().max() / h_ref.abs().max())
+            del h_fast, h_ref
+            device_steps(W, 20)
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            device_steps(K, 21)
+            f1.record()
+            torch.cuda.synchronize()
+            fms = f0.elapsed_time(f1)
+            out["fast_path"] = {"dtype": "tf32", "value": pairs / (fms / 1e3), "unit": "pairs/s", "ms_per_step": fms / K,
+                                "max_rel_err_of_encoder_output_vs_fp32_path": err,
+                                "note": "same workload with the dense layers in plain single-pass TF32 (PLNLP_GEMM=tf32c2; "
+                                        "tcgen05 kind::tf32, one MMA per product instead of the error-compensated three). "
+                                        "Stated separately: it does not meet the 1e-5 parity bar and is never used for the "
+                                        "headline value, the parity tests or smoke()"}
+        finally:
+            _ops.GEMM_BACKEND = was
+            model.encoder.train()
     return out
 
 
@@ -493,6 +523,8 @@ def run_ours(args):
             line["nvlink"] = m["nvlink"]
         if "parity_check" in m:
             line["parity_check"] = m["parity_check"]
+        if "fast_path" in m:
+            line["fast_path"] = m["fast_path"]
         if others:
             line["configs"] = others
         line["cpu_baseline"] = cpu

@@ -304,6 +304,28 @@ int plnlp_random_walk(const int64_t* rowptr, const int64_t* col, const int64_t* 
 int plnlp_walk_pairs(const int64_t* walk, int64_t n_walks, int walk_length, int64_t* pairs, float* weight,
                      uint8_t* keep, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Graph construction (csrc/graph_build.cu): what main.py does once per run before the hot path -- ToSparseTensor
+ * (main.py:81-83), to_symmetric (main.py:109-110), set_diag + D^-1/2 A D^-1/2 (plnlp/utils.py:83-89) -- with
+ * bit-exact index arrays.  An entry is the key row * n_cols + col; sorts are stable radix sorts of (key, position)
+ * pairs; counts that depend on the data come back through device counters the caller reads once.
+ * ------------------------------------------------------------------------------------ */
+int plnlp_graph_make_keys(const int64_t* row, const int64_t* col, int64_t n, int64_t n_cols, int both, int drop_diag,
+                          int64_t* keys, int64_t* pos, void* stream);
+int plnlp_graph_diag_keys(int64_t n_diag, int64_t n_cols, int64_t* keys, int64_t* pos, int64_t pos0, void* stream);
+int64_t plnlp_graph_sort_workspace_bytes(int64_t n);
+int plnlp_graph_sort_pairs(const int64_t* keys_in, const int64_t* pos_in, int64_t n, int64_t n_rows, int64_t n_cols,
+                           int has_dead, int64_t* keys_out, int64_t* pos_out, void* workspace, int64_t workspace_bytes,
+                           void* stream);
+int64_t plnlp_graph_unique_workspace_bytes(int64_t n);
+int plnlp_graph_unique(const int64_t* keys_in, int64_t n, int64_t* keys_out, int64_t* n_out, const int64_t* pos,
+                       const float* val, int64_t n_src, float* val_out, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+int plnlp_graph_keys_to_csr(const int64_t* keys, int64_t n, int64_t n_rows, int64_t n_cols, int64_t* rowptr,
+                            int64_t* col, void* stream);
+int plnlp_graph_sym_normalize(const int64_t* rowptr, const int64_t* col, const float* val_in, int64_t n_rows, float* dis,
+                              float* val_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,14 @@ SIGNATURES = {
     "plnlp_kth_largest_f32": (c_int, [_P, _L, _L, _P, _P, _L, _P]),
     "plnlp_count_greater_f32": (c_int, [_P, _L, _P, _P, _P]),
     "plnlp_mrr_counts_f32": (c_int, [_P, _P, _L, _L, _L, _P, _P, _P]),
+    "plnlp_graph_make_keys": (c_int, [_P, _P, _L, _L, _I, _I, _P, _P, _P]),
+    "plnlp_graph_diag_keys": (c_int, [_L, _L, _P, _P, _L, _P]),
+    "plnlp_graph_sort_workspace_bytes": (c_int64, [_L]),
+    "plnlp_graph_sort_pairs": (c_int, [_P, _P, _L, _L, _L, _I, _P, _P, _P, _L, _P]),
+    "plnlp_graph_unique_workspace_bytes": (c_int64, [_L]),
+    "plnlp_graph_unique": (c_int, [_P, _L, _P, _P, _P, _P, _L, _P, _P, _L, _P]),
+    "plnlp_graph_keys_to_csr": (c_int, [_P, _L, _L, _L, _P, _P, _P]),
+    "plnlp_graph_sym_normalize": (c_int, [_P, _P, _P, _L, _P, _P, _P]),
     "plnlp_random_walk": (c_int, [_P, _P, _P, _L, _I, _P, _U, _P, _P]),
     "plnlp_walk_pairs": (c_int, [_P, _L, _I, _P, _P, _P, _P]),
 }

@@ -43,6 +43,13 @@ class CSRGraph:
             sparse_sizes = (n, n)
         M, N = int(sparse_sizes[0]), int(sparse_sizes[1])
         row, col = row.to(torch.int64), col.to(torch.int64)
+        if row.is_cuda and not is_sorted and 0 < row.numel() < 2 ** 31:
+            # hand-written path (csrc/graph_build.cu): one stable radix sort of (row * N + col, position) pairs, then
+            # row pointers and column indices straight from the sorted keys
+            keys, pos = _gb_make_keys(row, col, N, both=False, drop_diag=False)
+            keys, perm = _gb_sort(keys, pos, M, N, has_dead=False)
+            rowptr, col = _gb_keys_to_csr(keys, M, N)
+            return CSRGraph(rowptr, col, None if value is None else value[perm], (M, N))
         if not is_sorted:
             perm = torch.argsort(row * N + col, stable=True)
             row, col = row[perm], col[perm]
@@ -110,6 +117,12 @@ class CSRGraph:
         """main.py:110: union of (r,c) and (c,r), sorted, duplicates merged (values summed)."""
         N = max(self._sizes)
         row, col, value = self.coo()
+        if col.is_cuda and 0 < col.numel() < 2 ** 30 and (value is None or value.dtype == torch.float32):
+            keys, pos = _gb_make_keys(row, col, N, both=True, drop_diag=False)
+            keys, pos = _gb_sort(keys, pos, N, N, has_dead=False)
+            ukeys, uval = _gb_unique(keys, pos, value, col.numel())
+            rowptr, ucol = _gb_keys_to_csr(ukeys, N, N)
+            return CSRGraph(rowptr, ucol, uval, (N, N))
         key = torch.cat([row * N + col, col * N + row])
         if value is None:
             key = torch.unique(key)
@@ -123,6 +136,21 @@ class CSRGraph:
         """utils.py:84: drop the stored diagonal, add one unit entry per row."""
         M, N = self._sizes
         row, col, value = self.coo()
+        if col.is_cuda and 0 < col.numel() < 2 ** 31 - max(M, N):
+            # key space: stored diagonal entries get a dead key, one unit entry per row is appended, one sort
+            n, nd = col.numel(), min(M, N)
+            keys = torch.empty(n + nd, dtype=torch.int64, device=col.device)
+            pos = torch.empty(n + nd, dtype=torch.int64, device=col.device)
+            _gb_make_keys(row, col, N, both=False, drop_diag=True, out=(keys, pos))
+            _gb_diag_keys(nd, N, keys[n:], pos[n:], n)
+            n_dead = int((row == col).sum())
+            keys, pos = _gb_sort(keys, pos, M, N, has_dead=n_dead > 0)
+            keys, pos = keys[: n + nd - n_dead], pos[: n + nd - n_dead]
+            rowptr, ncol = _gb_keys_to_csr(keys, M, N)
+            nval = None
+            if value is not None:
+                nval = torch.cat([value, torch.ones(nd, dtype=value.dtype, device=col.device)])[pos]
+            return CSRGraph(rowptr, ncol, nval, (M, N))
         keep = row != col
         d = torch.arange(min(M, N), dtype=torch.int64, device=col.device)
         nval = None
@@ -162,6 +190,87 @@ class CSRGraph:
 
 
 SparseTensor = CSRGraph  # name used by main.py-style code
+
+
+# ---------------------------------------------------------------------------
+# graph-construction kernels (csrc/graph_build.cu) -- CUDA tensors only
+# ---------------------------------------------------------------------------
+def _gb_make_keys(row, col, n_cols, both, drop_diag, out=None):
+    from . import _lib
+    lib = _lib.load()
+    n = row.numel()
+    row, col = row.contiguous(), col.contiguous()
+    if out is None:
+        m = 2 * n if both else n
+        out = (torch.empty(m, dtype=torch.int64, device=row.device), torch.empty(m, dtype=torch.int64, device=row.device))
+    keys, pos = out
+    _lib.check(lib.plnlp_graph_make_keys(_lib.ptr(row), _lib.ptr(col), n, int(n_cols), int(both), int(drop_diag),
+                                         _lib.ptr(keys), _lib.ptr(pos), _lib.stream()), "plnlp_graph_make_keys")
+    return keys, pos
+
+
+def _gb_diag_keys(n_diag, n_cols, keys, pos, pos0):
+    from . import _lib
+    lib = _lib.load()
+    _lib.check(lib.plnlp_graph_diag_keys(int(n_diag), int(n_cols), _lib.ptr(keys), _lib.ptr(pos), int(pos0), _lib.stream()),
+               "plnlp_graph_diag_keys")
+
+
+def _gb_sort(keys, pos, n_rows, n_cols, has_dead):
+    from . import _lib
+    lib = _lib.load()
+    n = keys.numel()
+    ko, po = torch.empty_like(keys), torch.empty_like(pos)
+    nbytes = lib.plnlp_graph_sort_workspace_bytes(n)
+    ws = _lib.workspace.get("graph_sort", nbytes, keys.device)
+    _lib.check(lib.plnlp_graph_sort_pairs(_lib.ptr(keys), _lib.ptr(pos), n, int(n_rows), int(n_cols), int(has_dead),
+                                          _lib.ptr(ko), _lib.ptr(po), _lib.ptr(ws), nbytes, _lib.stream()),
+               "plnlp_graph_sort_pairs")
+    return ko, po
+
+
+def _gb_unique(keys, pos, value, n_src):
+    """distinct keys of a sorted key array (+ the values of equal keys summed in sorted order); one host read"""
+    from . import _lib
+    lib = _lib.load()
+    n = keys.numel()
+    uk = torch.empty_like(keys)
+    cnt = torch.empty(1, dtype=torch.int64, device=keys.device)
+    uv = None if value is None else torch.empty(n, dtype=torch.float32, device=keys.device)
+    nbytes = lib.plnlp_graph_unique_workspace_bytes(n)
+    ws = _lib.workspace.get("graph_unique", nbytes, keys.device)
+    _lib.check(lib.plnlp_graph_unique(_lib.ptr(keys), n, _lib.ptr(uk), _lib.ptr(cnt), _lib.ptr(pos),
+                                      _lib.ptr(None if value is None else value.contiguous()), int(n_src), _lib.ptr(uv),
+                                      _lib.ptr(ws), nbytes, _lib.stream()), "plnlp_graph_unique")
+    m = int(cnt.item())
+    return uk[:m], None if uv is None else uv[:m]
+
+
+def _gb_keys_to_csr(keys, n_rows, n_cols):
+    from . import _lib
+    lib = _lib.load()
+    n = keys.numel()
+    rowptr = torch.empty(n_rows + 1, dtype=torch.int64, device=keys.device)
+    col = torch.empty(n, dtype=torch.int64, device=keys.device)
+    _lib.check(lib.plnlp_graph_keys_to_csr(_lib.ptr(keys.contiguous()), n, int(n_rows), int(n_cols), _lib.ptr(rowptr),
+                                           _lib.ptr(col), _lib.stream()), "plnlp_graph_keys_to_csr")
+    return rowptr, col
+
+
+def sym_normalize(adj):
+    """D^-1/2 A D^-1/2 of a CUDA CSRGraph in one kernel pair (deg = row sums, inf -> 0): the arithmetic of
+    utils.gcn_normalization after set_diag (plnlp/utils.py:85-88)"""
+    from . import _lib
+    lib = _lib.load()
+    rowptr, col, val = adj.csr()
+    n_rows = adj.size(0)
+    dis = torch.empty(n_rows, dtype=torch.float32, device=col.device)
+    out = torch.empty(col.numel(), dtype=torch.float32, device=col.device)
+    vin = None if val is None else val.to(torch.float32).contiguous()
+    _lib.check(lib.plnlp_graph_sym_normalize(_lib.ptr(rowptr.contiguous()), _lib.ptr(col.contiguous()), _lib.ptr(vin),
+                                             n_rows, _lib.ptr(dis), _lib.ptr(out), _lib.stream()),
+               "plnlp_graph_sym_normalize")
+    return adj.set_value(out)
 
 
 # ---------------------------------------------------------------------------

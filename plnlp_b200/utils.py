@@ -96,6 +96,9 @@ def gcn_normalization(adj_t):
     """utils.py:83-89: D^-1/2 (A + I) D^-1/2 with inf -> 0, on whatever adjacency type is given
     (CSRGraph or torch_sparse.SparseTensor: only set_diag / sum / broadcast-mul are used)."""
     adj_t = adj_t.set_diag()
+    from .graph import CSRGraph, sym_normalize
+    if isinstance(adj_t, CSRGraph) and adj_t.device.type == "cuda" and adj_t.size(0) == adj_t.size(1):
+        return sym_normalize(adj_t)                      # csrc/graph_build.cu: degree + scaling in one kernel pair
     deg = adj_t.sum(dim=1).to(torch.float)
     dis = deg.pow(-0.5)
     dis[dis == float('inf')] = 0

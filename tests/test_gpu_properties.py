@@ -82,3 +82,32 @@ def test_edge_gather_kernels_any_shape(N, P, H):
     ref.index_add_(0, edges[:, 0], (da * h[edges[:, 1]]).double())
     ref.index_add_(0, edges[:, 1], (da * h[edges[:, 0]]).double())
     assert rel_err(gh, ref) < 1e-5
+
+
+@settings(max_examples=40, deadline=None)
+@given(graphs(max_n=60, max_e=300), st.booleans())
+def test_graph_build_kernels_match_oracle(g, weighted):
+    """csrc/graph_build.cu behind CSRGraph on CUDA tensors -- ToSparseTensor (stable sort, duplicates kept),
+    to_symmetric (equal keys merged, values summed), set_diag (stored diagonal dropped, unit diagonal inserted),
+    D^-1/2 A D^-1/2 -- against the oracle's restatement of torch_sparse: index arrays bit-exact, values to rounding"""
+    from plnlp_b200.graph import CSRGraph
+    from plnlp_b200.utils import gcn_normalization
+    n, ei, w = g
+
+    def same(a, b, exact_values):
+        (ra, ca, va), (rb, cb, vb) = a.csr(), b.csr()
+        assert torch.equal(ra.cpu(), rb) and torch.equal(ca.cpu(), cb)
+        assert (va is None) == (vb is None)
+        if va is not None:
+            if exact_values:
+                assert torch.equal(va.cpu(), vb)
+            elif vb.numel():
+                assert float((va.cpu() - vb).abs().max()) <= 1e-6 * max(float(vb.abs().max()), 1e-30)
+
+    a = CSRGraph.from_edge_index(ei.cuda(), w.cuda() if weighted else None, n)
+    b = sparse.to_sparse_tensor(ei, w if weighted else None, n)
+    same(a, b, True)
+    same(a.to_symmetric(), b.to_symmetric(), False)            # merged values: summation order may differ
+    same(a.set_diag(), b.set_diag(), True)
+    same(gcn_normalization(a.to_symmetric()), sparse.gcn_normalization(b.to_symmetric()), False)
+    same(gcn_normalization(CSRGraph.from_edge_index(ei.cuda(), None, n)), sparse.gcn_normalization(sparse.to_sparse_tensor(ei, None, n)), False)

@@ -16,7 +16,7 @@ from plnlp_b200.graph import CSRGraph  # noqa: E402
 from plnlp_b200.utils import gcn_normalization  # noqa: E402
 from tools.microbench import HBM, powerlaw_graph, timeit  # noqa: E402
 
-N, E, P = 2927963, 30561187, 32 * 1024 * 1024
+N, E, P = 2927963, 30561187, 30 * 1024 * 1024
 g = torch.Generator(device="cuda").manual_seed(0)
 uni = torch.randint(0, N, (P, 2), generator=g, device="cuda")
 adj = gcn_normalization(CSRGraph.from_edge_index(powerlaw_graph(N, E, 1), None, N).to_symmetric())
