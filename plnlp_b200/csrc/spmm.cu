@@ -267,14 +267,15 @@ __global__ void __launch_bounds__(256, (NB * U * VEC <= 8) ? 8 : (NB * U * VEC <
 // row the time no longer falls with the width (3.0 ms at F = 16): the bound is the rate of random DRAM row
 // fetches, not bytes.
 // ---------------------------------------------------------------------------------------------------------
-template <bool HAS_VAL, int NB>
-__global__ void __launch_bounds__(256, 8) spmm_csr_narrow_kernel(const SpmmParams p) {
+template <typename T, bool HAS_VAL, int NB>
+__global__ void __launch_bounds__(256, (sizeof(T) == 4) ? 8 : 6) spmm_csr_narrow_kernel(const SpmmParamsT<T> p) {
+    constexpr int VEC = 16 / sizeof(T);                 // elements per 16-byte load: 4 fp32 / 8 bf16
     const int lane = threadIdx.x & 31;
     const int half = lane >> 4, hl = lane & 15;
     const int64_t warp_id = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t item = warp_id * 2 + half;
     const bool valid = item < p.n_items;
-    const int f = hl * 4;
+    const int f = hl * VEC;
     const bool act = f < p.F;
 
     int beg = 0, end = 0;
@@ -282,8 +283,10 @@ __global__ void __launch_bounds__(256, 8) spmm_csr_narrow_kernel(const SpmmParam
         beg = __ldg(p.item_ptr + item);
         end = p.item_end ? __ldg(p.item_end + item) : __ldg(p.item_ptr + item + 1);
     }
-    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    const float* __restrict__ xb = p.x + f;
+    float acc[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[e] = 0.0f;
+    const T* __restrict__ xb = p.x + f;
     const int src0 = half << 4;                        // first lane of this half
     for (int base = beg; __any_sync(0xffffffffu, base < end); base += 16) {
         const int n = max(0, min(16, end - base));
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(256, 8) spmm_csr_narrow_kernel(const SpmmParam
         const int nmax = max(n, n_other);              // warp-uniform trip count
 #pragma unroll 1
         for (int j = 0; j < nmax; j += NB) {
-            float t[NB][4];
+            float t[NB][VEC];
             float vv[NB];
             bool ok[NB];
 #pragma unroll
@@ -307,17 +310,17 @@ __global__ void __launch_bounds__(256, 8) spmm_csr_narrow_kernel(const SpmmParam
                 vv[b] = HAS_VAL ? __shfl_sync(0xffffffffu, v, src0 | (jj & 15)) : 1.0f;
                 ok[b] = jj < n;
                 if (ok[b] && act) {
-                    const float4 q = __ldg(reinterpret_cast<const float4*>(xb + static_cast<int64_t>(cj) * p.ldx));
-                    t[b][0] = q.x; t[b][1] = q.y; t[b][2] = q.z; t[b][3] = q.w;
+                    load_vec<VEC>(t[b], xb + static_cast<int64_t>(cj) * p.ldx);
                 } else {
-                    t[b][0] = t[b][1] = t[b][2] = t[b][3] = 0.0f;
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) t[b][e] = 0.0f;
                 }
             }
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
                 if (ok[b]) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
+                    for (int e = 0; e < VEC; ++e)
                         acc[e] = HAS_VAL ? __fadd_rn(acc[e], __fmul_rn(vv[b], t[b][e])) : __fadd_rn(acc[e], t[b][e]);
                 }
             }
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(256, 8) spmm_csr_narrow_kernel(const SpmmParam
     if (!valid || !act) return;
     const int row = __ldg(p.item_row + item);
     const int slot = __ldg(p.item_slot + item);
-    const int live = min(4, p.F - f);                  // columns of this lane that exist
+    const int live = min(VEC, p.F - f);                // columns of this lane that exist
     if (slot >= 0) {
         float* dst = p.partial + static_cast<int64_t>(slot) * p.F + f;
         for (int e = 0; e < live; ++e) dst[e] = acc[e];
@@ -335,14 +338,14 @@ __global__ void __launch_bounds__(256, 8) spmm_csr_narrow_kernel(const SpmmParam
     if (p.row_div) {
         const float d = __ldg(p.row_div + row);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[e] = acc[e] / d;
+        for (int e = 0; e < VEC; ++e) acc[e] = acc[e] / d;
     }
     if (p.bias) {
         for (int e = 0; e < live; ++e) acc[e] += __ldg(p.bias + f + e);
     }
     if (p.relu) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[e] = fmaxf(acc[e], 0.0f);
+        for (int e = 0; e < VEC; ++e) acc[e] = fmaxf(acc[e], 0.0f);
     }
     if (p.drop_p > 0.0f) {
         const float s = 1.0f / (1.0f - p.drop_p);
@@ -351,11 +354,14 @@ __global__ void __launch_bounds__(256, 8) spmm_csr_narrow_kernel(const SpmmParam
             acc[e] = dropout_keep(p.seed, idx, p.drop_p) ? acc[e] * s : 0.0f;
         }
     }
-    float* dst = p.out + static_cast<int64_t>(row) * p.ldo + f;
-    if (live == 4 && (p.ldo % 4 == 0) && (reinterpret_cast<uintptr_t>(p.out) % 16 == 0)) {
-        *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    T* dst = p.out + static_cast<int64_t>(row) * p.ldo + f;
+    if (live == VEC && (p.ldo % VEC == 0) && (reinterpret_cast<uintptr_t>(p.out) % 16 == 0)) {
+        store_vec<VEC>(dst, acc);
     } else {
-        for (int e = 0; e < live; ++e) dst[e] = acc[e];
+        for (int e = 0; e < live; ++e) {
+            float one[1] = {acc[e]};
+            store_vec<1>(dst + e, one);
+        }
     }
 }
 
@@ -397,21 +403,24 @@ static int launch_fix(const SpmmParamsT<T>& p, cudaStream_t st) {
 }
 
 // narrow rows: see spmm_csr_narrow_kernel.  PLNLP_SPMM_NARROW=0 switches the path off (tuning / A-B runs).
-static bool narrow_ok(const SpmmParams& p) {
+template <typename T>
+static bool narrow_ok(const SpmmParamsT<T>& p) {
     static const bool on = [] { const char* e = getenv("PLNLP_SPMM_NARROW"); return !(e && e[0] == '0'); }();
-    return on && p.F <= 64 && p.x_index == nullptr && (p.ldx % 4 == 0) && p.ldx >= ((p.F + 3) / 4) * 4 &&
+    constexpr int VEC = 16 / sizeof(T);
+    return on && p.F <= 16 * VEC && p.x_index == nullptr && (p.ldx % VEC == 0) && p.ldx >= ((p.F + VEC - 1) / VEC) * VEC &&
            aligned(p.x, 16);
 }
 
-static int launch_narrow(const SpmmParams& p, cudaStream_t st) {
+template <typename T>
+static int launch_narrow(const SpmmParamsT<T>& p, cudaStream_t st) {
     static const int nb_env = [] { const char* e = getenv("PLNLP_SPMM_NB"); return e ? atoi(e) : 0; }();
     // two neighbours per half in flight: measured best (F = 64: 3.78 ms vs 3.86 at four; eight spills)
     const int nb = nb_env ? nb_env : 2;
     const dim3 grid(static_cast<unsigned>(ceil_div(ceil_div(p.n_items, 2), 8)));
 #define PLNLP_NARROW_LAUNCH(NBV)                                                          \
     do {                                                                                  \
-        if (p.val) spmm_csr_narrow_kernel<true, NBV><<<grid, 256, 0, st>>>(p);            \
-        else       spmm_csr_narrow_kernel<false, NBV><<<grid, 256, 0, st>>>(p);           \
+        if (p.val) spmm_csr_narrow_kernel<T, true, NBV><<<grid, 256, 0, st>>>(p);         \
+        else       spmm_csr_narrow_kernel<T, false, NBV><<<grid, 256, 0, st>>>(p);        \
     } while (0)
     if (nb >= 4) PLNLP_NARROW_LAUNCH(4);
     else PLNLP_NARROW_LAUNCH(2);
@@ -517,8 +526,12 @@ extern "C" int plnlp_spmm_csr_bf16(const int32_t* item_ptr, const int32_t* item_
         return (F % v == 0) && (ldx % v == 0) && (ldo % v == 0) && aligned(x, 2 * v) && aligned(out, 2 * v) &&
                (!partial || aligned(partial, v >= 4 ? 16 : 4 * v));
     };
-    // widest access that still keeps a full warp busy on one row (F / v >= 32), else the widest legal one
-    if (ok(8) && F >= 256) return dispatch_u<__nv_bfloat16, 8>(p, st);
+    // 16-byte loads as soon as a row is longer than 256 bytes (F = 200: 25 lanes of one warp; 9.54 -> 8.17 ms on the
+    // citation2-shape graph), else the widest access that still keeps a full warp busy on one row (F / v >= 32), else
+    // the widest legal one.  (The two-rows-per-warp kernel was tried for bf16 rows of <= 256 bytes and was SLOWER than
+    // this path -- F = 64: 4.88 vs 3.67 ms -- the unpacking of 8 elements per load costs more than the extra rows in
+    // flight gain; it stays an fp32 kernel.)
+    if (ok(8) && F > 128) return dispatch_u<__nv_bfloat16, 8>(p, st);
     if (ok(4) && F >= 128) return dispatch_u<__nv_bfloat16, 4>(p, st);
     if (ok(2)) return dispatch_u<__nv_bfloat16, 2>(p, st);
     if (ok(4)) return dispatch_u<__nv_bfloat16, 4>(p, st);

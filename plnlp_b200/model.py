@@ -141,12 +141,19 @@ class BaseModel(object):
         n_touch = 2 * (pos_edge.size(0) + neg_edge.size(0)) * (self.world_size if self.partitioned else 1)
         return ROW_SPARSE_GRAD and n_touch < 0.5 * self.num_nodes
 
-    def prepare_batch(self, data, pos_edge, neg_edge):
+    def _side(self):
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        return self._side_stream
+
+    def prepare_batch(self, data, pos_edge, neg_edge, wait_main=True):
         """The index work of one step that does not depend on any parameter: the sorted distinct endpoint rows of the
         batch (on a row-partitioned run: the union over ranks), the edges renumbered into that compact table, the
         row-subset SpMM plan of the last conv and the index vector of its backward.  It runs on a SIDE stream, so
         ``run_batches`` can issue it for batch i + 1 while the GPU is still busy with batch i: the host reads it needs
-        (``torch.unique``, the plan's item counts) then cost nothing on the main stream.  Returns None when the batch
+        (``torch.unique``, the plan's item counts) then cost nothing on the main stream.  ``wait_main=False``: the
+        edge tensors were themselves produced on the side stream (``run_batches``), so the side stream must NOT wait
+        for the main one -- that would queue this work behind the whole step in flight.  Returns None when the batch
         is not row-sparse or the last conv cannot restrict itself (``train_batch`` then does everything itself)."""
         if not self._sparse_rows(pos_edge, neg_edge):
             return None
@@ -156,10 +163,9 @@ class BaseModel(object):
             return None
         from . import graph
         main = torch.cuda.current_stream()
-        if getattr(self, "_side_stream", None) is None:
-            self._side_stream = torch.cuda.Stream(device=self.device)
-        side = self._side_stream
-        side.wait_stream(main)                                   # the edge tensors were produced on the main stream
+        side = self._side()
+        if wait_main:                                            # the edge tensors were produced on the main stream
+            side.wait_stream(main)
         with torch.cuda.stream(side):
             mine = torch.cat([pos_edge, neg_edge], 0)
             if self.partitioned:
@@ -337,17 +343,41 @@ class BaseModel(object):
         total_loss = torch.zeros((), dtype=torch.float64, device=self.device)
         total_examples = n_batches = 0
         it = iter(batches)
-        cur = next(it, None)
-        prep = self.prepare_batch(data, cur[0], cur[1]) if cur is not None and PREPARE_AHEAD else None
+        if not PREPARE_AHEAD:
+            for pos_edge, neg_edge, w in it:
+                loss = self.train_batch(data, pos_edge, neg_edge, num_neg, w)
+                total_loss += loss.double() * pos_edge.size(0)
+                total_examples += pos_edge.size(0)
+                n_batches += 1
+            return total_loss, total_examples, n_batches
+        main, side = torch.cuda.current_stream(), self._side()
+        side.wait_stream(main)                  # once: the epoch's edge / negative tensors exist from here on
+
+        def fetch():
+            """slice out the next batch AND prepare it, all on the side stream (nothing here waits for the step that
+            the main stream is busy with)"""
+            with torch.cuda.stream(side):
+                b = next(it, None)
+                if b is None:
+                    return None, None, None
+                for t in b:
+                    if t is not None:
+                        t.record_stream(main)
+                ready = torch.cuda.Event()
+            prep = self.prepare_batch(data, b[0], b[1], wait_main=False)
+            ready.record(side)
+            return b, prep, ready
+
+        cur, prep, ready = fetch()
         while cur is not None:
             pos_edge, neg_edge, w = cur
+            main.wait_event(ready)
             loss = self.train_batch(data, pos_edge, neg_edge, num_neg, w, prepared=prep)
-            nxt = next(it, None)
-            prep = self.prepare_batch(data, nxt[0], nxt[1]) if nxt is not None and PREPARE_AHEAD else None
+            nxt, nprep, nready = fetch()        # enqueued while the GPU works on the step above
             total_loss += loss.double() * pos_edge.size(0)
             total_examples += pos_edge.size(0)
             n_batches += 1
-            cur = nxt
+            cur, prep, ready = nxt, nprep, nready
         return total_loss, total_examples, n_batches
 
     def _train_pos(self, split_edge):

@@ -228,7 +228,7 @@ def test_prepared_batches_equal_unprepared(golden_dir, monkeypatch):
         batches = [(pos[p].cuda(), R["negs"][0][p].reshape(-1, 2).cuda(), None) for p in R["perms"][0][:3]]
         calls = []
         orig = model.prepare_batch
-        model.prepare_batch = lambda *a: (calls.append(1), orig(*a))[1]
+        model.prepare_batch = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
         tot, n_ex, n_b = model.run_batches(data, iter(batches), cfg["num_neg"])
         assert n_b == len(batches) and len(calls) == (len(batches) if ahead else 0)
         outs.append((float(tot), [p.detach().clone() for p in model.para_list]))
