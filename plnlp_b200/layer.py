@@ -218,6 +218,11 @@ class GCNConv(torch.nn.Module):
                 raise RuntimeError("out_rows: this layer / adjacency cannot restrict its output rows")
             from . import parallel
             if isinstance(adj_t, parallel.ShardedAdj):
+                if parallel.RESTRICT_COMBINE == "rs":
+                    # every rank maps its 1 / R of the requested rows and the results are all-gathered
+                    aggs = [parallel.pspmm_rows(adj_t, p, out_rows, reduce="sum", sharded=True) for p in parts]
+                    y = _ops.fused_linear(aggs, ws, self.bias, act, drop_p, seed)
+                    return parallel.gather_rows(y, adj_t.group, tag="restricted rows")[: out_rows.numel()]
                 aggs = [parallel.pspmm_rows(adj_t, p, out_rows, reduce="sum") for p in parts]
             else:
                 aggs = [_ops.spmm_rows(adj_t, p, out_rows, reduce="sum") for p in parts]

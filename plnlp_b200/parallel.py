@@ -30,6 +30,9 @@ EXCHANGE = os.environ.get("PLNLP_EXCHANGE", "rows")
 # row-partitioned run: the last conv computes only the rows some rank's edge batch reads (DESIGN.md 4a item 3 for
 # the partitioned encoder, ``pspmm_rows``).  PLNLP_PARTITIONED_RESTRICT=0 switches it off.
 RESTRICT_LAST = os.environ.get("PLNLP_PARTITIONED_RESTRICT", "1") != "0"
+# how the partial rows of the restricted last conv are combined: "rs" = reduce-scatter, linear map on 1/R of the rows,
+# all-gather of the result; "ar" = all-reduce, every rank maps all rows
+RESTRICT_COMBINE = os.environ.get("PLNLP_RESTRICT_COMBINE", "rs")
 
 
 def world():
@@ -68,7 +71,7 @@ def allreduce_grads(params, group=None, average=False):
         off += g.numel()
 
 
-def _reduce_scatter_rows(full, blk, group=None, async_op=False):
+def _reduce_scatter_rows(full, blk, group=None, async_op=False, name="nccl reduce_scatter (rows)"):
     """sum ``full`` [R*blk, F] over ranks and return this rank's [blk, F] block.  ``async_op``: -> (block, wait)
     where ``wait()`` must be called before the block is read; the collective then runs beside whatever the caller
     enqueues in between."""
@@ -85,19 +88,19 @@ def _reduce_scatter_rows(full, blk, group=None, async_op=False):
         if async_op and not profiling.enabled():
             work = dist.reduce_scatter_tensor(out, full, group=group, async_op=True)
         else:
-            with profiling.span("nccl reduce_scatter (rows)", (ws - 1) * out.numel() * 4, 0):
+            with profiling.span(name, (ws - 1) * out.numel() * 4, 0):
                 dist.reduce_scatter_tensor(out, full, group=group)
     if async_op:
         return out, ((lambda: work.wait()) if work is not None else (lambda: None))
     return out
 
 
-def all_gather_rows(x_local, group=None):
+def all_gather_rows(x_local, group=None, name="nccl all_gather (rows)"):
     """[blk, F] row block -> [R*blk, F] (no autograd)"""
     _, ws = world()
     full = torch.empty(ws * x_local.size(0), x_local.size(1), dtype=x_local.dtype, device=x_local.device)
     from . import profiling
-    with profiling.span("nccl all_gather (rows)", (ws - 1) * x_local.numel() * 4, 0):
+    with profiling.span(name, (ws - 1) * x_local.numel() * 4, 0):
         dist.all_gather_into_tensor(full, x_local.contiguous(), group=group)
     return full
 
@@ -107,17 +110,17 @@ class GatherRows(torch.autograd.Function):
     Backward: reduce-scatter of the incoming gradient."""
 
     @staticmethod
-    def forward(ctx, x_local, group):
-        ctx.group, ctx.blk = group, x_local.size(0)
-        return all_gather_rows(x_local, group)
+    def forward(ctx, x_local, group, tag):
+        ctx.group, ctx.blk, ctx.tag = group, x_local.size(0), tag
+        return all_gather_rows(x_local, group, name=f"nccl all_gather ({tag})")
 
     @staticmethod
     def backward(ctx, g):
-        return _reduce_scatter_rows(g.contiguous(), ctx.blk, ctx.group), None
+        return _reduce_scatter_rows(g.contiguous(), ctx.blk, ctx.group, name=f"nccl reduce_scatter ({ctx.tag} grads)"), None, None
 
 
-def gather_rows(x_local, group=None):
-    return GatherRows.apply(x_local, group)
+def gather_rows(x_local, group=None, tag="rows"):
+    return GatherRows.apply(x_local, group, tag)
 
 
 class FetchRows(torch.autograd.Function):
@@ -211,6 +214,31 @@ def all_reduce_sum(x, group=None):
     return AllReduceSum.apply(x, group)
 
 
+class ReduceScatterSum(torch.autograd.Function):
+    """x [T, F] (a partial value of a replicated quantity on every rank) -> this rank's block of
+    ``ceil(T / R)`` rows of the SUM over ranks (zero rows past T).  Backward: the blocks' gradients are all-gathered
+    -- every rank's partial value feeds every block."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        _, ws = world()
+        T = x.size(0)
+        tb = (T + ws - 1) // ws
+        ctx.group, ctx.T = group, T
+        if tb * ws != T:
+            x = torch.cat([x, x.new_zeros(tb * ws - T, x.size(1))], 0)
+        return _reduce_scatter_rows(x.contiguous(), tb, group, name="nccl reduce_scatter (restricted rows)")
+
+    @staticmethod
+    def backward(ctx, g):
+        full = all_gather_rows(g.contiguous(), ctx.group, name="nccl all_gather (restricted row grads)")
+        return full[: ctx.T], None
+
+
+def reduce_scatter_sum(x, group=None):
+    return ReduceScatterSum.apply(x, group)
+
+
 def union_ids(ids_local, group=None):
     """sorted distinct union over ranks of every rank's id list (all ranks must pass the same count -- the
     data-parallel edge batches have equal sizes) -> the same tensor on every rank.  One all-gather of the raw ids;
@@ -292,7 +320,7 @@ def pad_rows(x, blk):
     return torch.cat([x, pad], 0)
 
 
-def pspmm_rows(sadj, x_local, rows, reduce="sum", local_op=None):
+def pspmm_rows(sadj, x_local, rows, reduce="sum", local_op=None, sharded=False):
     """(A @ X)[rows] on a row-partitioned X, for GLOBAL row ids ``rows`` (sorted, distinct, the SAME list on every
     rank -- ``union_ids``), returned in full, compactly, on every rank.
 
@@ -303,13 +331,18 @@ def pspmm_rows(sadj, x_local, rows, reduce="sum", local_op=None):
     view of its block of A^T -- and the [len(rows), F] partial results are summed over ranks (all-reduce:
     ~0.23 GB).  Backward: all-reduce of the compact gradient, then ``A[rows, lo:hi]^T @ g`` with the compact
     gradient as a row-sparse operand of the rank's own row block.  ``local_op(adj, x, rows, reduce)`` defaults to
-    the CUDA row-subset SpMM (``_ops.spmm_rows``)."""
+    the CUDA row-subset SpMM (``_ops.spmm_rows``).  ``sharded``: see below."""
     if reduce not in ("sum", "add"):
         raise NotImplementedError("row-restricted partitioned products are sums (GCNConv)")
     if local_op is None:
         from . import _ops
         local_op = _ops.spmm_rows
     partial = local_op(sadj.cols(), pad_rows(x_local, sadj.blk), rows, "sum")
+    if sharded:
+        # -> this rank's ceil(T / R) rows of the sum only: the caller runs its row-wise work (the conv's linear map)
+        # on 1 / R of the rows and all-gathers the result (``gather_rows``) -- same bytes on the wire as the
+        # all-reduce, the dense layer and both of its backward GEMMs R times smaller
+        return reduce_scatter_sum(partial, sadj.group)
     return all_reduce_sum(partial, sadj.group)
 
 

@@ -65,6 +65,7 @@ def _worker(rank, ws, port, ret):
         # ---- one training step, every way the partitioned model can take it
         adj2 = CSRGraph(*adj.csr(), (N, N))                     # fresh object: no cached dense form
         cases = {"restricted": dict(force_sparse=True),          # union of endpoint rows, column-block partial products
+                 "restricted_allreduce": dict(force_sparse=True),    # ... combined by all-reduce instead of RS + AG
                  "rows": dict(force_sparse=False),               # full last conv + compact endpoint-row exchange
                  "allgather": dict(force_sparse=False),          # full last conv + whole-matrix all-gather
                  "sparse_grad_only": dict(force_sparse=True),    # full last conv, row-sparse backward
@@ -72,10 +73,11 @@ def _worker(rank, ws, port, ret):
         for name, kw in cases.items():
             parallel.EXCHANGE = "allgather" if name == "allgather" else "rows"
             parallel.RESTRICT_LAST = name != "sparse_grad_only"
+            parallel.RESTRICT_COMBINE = "ar" if name == "restricted_allreduce" else "rs"
             errs = selfcheck.partitioned_step(rank, ws, dev, adj=adj2, feats=FEATS, emb=EMB, hid=HID, batch=BATCH,
                                               k=K, keep=True, **kw)
             out[name] = errs
-        parallel.EXCHANGE, parallel.RESTRICT_LAST = "rows", True
+        parallel.EXCHANGE, parallel.RESTRICT_LAST, parallel.RESTRICT_COMBINE = "rows", True, "rs"
         assert "_plnlp_agg_buffer" in adj2.__dict__
         ret[rank] = out
     finally:

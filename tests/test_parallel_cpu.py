@@ -159,6 +159,11 @@ def _restricted_worker(rank, world_size, port, N, F, symmetric, ret):
             local_op=lambda adj, x, r, reduce: sparse.matmul(adj.base.t(), x, reduce)[r])
         want_rows = sparse.matmul(full, X, "sum")[ids]
         assert rows.shape == (ids.numel(), F) and rel_err(rows.detach(), want_rows) < 1e-6
+        # the sharded form (reduce-scatter; a row-wise map on 1 / R of the rows; all-gather) gives the same rows
+        shard = parallel.pspmm_rows(sadj, x_local.detach(), ids, "sum", sharded=True,
+                                    local_op=lambda adj, x, r, reduce: sparse.matmul(adj.base.t(), x, reduce)[r])
+        back = parallel.gather_rows(shard * 2.0, tag="restricted rows")[: ids.numel()]
+        assert rel_err(back, 2.0 * want_rows) < 1e-6
         # each rank's loss reads its own endpoints only
         pos = torch.searchsorted(ids, mine)
         gout = torch.randn(mine.numel(), F, generator=gr)
