@@ -318,6 +318,13 @@ def measure(args, workload, world, rank, device, full):
     clk.stop()
     ms = max_over_ranks(e0.elapsed_time(e1))
     out["launches"] = _lib.launch_count() - l0
+    # host side of the same K steps: how long python + the launch calls take to ENQUEUE them (no device wait).  When
+    # this approaches ms_per_step the run is launch-bound, not kernel-bound
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    device_steps(K, 4)
+    out["host_enqueue_ms_per_step"] = max_over_ranks((time.perf_counter() - t0) * 1e3 / K)
+    barrier()
     pairs = K * Bl * (1 + k) * world
     out.update(ms=ms, pairs=pairs, value=pairs / (ms / 1e3), clocks=clk.summary(), Bl=Bl)
     if not full:
@@ -359,17 +366,17 @@ def measure(args, workload, world, rank, device, full):
                           "steps, D2H of the epoch loss (one 8-byte read per call, not per step)"}
 
     # ---- instrumented pass: per-kernel durations (rank 0) ------------------------------------
-    # every rank runs the pass (its steps contain collectives); only rank 0 records events
-    if rank == 0:
-        profiling.enable()
+    # every rank runs the pass instrumented (identical control flow on every rank: the instrumented form runs the
+    # collectives synchronously); only rank 0 reports
+    profiling.enable()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
     device_steps(K, 2)
     p1.record()
     barrier()
+    stats = profiling.disable()
     if rank == 0:
         pk = peaks()
-        stats = profiling.disable()
         ours = sum(s["ms"] for s in stats.values())
         stats["(torch plumbing: adam, clip, unique / sort, sampler glue, launch gaps)"] = {
             "n": 1, "ms": max(p0.elapsed_time(p1) - ours, 0.0), "bytes": 0, "flops": 0}
@@ -378,7 +385,7 @@ def measure(args, workload, world, rank, device, full):
         for name, s in sorted(stats.items(), key=lambda kv: -kv[1]["ms"]):
             rec = {"kernel": name, "launches": s["n"], "ms_total": round(s["ms"], 3),
                    "share": round(s["ms"] / total, 4), "avg_ms": round(s["ms"] / s["n"], 4)}
-            if name.startswith("nccl"):
+            if name.startswith(("nccl", "p2p")):
                 if s["bytes"]:
                     rec["recv_gbs_per_rank"] = round(s["bytes"] / s["ms"] / 1e6, 1)
                     rec["frac_nvlink"] = round(s["bytes"] / s["ms"] / 1e6 / NVLINK_PEER_GBS, 4)
@@ -392,7 +399,7 @@ def measure(args, workload, world, rank, device, full):
             kernels.append(rec)
         out["kernels"] = kernels
         # dominant kernel of OURS (collectives and torch glue have their own lines)
-        top = next(r for r in kernels if not r["kernel"].startswith(("(", "nccl", "torch")))
+        top = next(r for r in kernels if not r["kernel"].startswith(("(", "nccl", "p2p", "torch")))
         if "achieved_gbs" in top or "achieved_tflops" not in top:
             roof = {"kernel": top["kernel"], "bound": "hbm", "achieved": top.get("achieved_gbs"),
                     "peak": pk["hbm"], "unit": "GB/s", "frac": top.get("frac_hbm"), "traffic": None,
@@ -416,7 +423,7 @@ def measure(args, workload, world, rank, device, full):
             roof["spmm_note"] = ("source matrix exceeds L2" if src_bytes >= 126e6 else
                                  "source matrix is L2-resident: effective bandwidth of the gather model")
         out["roofline"] = roof
-        nccl = [r for r in kernels if r["kernel"].startswith("nccl")]
+        nccl = [r for r in kernels if r["kernel"].startswith(("nccl", "p2p"))]
         if nccl:
             out["nvlink"] = {"peak_gbs_per_direction": NVLINK_PEER_GBS, "peak_source": "measured peer copy (B200_PROFILING.md)",
                              "collectives": nccl, "ms_per_step_run_alone": round(sum(r["ms_total"] for r in nccl) / K, 3),
@@ -518,6 +525,7 @@ def run_ours(args):
                           "seconds": ms / K * EPOCH_BATCHES[args.workload] / 1e3,
                           "note": "ms_per_step x the batches of one full epoch (SURVEY.md 8d)"},
                 "clocks": m["clocks"], "e2e": m["e2e"], "gpu_launches": int(m["launches"]),
+                "host_enqueue_ms_per_step": round(m["host_enqueue_ms_per_step"], 3),
                 "roofline": m.get("roofline"), "kernels": m.get("kernels", [])[:14]}
         if "nvlink" in m:
             line["nvlink"] = m["nvlink"]

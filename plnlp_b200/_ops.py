@@ -609,11 +609,36 @@ def aggregate_into(adj, x, out):
     return spmm_raw(st.fwd, x, use_val=st.has_value, div_rows=False, out=out)
 
 
+# row-partitioned, symmetric adjacency: A^T g as all-gather(g) + row-block SpMM instead of transposed SpMM + reduce-scatter
+AGG_T_BY_GATHER = os.environ.get("PLNLP_AGG_T", "gather") == "gather"
+
+
+class _Deferred:
+    """a result that is only computed when asked for (after communication that was started earlier has landed)"""
+
+    def __init__(self, fn):
+        self.fn = fn
+
+
 def aggregate_t(adj, g, sparse_rows=False, async_op=False):
     """A^T @ g through the raw kernel; row-partitioned: the transposed product over all columns is
     reduce-scattered to the owners of the rows.  ``sparse_rows``: most rows of g are exactly zero -- measure
     which (one pass over g) and gather only the live ones.  ``async_op``: -> (result, wait); on a row-partitioned
     adjacency the reduce-scatter is then in flight until ``wait()`` is called."""
+    if isinstance(adj, parallel.ShardedAdj) and adj.symmetric and AGG_T_BY_GATHER:
+        # A == A^T: this rank's rows of A^T g are A[rows, :] @ g -- ALL-GATHER g (async: the caller's weight-gradient
+        # GEMM runs meanwhile) and multiply with the row block the forward pass uses.  Same bytes on the wire as the
+        # reduce-scatter of the transposed product, but a gather (pull over peer memory, no reduction), one CSR
+        # structure for both directions, and every row accumulated in the single-GPU order.
+        st = structure_of(adj.local)
+        full, wait = parallel.all_gather_rows(parallel.pad_rows(g, adj.blk), adj.group, tag="grad rows", async_op=True,
+                                              name="nccl all_gather (grad rows)")
+
+        def finish():
+            wait()
+            xi = row_nonzero_index_raw(full) if sparse_rows else None
+            return spmm_raw(st.fwd, full, use_val=st.has_value, div_rows=False, x_index=xi)
+        return (_Deferred(finish), None) if async_op else finish()
     x_index = row_nonzero_index_raw(g) if sparse_rows else None
     if isinstance(adj, parallel.ShardedAdj):
         st = structure_of(adj.local)
@@ -667,7 +692,7 @@ class AggLinear(torch.autograd.Function):
                 continue
             gu = gemm_raw(g, W[:, off:off + x.size(1)], C=_rows_for_spmm(g.size(0), x.size(1), g.device))   # d(A x_i) = dY W_i
             gx, wait = aggregate_t(ctx.adj, gu, ctx.sparse_grad, async_op=True)                 # A^T .
-            gxs.append(gx[: x.size(0)])
+            gxs.append(gx if isinstance(gx, _Deferred) else gx[: x.size(0)])
             waits.append(wait)
         gW = gb = None
         ext = ctx.holder.get("ext")
@@ -680,7 +705,9 @@ class AggLinear(torch.autograd.Function):
             gW = gemm_raw(g, buf, transa=True) if ctx.needs_input_grad[0] else None         # dW = dY^T [A x]
             gb = colsum_raw(g) if want_b else None
         for wait in waits:
-            wait()
+            if wait is not None:
+                wait()
+        gxs = [gx.fn()[: x.size(0)] if isinstance(gx, _Deferred) else gx for gx, x in zip(gxs, xs)]
         return (gW, gb, None, None, None, None, None, None, None, None, *gxs)
 
 

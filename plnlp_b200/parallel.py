@@ -95,14 +95,98 @@ def _reduce_scatter_rows(full, blk, group=None, async_op=False, name="nccl reduc
     return out
 
 
-def all_gather_rows(x_local, group=None, name="nccl all_gather (rows)"):
-    """[blk, F] row block -> [R*blk, F] (no autograd)"""
+# ---------------------------------------------------------------------------
+# all-gather of row blocks over NVLink peer memory
+# ---------------------------------------------------------------------------
+# "p2p" (default where it works): every rank publishes its block in a symmetric-memory buffer (torch.distributed.
+# _symmetric_memory: the same allocation mapped into every rank of the box) and PULLS the R-1 other blocks with
+# peer-to-peer copies over NVLink -- copy engines, no SMs, one device-side barrier before and one after.  Measured
+# against NCCL's all_gather for the [N / R, 50] embedding blocks: see DESIGN.md section 6.  "nccl": always NCCL.
+ALLGATHER = os.environ.get("PLNLP_ALLGATHER", "p2p")
+BARRIER_TIMEOUT_MS = int(os.environ.get("PLNLP_P2P_TIMEOUT_MS", "20000"))   # a lost peer traps instead of hanging
+_SYMM = {}          # (group name, tag) -> (symmetric-memory handle, capacity in bytes)
+_SYMM_BROKEN = []   # first failure: remember and use NCCL from then on
+
+
+def _symm_handle(group, tag, nbytes, device):
+    import torch.distributed._symmetric_memory as sm
+    pg = group if group is not None else dist.group.WORLD
+    gname = pg.group_name
+    key = (gname, tag)
+    hit = _SYMM.get(key)
+    if hit is None or hit[1] < nbytes:
+        try:
+            sm.enable_symm_mem_for_group(gname)
+        except Exception:
+            pass                                   # newer torch enables groups implicitly
+        cap = max(int(nbytes * 1.25), 1 << 20)
+        t = sm.empty(cap, dtype=torch.uint8, device=device)
+        hit = _SYMM[key] = (sm.rendezvous(t, gname), cap, t)
+    return hit[0]
+
+
+def _p2p_all_gather(x_local, group, tag, full):
+    """pull-based all-gather on the CURRENT stream; x_local [blk, F] contiguous, full [R*blk, F]"""
+    rank, ws = world()
+    hdl = _symm_handle(group, tag, x_local.numel() * x_local.element_size(), x_local.device)
+    mine = hdl.get_buffer(rank, x_local.shape, x_local.dtype)
+    mine.copy_(x_local)                            # publish (a device-to-device copy of one block)
+    blk = x_local.size(0)
+    full[rank * blk:(rank + 1) * blk].copy_(x_local)
+    hdl.barrier(channel=0, timeout_ms=BARRIER_TIMEOUT_MS)      # every rank's block is in place
+    for step in range(1, ws):
+        r = (rank - step) % ws                     # each rank starts at a different peer
+        full[r * blk:(r + 1) * blk].copy_(hdl.get_buffer(r, x_local.shape, x_local.dtype))
+    hdl.barrier(channel=0, timeout_ms=BARRIER_TIMEOUT_MS)      # nobody republishes before every peer has read
+    return full
+
+
+def all_gather_rows(x_local, group=None, name="nccl all_gather (rows)", tag="rows", async_op=False):
+    """[blk, F] row block -> [R*blk, F] (no autograd).  ``async_op``: -> (full, wait) -- the gather runs on a side
+    stream and ``wait()`` makes the current stream wait for it."""
     _, ws = world()
+    x_local = x_local.contiguous()
     full = torch.empty(ws * x_local.size(0), x_local.size(1), dtype=x_local.dtype, device=x_local.device)
     from . import profiling
-    with profiling.span(name, (ws - 1) * x_local.numel() * 4, 0):
-        dist.all_gather_into_tensor(full, x_local.contiguous(), group=group)
-    return full
+    use_p2p = (ALLGATHER == "p2p" and not _SYMM_BROKEN and x_local.is_cuda and ws > 1
+               and dist.get_backend(group) == "nccl")
+    nbytes = (ws - 1) * x_local.numel() * 4
+    if use_p2p:
+        try:
+            if async_op and not profiling.enabled():
+                cur = torch.cuda.current_stream()
+                side = _side_stream(x_local.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    # (the SAME buffer / barrier as the synchronous form: ranks may differ in which form they take --
+                    # bench.py instruments rank 0 only -- and must still meet at one barrier)
+                    _p2p_all_gather(x_local, group, tag, full)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                x_local.record_stream(side)
+                full.record_stream(side)
+                return full, (lambda: torch.cuda.current_stream().wait_event(ev))
+            with profiling.span(name.replace("nccl", "p2p"), nbytes, 0):
+                _p2p_all_gather(x_local, group, tag, full)
+            return (full, (lambda: None)) if async_op else full
+        except Exception as ex:                    # no symmetric memory on this box / torch: NCCL from now on
+            _SYMM_BROKEN.append(repr(ex))
+    if async_op and not profiling.enabled():
+        work = dist.all_gather_into_tensor(full, x_local, group=group, async_op=True)
+        return full, (lambda: work.wait())
+    with profiling.span(name, nbytes, 0):
+        dist.all_gather_into_tensor(full, x_local, group=group)
+    return (full, (lambda: None)) if async_op else full
+
+
+_SIDE = {}
+
+
+def _side_stream(device):
+    s = _SIDE.get(device)
+    if s is None:
+        s = _SIDE[device] = torch.cuda.Stream(device=device)
+    return s
 
 
 class GatherRows(torch.autograd.Function):
@@ -260,6 +344,7 @@ class ShardedAdj:
     def __init__(self, local_adj, n_global, rank, world_size, group=None, local_t=None):
         self.local = local_adj                  # CSRGraph-like, shape [blk, R*blk]
         self.local_t = local_t if local_t is not None else local_adj
+        self.symmetric = local_t is None        # A == A^T entry for entry (see shard_graph)
         self.n_global, self.rank, self.world_size, self.group = n_global, rank, world_size, group
         self.blk = block_size(n_global, world_size)
         self._cols = None
