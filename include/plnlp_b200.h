@@ -326,6 +326,15 @@ int plnlp_graph_keys_to_csr(const int64_t* keys, int64_t n, int64_t n_rows, int6
 int plnlp_graph_sym_normalize(const int64_t* rowptr, const int64_t* col, const float* val_in, int64_t n_rows, float* dis,
                               float* val_out, void* stream);
 
+/* Row-subset SpMM plan of the last conv (graph.py build_subset_plan; the rows a batch reads, model.py:152-156):
+ * count kernel -> caller's inclusive prefix sums of n_it / multi / n_slot -> fill kernel.  One host read per plan. */
+int plnlp_subset_plan_count(const int64_t* rowptr, const int64_t* rows, int64_t T, int chunk, int64_t* n_it,
+                            int64_t* multi, int64_t* n_slot, int64_t* len, void* stream);
+int plnlp_subset_plan_fill(const int64_t* rowptr, const int64_t* rows, int64_t T, int chunk, const int64_t* first,
+                           const int64_t* fixi, const int64_t* slot, const int64_t* n_it, int32_t* item_ptr,
+                           int32_t* item_end, int32_t* item_row, int32_t* item_slot, int32_t* fix_ptr,
+                           int32_t* fix_row, float* row_cnt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

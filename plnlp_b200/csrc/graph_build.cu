@@ -256,3 +256,92 @@ extern "C" int plnlp_graph_sym_normalize(const int64_t* rowptr, const int64_t* c
     PLNLP_LAUNCH_CHECK();
     return 0;
 }
+
+// ---- row-subset SpMM plan (plnlp_b200/graph.py build_subset_plan) -----------------------------------------------------
+// The last conv computes only the rows the batch reads (model.py:152-156): per step, a plan for T selected rows of
+// the adjacency.  Two kernels around three prefix sums instead of ~25 torch index ops and three host reads:
+//   count: n_it[t] = max(1, ceil(len_t / chunk)) items for row rows[t]; multi[t] = n_it[t] > 1
+//   (caller: exclusive prefix sums of n_it -> first, of multi -> fix index, of multi ? n_it : 0 -> partial slot base)
+//   fill : item arrays, fix arrays, mean divisors
+namespace plnlp {
+namespace {
+
+__global__ void __launch_bounds__(256) subset_count_kernel(const int64_t* __restrict__ rowptr, const int64_t* __restrict__ rows,
+                                                           int64_t T, int chunk, int64_t* __restrict__ n_it,
+                                                           int64_t* __restrict__ multi, int64_t* __restrict__ n_slot,
+                                                           int64_t* __restrict__ len_out) {
+    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int64_t r = rows[t];
+    const int64_t len = rowptr[r + 1] - rowptr[r];
+    int64_t n = (len + chunk - 1) / chunk;
+    if (n < 1) n = 1;
+    n_it[t] = n;
+    multi[t] = n > 1 ? 1 : 0;
+    n_slot[t] = n > 1 ? n : 0;
+    len_out[t] = len;
+}
+
+__global__ void __launch_bounds__(256) subset_fill_kernel(const int64_t* __restrict__ rowptr, const int64_t* __restrict__ rows,
+                                                          int64_t T, int chunk, const int64_t* __restrict__ first /* inclusive */,
+                                                          const int64_t* __restrict__ fixi /* inclusive */,
+                                                          const int64_t* __restrict__ slot /* inclusive */,
+                                                          const int64_t* __restrict__ n_it, int32_t* __restrict__ item_ptr,
+                                                          int32_t* __restrict__ item_end, int32_t* __restrict__ item_row,
+                                                          int32_t* __restrict__ item_slot, int32_t* __restrict__ fix_ptr,
+                                                          int32_t* __restrict__ fix_row, float* __restrict__ row_cnt) {
+    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int64_t r = rows[t];
+    const int64_t beg = rowptr[r], end = rowptr[r + 1];
+    const int64_t n = n_it[t];
+    const int64_t i0 = first[t] - n;                       // exclusive prefix
+    const bool multi = n > 1;
+    const int64_t s0 = multi ? slot[t] - n : -1;
+    for (int64_t k = 0; k < n; ++k) {
+        const int64_t b = beg + k * chunk;
+        const int64_t e = b + chunk < end ? b + chunk : end;
+        item_ptr[i0 + k] = static_cast<int32_t>(b);
+        item_end[i0 + k] = static_cast<int32_t>(e);
+        item_row[i0 + k] = static_cast<int32_t>(t);
+        item_slot[i0 + k] = multi ? static_cast<int32_t>(s0 + k) : -1;
+    }
+    if (multi) {
+        const int64_t j = fixi[t] - 1;
+        fix_row[j] = static_cast<int32_t>(t);
+        fix_ptr[j] = static_cast<int32_t>(s0);
+        // the closing entry fix_ptr[n_fix] = n_partial is written by whoever owns the last multi row
+        fix_ptr[j + 1] = static_cast<int32_t>(s0 + n);
+    }
+    const int64_t len = end - beg;
+    row_cnt[t] = static_cast<float>(len > 1 ? len : 1);
+}
+
+}  // namespace
+}  // namespace plnlp
+
+extern "C" int plnlp_subset_plan_count(const int64_t* rowptr, const int64_t* rows, int64_t T, int chunk, int64_t* n_it,
+                                       int64_t* multi, int64_t* n_slot, int64_t* len, void* stream) {
+    PLNLP_REQUIRE(T >= 0 && chunk > 0, PLNLP_E_SIZE);
+    if (T == 0) return 0;
+    PLNLP_REQUIRE(rowptr && rows && n_it && multi && n_slot && len, PLNLP_E_NULL);
+    plnlp::subset_count_kernel<<<static_cast<unsigned>(plnlp::ceil_div(T, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        rowptr, rows, T, chunk, n_it, multi, n_slot, len);
+    PLNLP_LAUNCH_CHECK();
+    return 0;
+}
+
+// first / fixi / slot: INCLUSIVE prefix sums of n_it / multi / n_slot.  fix_ptr has n_fix + 1 entries (at least 1).
+extern "C" int plnlp_subset_plan_fill(const int64_t* rowptr, const int64_t* rows, int64_t T, int chunk, const int64_t* first,
+                                      const int64_t* fixi, const int64_t* slot, const int64_t* n_it, int32_t* item_ptr,
+                                      int32_t* item_end, int32_t* item_row, int32_t* item_slot, int32_t* fix_ptr,
+                                      int32_t* fix_row, float* row_cnt, void* stream) {
+    PLNLP_REQUIRE(T >= 0 && chunk > 0, PLNLP_E_SIZE);
+    if (T == 0) return 0;
+    PLNLP_REQUIRE(rowptr && rows && first && fixi && slot && n_it && item_ptr && item_end && item_row && item_slot &&
+                      fix_ptr && row_cnt, PLNLP_E_NULL);
+    plnlp::subset_fill_kernel<<<static_cast<unsigned>(plnlp::ceil_div(T, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        rowptr, rows, T, chunk, first, fixi, slot, n_it, item_ptr, item_end, item_row, item_slot, fix_ptr, fix_row, row_cnt);
+    PLNLP_LAUNCH_CHECK();
+    return 0;
+}

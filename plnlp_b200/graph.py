@@ -348,6 +348,8 @@ def build_subset_plan(parent, rowptr, rows):
     dev = rows.device
     T = rows.numel()
     chunk = parent.chunk
+    if rows.is_cuda and T > 0:
+        return _build_subset_plan_cuda(parent, rowptr, rows)
     start = rowptr[rows]
     length = rowptr[rows + 1] - start
     n_it = torch.clamp((length + chunk - 1) // chunk, min=1)
@@ -386,6 +388,36 @@ def build_subset_plan(parent, rowptr, rows):
 def plan_tensors(plan):
     """the device tensors a plan owns or references (for stream bookkeeping)"""
     return [t for t in (getattr(plan, s) for s in SpmmPlan.__slots__) if isinstance(t, torch.Tensor)]
+
+
+def _build_subset_plan_cuda(parent, rowptr, rows):
+    """``build_subset_plan`` on the device (csrc/graph_build.cu): two kernels around one stacked prefix sum, ONE host
+    read (item count, split-row count, partial-slot count, stored entries)"""
+    from . import _lib
+    lib = _lib.load()
+    dev, T, chunk = rows.device, rows.numel(), parent.chunk
+    rows = rows.contiguous()
+    cnt = torch.empty(4, T, dtype=torch.int64, device=dev)          # n_it, multi, n_slot, len
+    _lib.check(lib.plnlp_subset_plan_count(_lib.ptr(rowptr), _lib.ptr(rows), T, chunk, _lib.ptr(cnt[0]), _lib.ptr(cnt[1]),
+                                           _lib.ptr(cnt[2]), _lib.ptr(cnt[3]), _lib.stream()), "plnlp_subset_plan_count")
+    cum = torch.cumsum(cnt, 1)                                       # inclusive, all four at once
+    n_items, n_fix, n_partial, nnz = cum[:, -1].tolist()             # the one host read
+    p = SpmmPlan()
+    p.n_rows, p.n_cols, p.chunk = int(T), parent.n_cols, chunk
+    p.col, p.val = parent.col, parent.val
+    i32 = lambda n: torch.empty(max(n, 1), dtype=torch.int32, device=dev)  # noqa: E731
+    p.item_ptr, p.item_end, p.item_row, p.item_slot = i32(n_items), i32(n_items), i32(n_items), i32(n_items)
+    p.fix_ptr, p.fix_row = torch.zeros(n_fix + 1, dtype=torch.int32, device=dev), i32(n_fix)
+    p.row_cnt = torch.empty(T, dtype=torch.float32, device=dev)
+    _lib.check(lib.plnlp_subset_plan_fill(_lib.ptr(rowptr), _lib.ptr(rows), T, chunk, _lib.ptr(cum[0]), _lib.ptr(cum[1]),
+                                          _lib.ptr(cum[2]), _lib.ptr(cnt[0]), _lib.ptr(p.item_ptr), _lib.ptr(p.item_end),
+                                          _lib.ptr(p.item_row), _lib.ptr(p.item_slot), _lib.ptr(p.fix_ptr),
+                                          _lib.ptr(p.fix_row), _lib.ptr(p.row_cnt), _lib.stream()), "plnlp_subset_plan_fill")
+    p.item_ptr, p.item_end = p.item_ptr[:n_items], p.item_end[:n_items]
+    p.item_row, p.item_slot = p.item_row[:n_items], p.item_slot[:n_items]
+    p.fix_row = p.fix_row[:n_fix]
+    p.n_items, p.subset, p.n_fix, p.n_partial, p.nnz = int(n_items), True, int(n_fix), int(n_partial), int(nnz)
+    return p
 
 
 class Structure:

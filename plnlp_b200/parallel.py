@@ -129,16 +129,24 @@ def _p2p_all_gather(x_local, group, tag, full):
     """pull-based all-gather on the CURRENT stream; x_local [blk, F] contiguous, full [R*blk, F]"""
     rank, ws = world()
     hdl = _symm_handle(group, tag, x_local.numel() * x_local.element_size(), x_local.device)
-    mine = hdl.get_buffer(rank, x_local.shape, x_local.dtype)
-    mine.copy_(x_local)                            # publish (a device-to-device copy of one block)
+    key = (id(hdl), tuple(x_local.shape), x_local.dtype)
+    peers = _PEER_VIEWS.get(key)
+    if peers is None:                              # tensor views of every rank's buffer, built once per shape
+        if len(_PEER_VIEWS) > 32:
+            _PEER_VIEWS.clear()
+        peers = _PEER_VIEWS[key] = [hdl.get_buffer(r, x_local.shape, x_local.dtype) for r in range(ws)]
     blk = x_local.size(0)
+    peers[rank].copy_(x_local)                     # publish (a device-to-device copy of one block)
     full[rank * blk:(rank + 1) * blk].copy_(x_local)
     hdl.barrier(channel=0, timeout_ms=BARRIER_TIMEOUT_MS)      # every rank's block is in place
     for step in range(1, ws):
         r = (rank - step) % ws                     # each rank starts at a different peer
-        full[r * blk:(r + 1) * blk].copy_(hdl.get_buffer(r, x_local.shape, x_local.dtype))
+        full[r * blk:(r + 1) * blk].copy_(peers[r])
     hdl.barrier(channel=0, timeout_ms=BARRIER_TIMEOUT_MS)      # nobody republishes before every peer has read
     return full
+
+
+_PEER_VIEWS = {}
 
 
 def all_gather_rows(x_local, group=None, name="nccl all_gather (rows)", tag="rows", async_op=False):

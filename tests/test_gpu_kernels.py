@@ -850,3 +850,25 @@ def test_dense_adjacency_path(ops, weighted, reduce):
     plan = st.fwd_noval if reduce == "mean" else st.fwd
     gk = ops.spmm_raw(plan, x.cuda(), use_val=reduce != "mean", div_rows=reduce == "mean")
     assert rel_err(ops.spmm(g, x.cuda(), reduce), gk) < TOL
+
+
+@pytest.mark.parametrize("chunk", [4, 32, 1024])
+def test_subset_plan_kernels_equal_host_construction(ops, chunk):
+    """csrc/graph_build.cu plnlp_subset_plan_count / _fill build the row-subset SpMM plan of the last conv on the
+    device: every array equals the torch construction on the host (index work: bit-exact), incl. split hub rows,
+    empty rows, a single row, all rows"""
+    from plnlp_b200.graph import build_plan, build_subset_plan
+    N = 500
+    ei, w = rand_graph(N, 6000, seed=31, weighted=True, hub=True)
+    o = sparse.to_sparse_tensor(ei, w, N)
+    rowptr, col, val = o.csr()
+    parent_c = build_plan(rowptr, col, val, N, N, chunk)
+    parent_g = build_plan(rowptr.cuda(), col.cuda(), val.cuda(), N, N, chunk)
+    g = torch.Generator().manual_seed(chunk)
+    for rows in (torch.tensor([2]), torch.arange(N), torch.unique(torch.randint(0, N, (120,), generator=g)),
+                 torch.tensor([0, 2, N - 2, N - 1])):
+        a = build_subset_plan(parent_c, rowptr, rows)
+        b = build_subset_plan(parent_g, rowptr.cuda(), rows.cuda())
+        assert (a.n_rows, a.n_items, a.n_fix, a.n_partial, a.nnz) == (b.n_rows, b.n_items, b.n_fix, b.n_partial, b.nnz)
+        for name in ("item_ptr", "item_end", "item_row", "item_slot", "fix_ptr", "fix_row", "row_cnt"):
+            assert torch.equal(getattr(a, name), getattr(b, name).cpu()), name
