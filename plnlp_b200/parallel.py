@@ -340,6 +340,14 @@ def union_ids(ids_local, group=None):
     if ws == 1:
         return torch.unique(ids_local)
     allv = torch.empty(ws * ids_local.numel(), dtype=ids_local.dtype, device=ids_local.device)
+    if ALLGATHER == "p2p" and not _SYMM_BROKEN and ids_local.is_cuda and dist.get_backend(group) == "nccl":
+        # over peer memory, not NCCL: this runs on the side stream that prepares batch i + 1 while batch i is in
+        # flight, and an NCCL collective would queue behind every collective of batch i on NCCL's own stream
+        try:
+            _p2p_all_gather(ids_local.view(-1, 1), group, "ids", allv.view(-1, 1))
+            return torch.unique(allv)
+        except Exception as ex:
+            _SYMM_BROKEN.append(repr(ex))
     dist.all_gather_into_tensor(allv, ids_local, group=group)
     return torch.unique(allv)
 
