@@ -85,6 +85,9 @@ int64_t plnlp_launch_count(void);
  * row_div[r] = max(row_nnz, 1) and gets the IEEE division upstream performs.
  * F: feature width; x/out leading dims in floats.  16-byte vector loads are used when F,
  * ldx, ldo are multiples of 4 and the bases are 16-byte aligned; otherwise 8- or 4-byte.
+ * mask (optional, fp32 [rows, ldmask]): the forward activation Y = dropout(relu(.)) this product is the gradient of;
+ * the epilogue then writes  Y[row, f] > 0 ? out * mask_scale : 0  -- the relu / dropout backward of the PREVIOUS layer
+ * fused into the backward SpMM of the conv that consumed Y (layer.py:21-22), instead of a separate pass over [N, F].
  */
 int plnlp_spmm_csr_f32(const int32_t* item_ptr, const int32_t* item_row, const int32_t* item_slot,
                        int64_t n_items, const int32_t* item_end, const int32_t* x_index,
@@ -92,7 +95,7 @@ int plnlp_spmm_csr_f32(const int32_t* item_ptr, const int32_t* item_row, const i
                        const float* row_div, const float* bias, int relu, float drop_p, uint64_t seed,
                        const float* x, int64_t ldx, float* out, int64_t ldo, int64_t F,
                        float* partial, const int32_t* fix_ptr, const int32_t* fix_row, int64_t n_fix,
-                       void* stream);
+                       const float* mask, int64_t ldmask, float mask_scale, void* stream);
 
 /* index[r] = r if any of x[r, 0..F) is non-zero (NaN counts as non-zero), else -1: an x_index of the SpMM. */
 int plnlp_row_nonzero_index_f32(const float* x, int64_t ldx, int64_t rows, int64_t F, int32_t* index, void* stream);
@@ -108,7 +111,7 @@ int plnlp_spmm_csr_bf16(const int32_t* item_ptr, const int32_t* item_row, const 
                         const float* row_div, const float* bias, int relu, float drop_p, uint64_t seed,
                         const uint16_t* x, int64_t ldx, uint16_t* out, int64_t ldo, int64_t F,
                         float* partial, const int32_t* fix_ptr, const int32_t* fix_row, int64_t n_fix,
-                        void* stream);
+                        const float* mask, int64_t ldmask, float mask_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Dense layers (replace torch.nn.Linear -> cuBLAS sgemm under SAGEConv.lin_l/lin_r,

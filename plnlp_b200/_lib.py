@@ -23,8 +23,8 @@ SIGNATURES = {
     "plnlp_abi_version": (c_int, []),
     "plnlp_check_device": (c_int, []),
     "plnlp_launch_count": (c_int64, []),
-    "plnlp_spmm_csr_f32": (c_int, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _I, _F, _U, _P, _L, _P, _L, _L, _P, _P, _P, _L, _P]),
-    "plnlp_spmm_csr_bf16": (c_int, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _I, _F, _U, _P, _L, _P, _L, _L, _P, _P, _P, _L, _P]),
+    "plnlp_spmm_csr_f32": (c_int, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _I, _F, _U, _P, _L, _P, _L, _L, _P, _P, _P, _L, _P, _L, _F, _P]),
+    "plnlp_spmm_csr_bf16": (c_int, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _I, _F, _U, _P, _L, _P, _L, _L, _P, _P, _P, _L, _P, _L, _F, _P]),
     "plnlp_row_nonzero_index_f32": (c_int, [_P, _L, _L, _L, _P, _P]),
     "plnlp_gemm_f32": (c_int, [_I, _I, _L, _L, _L, _P, _L, _P, _L, _P, _L, _F, _P, _I, _P, _L, _F, _U, _P, _L, _I, _P]),
     "plnlp_gemm_tf32": (c_int, [_I, _I, _I, _L, _L, _L, _P, _L, _P, _L, _P, _L, _F, _P, _I, _P, _L, _F, _U, _P, _L, _I, _P]),

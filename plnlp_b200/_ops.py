@@ -92,7 +92,8 @@ def new_seed():
 # ---------------------------------------------------------------------------
 # raw launches
 # ---------------------------------------------------------------------------
-def spmm_raw(plan, x, use_val, div_rows, bias=None, relu=False, drop_p=0.0, seed=0, out=None, x_index=None):
+def spmm_raw(plan, x, use_val, div_rows, bias=None, relu=False, drop_p=0.0, seed=0, out=None, x_index=None,
+             mask=None, mask_scale=1.0):
     """fp32 features, or bf16 features (bf16 storage in and out, fp32 accumulation -- the separately stated
     bf16 path; autograd and the models stay fp32)."""
     lib = _lib.load()
@@ -128,7 +129,8 @@ def spmm_raw(plan, x, use_val, div_rows, bias=None, relu=False, drop_p=0.0, seed
         check(fn(ptr(plan.item_ptr), ptr(plan.item_row), ptr(plan.item_slot), plan.n_items,
                  ptr(plan.item_end), ptr(x_index), ptr(plan.col), ptr(val), ptr(plan.row_cnt if div_rows else None), ptr(bias),
                  int(relu), float(drop_p), int(seed), ptr(x), _ld(x), ptr(out), _ld(out), F,
-                 ptr(partial), ptr(plan.fix_ptr), ptr(plan.fix_row), plan.n_fix, stream()),
+                 ptr(partial), ptr(plan.fix_ptr), ptr(plan.fix_row), plan.n_fix,
+                 ptr(mask), _ld(mask) if mask is not None else 0, float(mask_scale), stream()),
               "plnlp_" + name.split(" ")[0])
     return out
 
@@ -507,8 +509,12 @@ class SpMMRows(torch.autograd.Function):
     A[rows, :]^T @ g with the compact gradient as a row-sparse operand of the transposed plan (x_index)."""
 
     @staticmethod
-    def forward(ctx, x, bias, adj, rows, reduce, relu, drop_p, seed):
+    def forward(ctx, x, bias, adj, rows, reduce, relu, drop_p, seed, premask=None):
         from .graph import build_subset_plan
+        # premask (a float: the dropout scale of the layer that produced x): x is a relu(-dropout) OUTPUT with no other
+        # consumer; the backward then returns the gradient w.r.t. that layer's PRE-activation (mask fused into the
+        # SpMM epilogue) and the producing layer skips its own relu backward (``grad_premasked``)
+        ctx.premask = premask
         st = structure_of(adj)
         mean = reduce == "mean"
         parent = st.fwd_noval if mean else st.fwd
@@ -521,12 +527,12 @@ class SpMMRows(torch.autograd.Function):
                 plan = build_subset_plan(parent, st.rowptr, rows)
         out = spmm_raw(plan, x, use_val=not mean, div_rows=mean, bias=bias, relu=relu, drop_p=drop_p, seed=seed)
         ctx.st, ctx.mean, ctx.drop_p, ctx.has_bias = st, mean, drop_p, bias is not None
-        ctx.save_for_backward(rows, out if (relu or drop_p > 0) else None)
+        ctx.save_for_backward(rows, out if (relu or drop_p > 0) else None, x if premask is not None else None)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        rows, out = ctx.saved_tensors
+        rows, out, xmask = ctx.saved_tensors
         st = ctx.st
         g = _rowmajor(g)
         if out is not None:
@@ -540,18 +546,20 @@ class SpMMRows(torch.autograd.Function):
                     x_index = torch.full((st.n_rows,), -1, dtype=torch.int32, device=g.device)
                     x_index[rows] = torch.arange(rows.numel(), dtype=torch.int32, device=g.device)
             plan = st.bwd_mean if ctx.mean else st.bwd
-            gx = spmm_raw(plan, g, use_val=True if ctx.mean else st.has_value, div_rows=False, x_index=x_index)
-        return gx, gb, None, None, None, None, None, None
+            gx = spmm_raw(plan, g, use_val=True if ctx.mean else st.has_value, div_rows=False, x_index=x_index,
+                          mask=xmask, mask_scale=ctx.premask if xmask is not None else 1.0)
+        return gx, gb, None, None, None, None, None, None, None
 
 
-def spmm_rows(adj, x, rows, reduce="sum", bias=None, relu=False, drop_p=0.0, seed=0):
+def spmm_rows(adj, x, rows, reduce="sum", bias=None, relu=False, drop_p=0.0, seed=0, premask=None):
     if reduce == "add":
         reduce = "sum"
     if reduce not in ("sum", "mean"):
         raise NotImplementedError(f"reduce={reduce!r}")
     if rows.dtype != torch.int64 or rows.dim() != 1 or not rows.is_cuda:
         raise RuntimeError("rows must be a 1-D CUDA int64 tensor of distinct row ids")
-    return SpMMRows.apply(x, bias, adj, rows, reduce, bool(relu), float(drop_p), int(seed))
+    return SpMMRows.apply(x, bias, adj, rows, reduce, bool(relu), float(drop_p), int(seed),
+                          None if premask is None else float(premask))
 
 
 class FusedLinear(torch.autograd.Function):
@@ -660,8 +668,9 @@ class AggLinear(torch.autograd.Function):
     the live blocks are recomputed first.  Works on a row-partitioned adjacency too (``aggregate_into``)."""
 
     @staticmethod
-    def forward(ctx, W, bias, adj, buf, holder, offs, act, drop_p, seed, sparse_grad, *xs):
+    def forward(ctx, W, bias, adj, buf, holder, offs, act, drop_p, seed, sparse_grad, grad_premasked, *xs):
         ctx.sparse_grad = bool(sparse_grad)
+        ctx.grad_premasked = bool(grad_premasked)      # the consumer's backward already applied this layer's relu mask
         for off, x in zip(offs, xs):
             aggregate_into(adj, x, buf[:, off:off + x.size(1)])
         holder["stamp"] = holder.get("stamp", 0) + 1
@@ -677,7 +686,7 @@ class AggLinear(torch.autograd.Function):
         xs = ctx.saved_tensors[2:]
         buf = ctx.buf
         g = _rowmajor(g)
-        if Y is not None:
+        if Y is not None and not ctx.grad_premasked:
             g = relu_drop_bwd_raw(Y, g, 1.0 / (1.0 - ctx.drop_p))
         if ctx.holder["stamp"] != ctx.stamp:          # buf was reused by a later forward: restore our blocks
             for off, x in zip(ctx.offs, xs):
@@ -687,7 +696,7 @@ class AggLinear(torch.autograd.Function):
         # the weight-gradient GEMM below runs
         gxs, waits = [], []
         for i, (off, x) in enumerate(zip(ctx.offs, xs)):
-            if not ctx.needs_input_grad[10 + i]:
+            if not ctx.needs_input_grad[11 + i]:
                 gxs.append(None)
                 continue
             gu = gemm_raw(g, W[:, off:off + x.size(1)], C=_rows_for_spmm(g.size(0), x.size(1), g.device))   # d(A x_i) = dY W_i
@@ -708,12 +717,13 @@ class AggLinear(torch.autograd.Function):
             if wait is not None:
                 wait()
         gxs = [gx.fn()[: x.size(0)] if isinstance(gx, _Deferred) else gx for gx, x in zip(gxs, xs)]
-        return (gW, gb, None, None, None, None, None, None, None, None, *gxs)
+        return (gW, gb, None, None, None, None, None, None, None, None, None, *gxs)
 
 
-def agg_linear(adj, buf, holder, offs, xs, W, bias, act=ACT_NONE, drop_p=0.0, seed=0, sparse_grad=False):
+def agg_linear(adj, buf, holder, offs, xs, W, bias, act=ACT_NONE, drop_p=0.0, seed=0, sparse_grad=False,
+               grad_premasked=False):
     return AggLinear.apply(W, bias, adj, buf, holder, tuple(offs), int(act), float(drop_p), int(seed),
-                           bool(sparse_grad), *xs)
+                           bool(sparse_grad), bool(grad_premasked), *xs)
 
 
 class GatherHadamard(torch.autograd.Function):

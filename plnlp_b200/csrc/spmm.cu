@@ -46,6 +46,13 @@ struct SpmmParamsT {
     const int32_t* fix_ptr;
     const int32_t* fix_row;
     int64_t n_fix;
+    // optional relu(-dropout) backward mask fused into the epilogue: out = mask[row, f] > 0 ? out * mask_scale : 0.
+    // `mask` is the forward activation Y = dropout(relu(.)) whose gradient this product is (the backward SpMM of the
+    // conv that consumed Y then hands the previous layer the gradient w.r.t. its PRE-activation: no separate
+    // relu-backward pass over [N, F])
+    const float* mask;
+    int64_t ldmask;
+    float mask_scale;
 };
 using SpmmParams = SpmmParamsT<float>;
 
@@ -112,6 +119,11 @@ __device__ __forceinline__ void finish_store(const SpmmParamsT<T>& p, int row, i
             const uint64_t idx = static_cast<uint64_t>(row) * static_cast<uint64_t>(p.F) + (f + e);
             a[e] = dropout_keep(p.seed, idx, p.drop_p) ? a[e] * s : 0.0f;
         }
+    }
+    if (p.mask) {
+        const float* m = p.mask + static_cast<int64_t>(row) * p.ldmask + f;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) a[e] = __ldg(m + e) > 0.0f ? a[e] * p.mask_scale : 0.0f;
     }
     store_vec<VEC>(p.out + static_cast<int64_t>(row) * p.ldo + f, a);
 }
@@ -354,6 +366,10 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4) ? 8 : 6) spmm_csr_narrow
             acc[e] = dropout_keep(p.seed, idx, p.drop_p) ? acc[e] * s : 0.0f;
         }
     }
+    if (p.mask) {
+        const float* m = p.mask + static_cast<int64_t>(row) * p.ldmask + f;
+        for (int e = 0; e < live; ++e) acc[e] = __ldg(m + e) > 0.0f ? acc[e] * p.mask_scale : 0.0f;
+    }
     T* dst = p.out + static_cast<int64_t>(row) * p.ldo + f;
     if (live == VEC && (p.ldo % VEC == 0) && (reinterpret_cast<uintptr_t>(p.out) % 16 == 0)) {
         store_vec<VEC>(dst, acc);
@@ -472,7 +488,7 @@ extern "C" int plnlp_spmm_csr_f32(const int32_t* item_ptr, const int32_t* item_r
                                   const float* row_div, const float* bias, int relu, float drop_p,
                                   uint64_t seed, const float* x, int64_t ldx, float* out, int64_t ldo,
                                   int64_t F, float* partial, const int32_t* fix_ptr, const int32_t* fix_row,
-                                  int64_t n_fix, void* stream) {
+                                  int64_t n_fix, const float* mask, int64_t ldmask, float mask_scale, void* stream) {
     using namespace plnlp;
     PLNLP_REQUIRE(n_items >= 0 && n_fix >= 0 && F > 0 && F < (1 << 30), PLNLP_E_SIZE);
     if (n_items == 0) return 0;
@@ -481,7 +497,8 @@ extern "C" int plnlp_spmm_csr_f32(const int32_t* item_ptr, const int32_t* item_r
     PLNLP_REQUIRE(drop_p >= 0.0f && drop_p < 1.0f, PLNLP_E_SIZE);
     if (n_fix > 0) PLNLP_REQUIRE(partial && fix_ptr && fix_row, PLNLP_E_NULL);
     SpmmParams p{item_ptr, item_row, item_slot, n_items, item_end, x_index, col, val, row_div, bias, relu, drop_p, seed,
-                 x, ldx, out, ldo, static_cast<int>(F), partial, fix_ptr, fix_row, n_fix};
+                 x, ldx, out, ldo, static_cast<int>(F), partial, fix_ptr, fix_row, n_fix, mask, ldmask, mask_scale};
+    PLNLP_REQUIRE(!mask || ldmask >= F, PLNLP_E_SIZE);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool v4 = (F % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned(x, 16) && aligned(out, 16) &&
                     (!partial || aligned(partial, 16));
@@ -509,7 +526,7 @@ extern "C" int plnlp_spmm_csr_bf16(const int32_t* item_ptr, const int32_t* item_
                                    const float* row_div, const float* bias, int relu, float drop_p,
                                    uint64_t seed, const uint16_t* x, int64_t ldx, uint16_t* out, int64_t ldo,
                                    int64_t F, float* partial, const int32_t* fix_ptr, const int32_t* fix_row,
-                                   int64_t n_fix, void* stream) {
+                                   int64_t n_fix, const float* mask, int64_t ldmask, float mask_scale, void* stream) {
     using namespace plnlp;
     PLNLP_REQUIRE(n_items >= 0 && n_fix >= 0 && F > 0 && F < (1 << 30), PLNLP_E_SIZE);
     if (n_items == 0) return 0;
@@ -520,7 +537,8 @@ extern "C" int plnlp_spmm_csr_bf16(const int32_t* item_ptr, const int32_t* item_
     SpmmParamsT<__nv_bfloat16> p{item_ptr, item_row, item_slot, n_items, item_end, x_index, col, val, row_div, bias, relu, drop_p, seed,
                                  reinterpret_cast<const __nv_bfloat16*>(x), ldx,
                                  reinterpret_cast<__nv_bfloat16*>(out), ldo, static_cast<int>(F), partial, fix_ptr,
-                                 fix_row, n_fix};
+                                 fix_row, n_fix, mask, ldmask, mask_scale};
+    PLNLP_REQUIRE(!mask || ldmask >= F, PLNLP_E_SIZE);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     auto ok = [&](int v) {   // v bf16 elements per access: 2v bytes for x / out, 4v (<= 16-byte pieces) for partial
         return (F % v == 0) && (ldx % v == 0) && (ldo % v == 0) && aligned(x, 2 * v) && aligned(out, 2 * v) &&

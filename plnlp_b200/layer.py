@@ -18,6 +18,8 @@ from . import _ops
 
 # GCNConv: aggregate before the linear map when that side is narrower (see GCNConv.forward)
 REASSOCIATE = os.environ.get("PLNLP_GCN_REASSOCIATE", "1") != "0"
+# relu backward of the layer before a row-restricted last conv fused into that conv's backward SpMM (BaseGNN.forward)
+FUSE_RELU_BWD = os.environ.get("PLNLP_FUSE_RELU_BWD", "1") != "0"
 
 
 def mark_constant(x):
@@ -207,10 +209,26 @@ class GCNConv(torch.nn.Module):
             return parallel.RESTRICT_LAST and not _ops.structure_of(adj_t.local).dense_ok
         return not _ops.structure_of(adj_t).dense_ok
 
-    def forward(self, x, adj_t, act=_ops.ACT_NONE, drop_p=0.0, out_rows=None, sparse_grad=False):
+    def uses_agg_buffer(self, x, adj_t):
+        """will ``forward(x, adj_t)`` (all rows) take the aggregate-buffer path (``_ops.AggLinear``)?"""
+        parts = _as_parts(x)
+        live = sum(p.size(1) for p in parts if not _is_const(p))
+        return REASSOCIATE and live < self.out_channels and _agg_buffer_ok(adj_t, parts)
+
+    def forward(self, x, adj_t, act=_ops.ACT_NONE, drop_p=0.0, out_rows=None, sparse_grad=False, grad_premasked=False,
+                premask_input=None):
+        """``grad_premasked``: the only consumer of this layer's relu(-dropout) output applies the relu mask to the
+        gradient itself (see ``premask_input``), so this layer's backward must not.  ``premask_input`` (the dropout
+        scale of the layer that produced x): x is such an output and this conv is its only consumer -- the backward of
+        the row-subset SpMM writes the gradient w.r.t. the producer's PRE-activation (mask in the SpMM epilogue; saves
+        the separate relu-backward pass over [N, F]).  Both are set together by ``BaseGNN.forward``."""
         parts = _as_parts(x)
         ws = _split_cols(self.lin.weight, parts)
         seed = _ops.new_seed() if drop_p > 0 else 0
+        if grad_premasked and not (out_rows is None and self.uses_agg_buffer(x, adj_t)):
+            raise RuntimeError("grad_premasked is only implemented for the aggregate-buffer path")
+        if premask_input is not None and (out_rows is None or len(parts) != 1):
+            raise RuntimeError("premask_input needs the row-restricted path and a single input block")
         if out_rows is not None:
             # only these rows of the layer output, as a compact [T, out] matrix: (A_hat[rows, :] x) W^T + b.
             # Aggregating first keeps the linear map and both of its backward GEMMs at T rows instead of N.
@@ -220,12 +238,13 @@ class GCNConv(torch.nn.Module):
             if isinstance(adj_t, parallel.ShardedAdj):
                 if parallel.RESTRICT_COMBINE == "rs":
                     # every rank maps its 1 / R of the requested rows and the results are all-gathered
-                    aggs = [parallel.pspmm_rows(adj_t, p, out_rows, reduce="sum", sharded=True) for p in parts]
+                    aggs = [parallel.pspmm_rows(adj_t, p, out_rows, reduce="sum", sharded=True, premask=premask_input)
+                            for p in parts]
                     y = _ops.fused_linear(aggs, ws, self.bias, act, drop_p, seed)
                     return parallel.gather_rows(y, adj_t.group, tag="restricted rows")[: out_rows.numel()]
-                aggs = [parallel.pspmm_rows(adj_t, p, out_rows, reduce="sum") for p in parts]
+                aggs = [parallel.pspmm_rows(adj_t, p, out_rows, reduce="sum", premask=premask_input) for p in parts]
             else:
-                aggs = [_ops.spmm_rows(adj_t, p, out_rows, reduce="sum") for p in parts]
+                aggs = [_ops.spmm_rows(adj_t, p, out_rows, reduce="sum", premask=premask_input) for p in parts]
             return _ops.fused_linear(aggs, ws, self.bias, act, drop_p, seed)
         live = sum(p.size(1) for p in parts if not _is_const(p))
         if REASSOCIATE and live < self.out_channels:
@@ -237,7 +256,7 @@ class GCNConv(torch.nn.Module):
             if _agg_buffer_ok(adj_t, parts):
                 buf, holder, offs, xs = _agg_buffer(adj_t, parts)
                 return _ops.agg_linear(adj_t, buf, holder, offs, xs, self.lin.weight, self.bias, act, drop_p, seed,
-                                       sparse_grad=sparse_grad)
+                                       sparse_grad=sparse_grad, grad_premasked=grad_premasked)
             aggs = [_const_aggregate(adj_t, p, "sum") if _is_const(p)
                     else _ops.spmm(adj_t, p, reduce="sum", sparse_grad=sparse_grad) for p in parts]
             return _ops.fused_linear(aggs, ws, self.bias, act, drop_p, seed)
@@ -309,13 +328,23 @@ class BaseGNN(torch.nn.Module):
         p = self.dropout if self.training else 0.0
         last = len(self.convs) - 1
         restricted = False
+        will_restrict = (out_rows is not None and getattr(self.convs[last], "can_restrict", None)
+                         and self.convs[last].can_restrict(None, adj_t))
+        premask = False
         for i, conv in enumerate(self.convs):
             fused = i < last or self.num_layers == 1
             kw = {}
-            if i == last and out_rows is not None and getattr(conv, "can_restrict", None) and conv.can_restrict(x, adj_t):
+            if i == last and will_restrict:
                 kw["out_rows"], restricted = out_rows, True
+                if premask:
+                    kw["premask_input"] = 1.0 / (1.0 - p)
             elif i == last and (sparse_grad or out_rows is not None):
                 kw["sparse_grad"] = True
+            elif (i == last - 1 and will_restrict and FUSE_RELU_BWD and isinstance(conv, GCNConv)
+                  and isinstance(self.convs[last], GCNConv) and torch.is_grad_enabled() and conv.uses_agg_buffer(x, adj_t)):
+                # this layer's relu(-dropout) output feeds ONLY the row-subset SpMM of the last conv: that SpMM's
+                # backward applies the relu mask in its epilogue and this layer skips its relu-backward pass
+                kw["grad_premasked"] = premask = True
             x = conv(x, adj_t, act=_ops.ACT_RELU if fused else _ops.ACT_NONE, drop_p=p if fused else 0.0, **kw)
         return x if out_rows is None else (x, restricted)
 

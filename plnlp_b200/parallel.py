@@ -421,7 +421,7 @@ def pad_rows(x, blk):
     return torch.cat([x, pad], 0)
 
 
-def pspmm_rows(sadj, x_local, rows, reduce="sum", local_op=None, sharded=False):
+def pspmm_rows(sadj, x_local, rows, reduce="sum", local_op=None, sharded=False, premask=None):
     """(A @ X)[rows] on a row-partitioned X, for GLOBAL row ids ``rows`` (sorted, distinct, the SAME list on every
     rank -- ``union_ids``), returned in full, compactly, on every rank.
 
@@ -438,7 +438,8 @@ def pspmm_rows(sadj, x_local, rows, reduce="sum", local_op=None, sharded=False):
     if local_op is None:
         from . import _ops
         local_op = _ops.spmm_rows
-    partial = local_op(sadj.cols(), pad_rows(x_local, sadj.blk), rows, "sum")
+    kw = {} if premask is None else {"premask": premask}      # see layer.GCNConv.forward(premask_input=)
+    partial = local_op(sadj.cols(), pad_rows(x_local, sadj.blk), rows, "sum", **kw)
     if sharded:
         # -> this rank's ceil(T / R) rows of the sum only: the caller runs its row-wise work (the conv's linear map)
         # on 1 / R of the rows and all-gathers the result (``gather_rows``) -- same bytes on the wire as the
