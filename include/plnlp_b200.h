@@ -83,8 +83,11 @@ int64_t plnlp_launch_count(void);
  * non-zero, plnlp_row_nonzero_index_f32 builds that).
  * val == NULL: value-less adjacency.  row_div == NULL: no division (sum); SAGE mean passes
  * row_div[r] = max(row_nnz, 1) and gets the IEEE division upstream performs.
- * F: feature width; x/out leading dims in floats.  16-byte vector loads are used when F,
- * ldx, ldo are multiples of 4 and the bases are 16-byte aligned; otherwise 8- or 4-byte.
+ * F: feature width; x/out leading dims in floats; x_rows: rows of x (every column index, or x_index value, is below
+ * it -- the caller's promise; the kernels use it only to keep whole-vector copies of the last row inside the operand).
+ * 16-byte vector loads are used when F, ldx, ldo are multiples of 4 and the bases are 16-byte aligned; otherwise 8- or
+ * 4-byte.  fp32 operands of an even width <= 64 floats on a 16-byte aligned base run on the shared-memory staged
+ * kernel (cp.async row copies, see plnlp_spmm_tune).
  * mask (optional, fp32 [rows, ldmask]): the forward activation Y = dropout(relu(.)) this product is the gradient of;
  * the epilogue then writes  Y[row, f] > 0 ? out * mask_scale : 0  -- the relu / dropout backward of the PREVIOUS layer
  * fused into the backward SpMM of the conv that consumed Y (layer.py:21-22), instead of a separate pass over [N, F].
@@ -93,9 +96,22 @@ int plnlp_spmm_csr_f32(const int32_t* item_ptr, const int32_t* item_row, const i
                        int64_t n_items, const int32_t* item_end, const int32_t* x_index,
                        const int32_t* col, const float* val,
                        const float* row_div, const float* bias, int relu, float drop_p, uint64_t seed,
-                       const float* x, int64_t ldx, float* out, int64_t ldo, int64_t F,
+                       const float* x, int64_t ldx, int64_t x_rows, float* out, int64_t ldo, int64_t F,
                        float* partial, const int32_t* fix_ptr, const int32_t* fix_row, int64_t n_fix,
                        const float* mask, int64_t ldmask, float mask_scale, void* stream);
+
+/* Process-wide tuning of the SpMM gather kernels (A/B runs and the defaults plnlp_b200/_ops.py applies at load;
+ * a negative / zero argument leaves that knob unchanged).  None of them changes a single output bit.
+ *   prefetch_mode : 0 off; 1 = every lane asks the L2 for the row behind its column index as soon as the batch's
+ *                   indices are known (prefetch.global.L2 per 128-byte line); 2 = the same with one
+ *                   cp.async.bulk.prefetch.L2 per row; 3 = mode 2 for rows of 257..512 bytes, off otherwise (where it
+ *                   was measured to pay).  All rows of a batch are then in flight at once instead of NB per warp.
+ *   staged_mode   : 0 off; 1..12 = fp32 operands of an even width <= 64 floats run on the shared-memory staged kernel
+ *                   (cp.async row copies; per warp a ring of 1: 16 rows x 4 stages, 2: 32 x 3, 3: 16 x 6, 4: 32 x 4,
+ *                   5: 16 x 3, 6: 16 x 2, 7: 8 x 3, 8: 8 x 4, 9: 32 x 2, 10: 32 x 1, 11: 16 x 1; 12 = auto, the default:
+ *                   32 x 1); staged_warps = warps per CTA (1..16).
+ *   l2_fetch_bytes: cudaLimitMaxL2FetchGranularity (32 / 64 / 128) of the current device. */
+int plnlp_spmm_tune(int prefetch_mode, int staged_mode, int staged_warps, int l2_fetch_bytes);
 
 /* index[r] = r if any of x[r, 0..F) is non-zero (NaN counts as non-zero), else -1: an x_index of the SpMM. */
 int plnlp_row_nonzero_index_f32(const float* x, int64_t ldx, int64_t rows, int64_t F, int32_t* index, void* stream);
@@ -109,7 +125,7 @@ int plnlp_spmm_csr_bf16(const int32_t* item_ptr, const int32_t* item_row, const 
                         int64_t n_items, const int32_t* item_end, const int32_t* x_index,
                        const int32_t* col, const float* val,
                         const float* row_div, const float* bias, int relu, float drop_p, uint64_t seed,
-                        const uint16_t* x, int64_t ldx, uint16_t* out, int64_t ldo, int64_t F,
+                        const uint16_t* x, int64_t ldx, int64_t x_rows, uint16_t* out, int64_t ldo, int64_t F,
                         float* partial, const int32_t* fix_ptr, const int32_t* fix_row, int64_t n_fix,
                         const float* mask, int64_t ldmask, float mask_scale, void* stream);
 
@@ -179,6 +195,22 @@ int plnlp_edge_mlp_fwd_tf32(int passes, const float* h, int64_t ldh, int64_t n_r
                             int64_t P, int64_t H, const float* W1, int64_t ldw, const float* b1, int64_t N1,
                             float drop_p, uint64_t seed, const float* w2, float* a1, int64_t lda1,
                             float* score_part, int64_t score_ld, void* stream);
+
+/* Fused edge scoring, MLP head BACKWARD (model.py:161 through layer.py:80-87).  With a1 = dropout(relu(a0 W1^T + b1))
+ * stored by plnlp_edge_mlp_fwd_tf32 and dscore = d loss / d score (plnlp_pair_loss_f32):
+ *     dZ1 = (dscore (x) w2) . [a1 > 0] * drop_scale      formed inside the operand loaders, never written to HBM
+ *     dA0 = dZ1 @ W1                    [P, H]           gradient of the Hadamard product (plnlp_edge_scatter_* next)
+ *     dW1 = dZ1^T @ (h[src] * h[dst])   [N1, H]          the Hadamard product is re-gathered by the loader
+ * Neither dZ1 nor the Hadamard product round-trips through HBM (before: 537 MB written and read twice each at the
+ * ddi shape).  dw2 / db2 / db1 = colsum(dZ1) come from plnlp_mlp_out_bwd_f32 with dz = NULL.  H, N1 and the leading
+ * dimensions must be multiples of 4, bases 16-byte aligned, N1 <= 1088.  dW1 is a split-k product over the P pairs:
+ * workspace = plnlp_edge_mlp_bwd_workspace_bytes(P, H, N1, split_k) bytes, partials combined in split order. */
+int64_t plnlp_edge_mlp_bwd_workspace_bytes(int64_t P, int64_t H, int64_t N1, int split_k);
+int plnlp_edge_mlp_bwd_tf32(int passes, const float* h, int64_t ldh, int64_t n_rows, const int64_t* edges,
+                            int64_t P, int64_t H, const float* W1, int64_t ldw, int64_t N1,
+                            const float* a1, int64_t lda1, const float* dscore, const float* w2,
+                            float drop_scale, float* dA0, int64_t ldda0, float* dW1, int64_t lddw1,
+                            float* workspace, int64_t workspace_bytes, int split_k, void* stream);
 /* out[p, :] = h[src_p, :] * h[dst_p, :] */
 int plnlp_gather_hadamard_f32(const float* h, int64_t ldh, int64_t n_rows, const int64_t* edges, int64_t P, int64_t H,
                               float* out, int64_t ldo, void* stream);
@@ -213,11 +245,13 @@ int plnlp_mlp_out_fwd_f32(const float* a, int64_t lda, const float* w, const flo
 /* backward of the above fused with the relu/dropout mask of `a`:
  *   dz[p, j] = dscore[p] * w[j] * (a[p, j] > 0 ? drop_scale : 0)     (mask_a != 0)
  *   dw[j] = sum_p dscore[p] * a[p, j];  db[0] = sum_p dscore[p]
+ *   dzsum[j] = sum_p dz[p, j]   (optional: the bias gradient of the layer that produced `a`)
+ * dz == NULL: dz is not written (the fused backward plnlp_edge_mlp_bwd_tf32 forms it in its loaders).
  * workspace: plnlp_mlp_out_bwd_workspace_bytes(P, H) bytes.  Deterministic. */
 int64_t plnlp_mlp_out_bwd_workspace_bytes(int64_t P, int64_t H);
 int plnlp_mlp_out_bwd_f32(const float* a, int64_t lda, const float* w, const float* dscore, int64_t P,
                           int64_t H, int mask_a, float drop_scale, float* dz, int64_t lddz, float* dw,
-                          float* db, void* workspace, int64_t workspace_bytes, void* stream);
+                          float* db, float* dzsum, void* workspace, int64_t workspace_bytes, void* stream);
 /* Backward of the endpoint gather (replaces index_put_(accumulate=True), model.py:161).
  *   g[p, :] = da[p, :]            (MLP head; da = d loss / d hadamard)       or
  *   g[p, :] = dscore[p]           (DOT head; da == NULL)

@@ -23,8 +23,9 @@ SIGNATURES = {
     "plnlp_abi_version": (c_int, []),
     "plnlp_check_device": (c_int, []),
     "plnlp_launch_count": (c_int64, []),
-    "plnlp_spmm_csr_f32": (c_int, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _I, _F, _U, _P, _L, _P, _L, _L, _P, _P, _P, _L, _P, _L, _F, _P]),
-    "plnlp_spmm_csr_bf16": (c_int, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _I, _F, _U, _P, _L, _P, _L, _L, _P, _P, _P, _L, _P, _L, _F, _P]),
+    "plnlp_spmm_csr_f32": (c_int, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _I, _F, _U, _P, _L, _L, _P, _L, _L, _P, _P, _P, _L, _P, _L, _F, _P]),
+    "plnlp_spmm_csr_bf16": (c_int, [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _I, _F, _U, _P, _L, _L, _P, _L, _L, _P, _P, _P, _L, _P, _L, _F, _P]),
+    "plnlp_spmm_tune": (c_int, [_I, _I, _I, _I]),
     "plnlp_row_nonzero_index_f32": (c_int, [_P, _L, _L, _L, _P, _P]),
     "plnlp_gemm_f32": (c_int, [_I, _I, _L, _L, _L, _P, _L, _P, _L, _P, _L, _F, _P, _I, _P, _L, _F, _U, _P, _L, _I, _P]),
     "plnlp_gemm_tf32": (c_int, [_I, _I, _I, _L, _L, _L, _P, _L, _P, _L, _P, _L, _F, _P, _I, _P, _L, _F, _U, _P, _L, _I, _P]),
@@ -40,7 +41,9 @@ SIGNATURES = {
     "plnlp_edge_dot_fwd_f32": (c_int, [_P, _L, _L, _P, _L, _L, _P, _P]),
     "plnlp_mlp_out_fwd_f32": (c_int, [_P, _L, _P, _P, _L, _L, _P, _P]),
     "plnlp_mlp_out_bwd_workspace_bytes": (c_int64, [_L, _L]),
-    "plnlp_mlp_out_bwd_f32": (c_int, [_P, _L, _P, _P, _L, _L, _I, _F, _P, _L, _P, _P, _P, _L, _P]),
+    "plnlp_mlp_out_bwd_f32": (c_int, [_P, _L, _P, _P, _L, _L, _I, _F, _P, _L, _P, _P, _P, _P, _L, _P]),
+    "plnlp_edge_mlp_bwd_workspace_bytes": (c_int64, [_L, _L, _L, _I]),
+    "plnlp_edge_mlp_bwd_tf32": (c_int, [_I, _P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _P, _P, _F, _P, _L, _P, _L, _P, _L, _I, _P]),
     "plnlp_edge_scatter_atomic_f32": (c_int, [_P, _L, _L, _P, _L, _L, _P, _L, _P, _P, _L, _P]),
     "plnlp_edge_scatter_sorted_f32": (c_int, [_P, _L, _L, _P, _L, _L, _P, _L, _P, _P, _P, _L, _P, _P, _L, _P]),
     "plnlp_pair_loss_workspace_bytes": (c_int64, [_L]),
@@ -90,8 +93,21 @@ def load():
         fn.restype, fn.argtypes = res, args
     if lib.plnlp_abi_version() != 1:
         raise RuntimeError("libplnlp_b200.so ABI version mismatch")
+    apply_spmm_tuning(lib)
     _lib = lib
     return lib
+
+
+def apply_spmm_tuning(lib=None):
+    """SpMM gather knobs (plnlp_spmm_tune): the library's built-in defaults unless the environment overrides them --
+    PLNLP_SPMM_PREFETCH (0/1/2), PLNLP_SPMM_STAGED (0..5), PLNLP_SPMM_STAGED_WARPS, PLNLP_L2_FETCH (bytes).  A/B
+    tools call plnlp_spmm_tune directly."""
+    lib = lib or load()
+    env = os.environ.get
+    rc = lib.plnlp_spmm_tune(int(env("PLNLP_SPMM_PREFETCH", "-1")), int(env("PLNLP_SPMM_STAGED", "-1")),
+                             int(env("PLNLP_SPMM_STAGED_WARPS", "0")), int(env("PLNLP_L2_FETCH", "0")))
+    if rc != 0:
+        raise RuntimeError(f"plnlp_spmm_tune -> {rc}")
 
 
 def check(rc, name):

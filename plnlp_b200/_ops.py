@@ -39,6 +39,10 @@ GEMM_TMA = os.environ.get("PLNLP_GEMM_TMA", "auto")
 
 # fused edge scoring for the MLP head (gather + Hadamard + layer 1 + out layer in one tcgen05 kernel)
 FUSED_EDGE_MLP = os.environ.get("PLNLP_FUSED_EDGE", "1") != "0"
+# ... and its backward (dZ1 formed in the loaders of both GEMMs, Hadamard product re-gathered in the weight-gradient
+# GEMM): "auto" = when the embedding table fits the L2 budget below, "1" = whenever legal, "0" = off
+FUSED_EDGE_BWD = os.environ.get("PLNLP_FUSED_EDGE_BWD", "0")
+FUSED_EDGE_BWD_L2_BYTES = 48 << 20
 
 
 def _f32c(t):
@@ -81,6 +85,16 @@ def _rows_for_spmm(rows, F, device):
     if F <= 64 and F % 4:
         return torch.empty(rows, 64, dtype=torch.float32, device=device)[:, :F]
     return torch.empty(rows, F, dtype=torch.float32, device=device)
+
+
+def apply_spmm_defaults():
+    """reset the SpMM tuning knobs to the library defaults + environment overrides (after an A/B run)"""
+    _lib.load().plnlp_spmm_tune(SPMM_TUNE_DEFAULT[0], SPMM_TUNE_DEFAULT[1], SPMM_TUNE_DEFAULT[2], 0)
+    _lib.apply_spmm_tuning()
+
+
+# the library's built-in (prefetch_mode, staged_mode, staged_warps): see csrc/spmm.cu g_spmm_*
+SPMM_TUNE_DEFAULT = (3, 12, 4)
 
 
 def new_seed():
@@ -128,7 +142,7 @@ def spmm_raw(plan, x, use_val, div_rows, bias=None, relu=False, drop_p=0.0, seed
     with profiling.span(f"{name} F={F}", alg, 0):
         check(fn(ptr(plan.item_ptr), ptr(plan.item_row), ptr(plan.item_slot), plan.n_items,
                  ptr(plan.item_end), ptr(x_index), ptr(plan.col), ptr(val), ptr(plan.row_cnt if div_rows else None), ptr(bias),
-                 int(relu), float(drop_p), int(seed), ptr(x), _ld(x), ptr(out), _ld(out), F,
+                 int(relu), float(drop_p), int(seed), ptr(x), _ld(x), x.size(0), ptr(out), _ld(out), F,
                  ptr(partial), ptr(plan.fix_ptr), ptr(plan.fix_row), plan.n_fix,
                  ptr(mask), _ld(mask) if mask is not None else 0, float(mask_scale), stream()),
               "plnlp_" + name.split(" ")[0])
@@ -343,23 +357,68 @@ def mlp_out_fwd_raw(a, w, b):
     return score
 
 
-def mlp_out_bwd_raw(a, w, dscore, mask_a, drop_scale):
-    """-> dz [P,H], dw [H], db [1]"""
+def mlp_out_bwd_raw(a, w, dscore, mask_a, drop_scale, need_dz=True, need_dzsum=False):
+    """-> dz [P,H] (None when need_dz is False), dw [H], db [1] (, dzsum [H] = column sums of dz when asked for)"""
     lib = _lib.load()
     a = _rowmajor(a)
     w = _f32c(w).reshape(-1).contiguous()
     dscore = _f32c(dscore).contiguous()
     P, H = a.shape
-    dz = torch.empty(P, H, dtype=torch.float32, device=a.device)
+    dz = torch.empty(P, H, dtype=torch.float32, device=a.device) if need_dz else None
     dw = torch.empty(H, dtype=torch.float32, device=a.device)
     db = torch.empty(1, dtype=torch.float32, device=a.device)
+    dzsum = torch.empty(H, dtype=torch.float32, device=a.device) if need_dzsum else None
     nbytes = lib.plnlp_mlp_out_bwd_workspace_bytes(P, H)
     ws = workspace.get("mlp_out_bwd", nbytes, a.device)
-    with profiling.span("mlp_out_bwd_f32", P * (2 * H * 4 + 4), 0):
+    with profiling.span("mlp_out_bwd_f32" if need_dz else "mlp_out_bwd_f32 (reductions only)",
+                        P * ((2 if need_dz else 1) * H * 4 + 4), 0):
         check(lib.plnlp_mlp_out_bwd_f32(ptr(a), _ld(a), ptr(w), ptr(dscore), P, H, int(mask_a), float(drop_scale),
-                                        ptr(dz), H, ptr(dw), ptr(db), ptr(ws), nbytes, stream()),
+                                        ptr(dz), H, ptr(dw), ptr(db), ptr(dzsum), ptr(ws), nbytes, stream()),
               "plnlp_mlp_out_bwd_f32")
+    if need_dzsum:
+        return dz, dw, db, dzsum
     return dz, dw, db
+
+
+def fused_edge_mlp_bwd_ok(h, a1, params):
+    """the fused backward re-gathers the Hadamard product inside the weight-gradient GEMM: it pays while the embedding
+    table the pairs index stays in the L2 (ddi shape: 8.7 MB; the 232 MB compact table of the citation2 shape would be
+    gathered from DRAM inside a tensor-core loader with two slabs in flight)"""
+    if FUSED_EDGE_BWD == "0":
+        return False
+    W1 = params[0]
+    H, N1 = h.size(1), W1.size(0)
+    ok = (H % 4 == 0 and N1 % 4 == 0 and N1 <= 1088 and _ld(h) % 4 == 0 and _ld(W1) % 4 == 0 and _ld(a1) % 4 == 0
+          and h.data_ptr() % 16 == 0 and W1.data_ptr() % 16 == 0 and a1.data_ptr() % 16 == 0)
+    if FUSED_EDGE_BWD == "1":
+        return ok
+    return ok and h.numel() * 4 <= FUSED_EDGE_BWD_L2_BYTES
+
+
+def edge_mlp_bwd_raw(h, edges, W1, a1, dscore, w2, drop_scale):
+    """fused backward of the 2-layer MLP head behind the Hadamard gather: -> dA0 [P, H], dW1 [N1, H]"""
+    lib = _lib.load()
+    h, edges, W1, a1 = _rowmajor(h), _edges_i64(edges), _rowmajor(W1), _rowmajor(a1)
+    w2 = _f32c(w2).reshape(-1).contiguous()
+    dscore = _f32c(dscore).contiguous()
+    P, H, N1 = edges.size(0), h.size(1), W1.size(0)
+    da0 = torch.empty(P, H, dtype=torch.float32, device=h.device)
+    dw1 = torch.empty(N1, H, dtype=torch.float32, device=h.device)
+    passes = 3 if GEMM_BACKEND == "tf32x3c2" else 1
+    tiles = ((N1 + 127) // 128) * ((H + 255) // 256)           # the split-k rule of gemm_raw for dW1 [N1, H] over K = P
+    split_k = 1
+    if tiles < 148 and P >= 2048:
+        split_k = int(min(max(1, (2 * 148) // tiles), P // 512, 64))
+    if passes == 3:
+        split_k = max(split_k, (P + TF32X3_KCAP - 1) // TF32X3_KCAP)
+    nbytes = lib.plnlp_edge_mlp_bwd_workspace_bytes(P, H, N1, split_k)
+    ws = workspace.get("gemm_splitk", nbytes, h.device)
+    with profiling.span(f"edge_mlp_bwd_fused {P}x{N1}x{H}", 0, 4 * P * N1 * H):
+        check(lib.plnlp_edge_mlp_bwd_tf32(passes, ptr(h), _ld(h), h.size(0), ptr(edges), P, H, ptr(W1), _ld(W1), N1,
+                                          ptr(a1), _ld(a1), ptr(dscore), ptr(w2), float(drop_scale), ptr(da0), H,
+                                          ptr(dw1), H, ptr(ws), nbytes, split_k, stream()),
+              "plnlp_edge_mlp_bwd_tf32")
+    return da0, dw1
 
 
 _RANGE_CACHE = {}
@@ -873,8 +932,6 @@ class EdgeScoreLoss(torch.autograd.Function):
         h, edges, dpos, dneg = saved[:4]
         acts = saved[4:4 + ctx.n_acts]
         params = saved[4 + ctx.n_acts:]
-        if ctx.fused:        # the forward never stored the Hadamard product: re-gather it for dW_0
-            acts = (gather_hadamard_raw(h, edges),) + tuple(acts)
         dscore = torch.cat([dpos, dneg]) * g
         if ctx.head == "DOT":
             gh = edge_scatter_raw(h, edges, dscore=dscore)
@@ -882,6 +939,19 @@ class EdgeScoreLoss(torch.autograd.Function):
         L = len(params) // 2
         scale = 1.0 / (1.0 - ctx.drop_p)
         grads = [None] * len(params)
+        if ctx.fused and fused_edge_mlp_bwd_ok(h, acts[0], params):
+            # one pass over a1 for the reductions (dw2, db2, db1), then the two GEMMs with dZ1 formed in their loaders
+            # and the Hadamard product re-gathered inside the dW1 loader: no [P, H] intermediate but dA0
+            a1 = acts[0]
+            _, dw2, db2, db1 = mlp_out_bwd_raw(a1, params[2], dscore, mask_a=True, drop_scale=scale, need_dz=False,
+                                               need_dzsum=True)
+            da0, dw1 = edge_mlp_bwd_raw(h, edges, params[0], a1, dscore, params[2], scale)
+            grads[0], grads[1] = dw1, db1.reshape(params[1].shape)
+            grads[2], grads[3] = dw2.reshape(params[2].shape), db2.reshape(params[3].shape)
+            gh = edge_scatter_raw(h, edges, da=da0)
+            return (gh,) + (None,) * 8 + tuple(grads)
+        if ctx.fused:        # the forward never stored the Hadamard product: re-gather it for dW_0
+            acts = (gather_hadamard_raw(h, edges),) + tuple(acts)
         # last layer: dz w.r.t. the pre-activation of the previous hidden layer (mask fused)
         dz, dw, db = mlp_out_bwd_raw(acts[-1], params[2 * (L - 1)], dscore, mask_a=(L > 1), drop_scale=scale)
         grads[2 * (L - 1)] = dw.reshape(params[2 * (L - 1)].shape)

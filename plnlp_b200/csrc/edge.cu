@@ -85,17 +85,18 @@ __global__ void __launch_bounds__(128) mlp_out_bwd_kernel(const float* __restric
                                                           const float* __restrict__ w,
                                                           const float* __restrict__ dscore, int64_t P, int H,
                                                           int mask_a, float drop_scale, float* __restrict__ dz,
-                                                          int64_t lddz, float* __restrict__ ws_dw) {
+                                                          int64_t lddz, float* __restrict__ ws_dw,
+                                                          float* __restrict__ ws_dzsum) {
     const int64_t r0 = static_cast<int64_t>(blockIdx.x) * MLP_RB;
     const int64_t r1 = min(P, r0 + MLP_RB);
     __shared__ float ds[MLP_RB];
     for (int i = threadIdx.x; i < MLP_RB; i += blockDim.x) ds[i] = (r0 + i < P) ? __ldg(dscore + r0 + i) : 0.0f;
     __syncthreads();
     for (int f = threadIdx.x * VEC; f < H; f += blockDim.x * VEC) {
-        float wv[VEC], acc[VEC];
+        float wv[VEC], acc[VEC], gsum[VEC];
         load_vec<VEC>(wv, w + f);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) acc[e] = 0.0f;
+        for (int e = 0; e < VEC; ++e) acc[e] = gsum[e] = 0.0f;
         // rows are fetched RU at a time (independent loads in flight) and consumed in row order, so the
         // per-column sums keep their order
         constexpr int RU = 4;
@@ -113,8 +114,9 @@ __global__ void __launch_bounds__(128) mlp_out_bwd_kernel(const float* __restric
                     acc[e] = fmaf(d, av[i][e], acc[e]);
                     g[e] = d * wv[e];
                     if (mask_a) g[e] = av[i][e] > 0.0f ? g[e] * drop_scale : 0.0f;
+                    gsum[e] += g[e];
                 }
-                store_vec<VEC>(dz + (r + i) * lddz + f, g);
+                if (dz) store_vec<VEC>(dz + (r + i) * lddz + f, g);
             }
         }
         for (; r < r1; ++r) {
@@ -126,17 +128,21 @@ __global__ void __launch_bounds__(128) mlp_out_bwd_kernel(const float* __restric
                 acc[e] = fmaf(d, av[e], acc[e]);
                 g[e] = d * wv[e];
                 if (mask_a) g[e] = av[e] > 0.0f ? g[e] * drop_scale : 0.0f;
+                gsum[e] += g[e];
             }
-            store_vec<VEC>(dz + r * lddz + f, g);
+            if (dz) store_vec<VEC>(dz + r * lddz + f, g);
         }
         store_vec<VEC>(ws_dw + static_cast<int64_t>(blockIdx.x) * H + f, acc);
+        if (ws_dzsum) store_vec<VEC>(ws_dzsum + static_cast<int64_t>(blockIdx.x) * H + f, gsum);
     }
 }
 
 // dw[j] = sum over row blocks (in block order); the extra last block reduces db = sum dscore.
 __global__ void __launch_bounds__(256) mlp_out_bwd_reduce_kernel(const float* __restrict__ ws_dw, int64_t nblk,
                                                                  int H, const float* __restrict__ dscore, int64_t P,
-                                                                 float* __restrict__ dw, float* __restrict__ db) {
+                                                                 float* __restrict__ dw, float* __restrict__ db,
+                                                                 const float* __restrict__ ws_dzsum,
+                                                                 float* __restrict__ dzsum) {
     const int ncolblk = (H + 255) / 256;
     if (static_cast<int>(blockIdx.x) < ncolblk) {
         const int j = blockIdx.x * 256 + threadIdx.x;
@@ -144,6 +150,11 @@ __global__ void __launch_bounds__(256) mlp_out_bwd_reduce_kernel(const float* __
         float acc = 0.0f;
         for (int64_t b = 0; b < nblk; ++b) acc += ws_dw[b * H + j];
         dw[j] = acc;
+        if (dzsum) {                 // column sums of dz (the previous layer's bias gradient), fp64 over the blocks
+            double s = 0.0;
+            for (int64_t b = 0; b < nblk; ++b) s += static_cast<double>(ws_dzsum[b * H + j]);
+            dzsum[j] = static_cast<float>(s);
+        }
     } else {
         __shared__ double sm[256];
         double acc = 0.0;
@@ -401,31 +412,33 @@ extern "C" int plnlp_mlp_out_fwd_f32(const float* a, int64_t lda, const float* w
 
 extern "C" int64_t plnlp_mlp_out_bwd_workspace_bytes(int64_t P, int64_t H) {
     if (P < 0 || H < 0) return 0;
-    return ceil_div(P, MLP_RB) * H * 4 + 16;
+    return 2 * ceil_div(P, MLP_RB) * H * 4 + 16;
 }
 
 extern "C" int plnlp_mlp_out_bwd_f32(const float* a, int64_t lda, const float* w, const float* dscore, int64_t P,
                                      int64_t H, int mask_a, float drop_scale, float* dz, int64_t lddz, float* dw,
-                                     float* db, void* workspace, int64_t workspace_bytes, void* stream) {
+                                     float* db, float* dzsum, void* workspace, int64_t workspace_bytes,
+                                     void* stream) {
     PLNLP_REQUIRE(P >= 0 && H > 0, PLNLP_E_SIZE);
-    PLNLP_REQUIRE(a && w && dscore && dz && dw && workspace, PLNLP_E_NULL);
-    PLNLP_REQUIRE(lda >= H && lddz >= H, PLNLP_E_SIZE);
+    PLNLP_REQUIRE(a && w && dscore && dw && workspace, PLNLP_E_NULL);
+    PLNLP_REQUIRE(lda >= H && (!dz || lddz >= H), PLNLP_E_SIZE);
     PLNLP_REQUIRE(workspace_bytes >= plnlp_mlp_out_bwd_workspace_bytes(P, H), PLNLP_E_WORKSPACE);
     PLNLP_REQUIRE(aligned(workspace, 16), PLNLP_E_ALIGN);
     const int64_t nblk = ceil_div(P, MLP_RB);
     float* ws = static_cast<float*>(workspace);
+    float* ws2 = dzsum ? ws + nblk * H : nullptr;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (nblk > 0) {
-        const int vec = pick_vec(H, {lda, lddz}, {a, w, dz});
+        const int vec = pick_vec(H, {lda, dz ? lddz : 4}, {a, w, dz, ws2});
         const unsigned grid = static_cast<unsigned>(nblk);
 #define CALL(V) \
-    mlp_out_bwd_kernel<V><<<grid, 128, 0, st>>>(a, lda, w, dscore, P, static_cast<int>(H), mask_a, drop_scale, dz, lddz, ws)
+    mlp_out_bwd_kernel<V><<<grid, 128, 0, st>>>(a, lda, w, dscore, P, static_cast<int>(H), mask_a, drop_scale, dz, lddz, ws, ws2)
         DISPATCH_VEC(vec, CALL);
 #undef CALL
         PLNLP_LAUNCH_CHECK();
     }
     const unsigned rgrid = static_cast<unsigned>((H + 255) / 256 + 1);
-    mlp_out_bwd_reduce_kernel<<<rgrid, 256, 0, st>>>(ws, nblk, static_cast<int>(H), dscore, P, dw, db);
+    mlp_out_bwd_reduce_kernel<<<rgrid, 256, 0, st>>>(ws, nblk, static_cast<int>(H), dscore, P, dw, db, ws2, dzsum);
     PLNLP_LAUNCH_CHECK();
     return 0;
 }

@@ -36,6 +36,14 @@ struct TcGemmParams {
     // this CTA's column half of C[r, c] * w_out[c]; C == NULL skips the store of C.
     const int64_t* a_edges; int64_t a_rows;
     const float* w_out; float* score_part; int64_t score_ld;
+    // fused edge scoring, backward half (plnlp_edge_mlp_bwd_tf32): when dz_dscore != NULL the A operand is
+    //     dZ1[p, c] = A[p, c] > 0 ? (dscore[p] * dz_scale) * w2[c] : 0          (A = the stored activation a1)
+    // formed by the loader (DzLoader) instead of being read from HBM -- K-major for dA0 = dZ1 @ W1 (row = pair,
+    // k = hidden column), MN-major for dW1 = dZ1^T @ a0 (row = hidden column, k = pair).  When b_edges != NULL the
+    // B operand of the second product, a0[p, j] = h[src_p, j] * h[dst_p, j] (B = h, ldb = ldh, b_rows = rows of
+    // h), is re-gathered by the loader (HadamardLoaderMN): neither dZ1 nor the Hadamard product exists in HBM.
+    const float* dz_dscore; const float* dz_w2; float dz_scale;
+    const int64_t* b_edges; int64_t b_rows;
 };
 
 __host__ __device__ constexpr int tile_lbo(int rows) { return 18 * rows + 32; }
@@ -232,6 +240,155 @@ struct GatherLoader {
     __device__ __forceinline__ void stash(uint8_t* hi, uint8_t* lo, const float (&reg)[NR][4]) const {
 #pragma unroll
         for (int i = 0; i < NR; ++i) put_chunk<SPLIT>(hi, lo, soff[i], reg[i]);
+    }
+};
+
+// A-operand provider of the fused edge-scoring BACKWARD: the stored hidden activation a1 = dropout(relu(z1)) is read
+// with Loader's own chunk mapping and turned into dZ1 = (dscore (x) w2) . mask(a1) on the fly -- replaces the
+// [P, N1] matrix plnlp_mlp_out_bwd_f32 writes and both GEMMs read back (layer.py:80-87 backward).
+//   MN = false (dA0 = dZ1 @ W1):   chunk = 4 consecutive hidden columns of one pair: dscore fixed per chunk slot,
+//                                  w2 moves with the slab
+//   MN = true  (dW1 = dZ1^T @ a0): block = 4 hidden columns x 4 pairs: w2 fixed per block slot, dscore moves with
+//                                  the slab (one 16-byte load)
+template <int R, bool MN, bool VEC>
+struct DzLoader {
+    using Base = Loader<R, MN, VEC>;
+    static constexpr int NR = Base::NR;
+    static constexpr int NP = Base::NP;
+    Base base;
+    float fix[NP][4];          // MN: w2 of the block's 4 rows; !MN: fix[i][0] = scaled dscore of the chunk's row
+    const float* mov[NP];      // MN: dscore at the block's first k; !MN: w2 at the chunk's first k
+    float scale;
+
+    __device__ __forceinline__ void init(const float* a1, int64_t ld, int64_t r0, int64_t rows, int64_t kbeg,
+                                         const float* dscore, const float* w2, float s, int tid) {
+        base.init(a1, ld, r0, rows, kbeg, tid);
+        scale = s;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            const int c = tid + LOADERS * i;
+            if (!MN) {
+                const int r = c / KQ;
+                fix[i][0] = (r0 + r) < rows ? __ldg(dscore + r0 + r) * s : 0.0f;
+                fix[i][1] = fix[i][2] = fix[i][3] = 0.0f;
+                mov[i] = w2 + kbeg + base.kq4[i];
+            } else {
+                const int rg = c % (R / 4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) fix[i][e] = (r0 + rg * 4 + e) < rows ? __ldg(w2 + r0 + rg * 4 + e) : 0.0f;
+                mov[i] = dscore + kbeg + base.kq4[i];
+            }
+        }
+    }
+
+    __device__ __forceinline__ void fetch(int kleft, float (&reg)[NR][4]) {
+        base.fetch(kleft, reg);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            float m[4];
+            if (base.kq4[i] + 3 < kleft) {                 // whole group inside K: one 16-byte load
+                const float4 t = __ldg(reinterpret_cast<const float4*>(mov[i]));
+                m[0] = t.x; m[1] = t.y; m[2] = t.z; m[3] = t.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) m[e] = (base.kq4[i] + e) < kleft ? __ldg(mov[i] + e) : 0.0f;
+            }
+            if (!MN) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) reg[i][e] = reg[i][e] > 0.0f ? fix[i][0] * m[e] : 0.0f;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float d = m[j] * scale;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) reg[4 * i + j][e] = reg[4 * i + j][e] > 0.0f ? d * fix[i][e] : 0.0f;
+                }
+            }
+            mov[i] += TBK;
+        }
+    }
+
+    template <bool SPLIT>
+    __device__ __forceinline__ void stash(uint8_t* hi, uint8_t* lo, const float (&reg)[NR][4]) const {
+        base.template stash<SPLIT>(hi, lo, reg);
+    }
+};
+
+// B-operand provider of dW1 = dZ1^T @ a0: element (n = column j of h, k = pair p) is h[src_p, j] * h[dst_p, j], gathered
+// with Loader<R, true, VEC>'s block mapping (4 columns x 4 pairs per block).  The endpoint ids of the NEXT slab are
+// fetched while the current slab's rows are in flight, so a fetch never waits on an index load.
+template <int R, bool VEC>
+struct HadamardLoaderMN {
+    static constexpr int NR = nreg(R, true);
+    static constexpr int NP = NR / 4;
+    static_assert(NP == 1, "one block per loader thread");
+    const float* hcol;          // h + first column of the block
+    const int64_t* eptr;        // edges of the NEXT slab's first pair of this block
+    int64_t ldh, h_rows;
+    int es[4], ed[4];           // endpoint rows of the current slab's 4 pairs (h has < 2^31 rows)
+    int soff, kq4, nrow;
+    bool live;
+
+    __device__ __forceinline__ void load_ids(int kleft) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int64_t s = 0, d = 0;
+            if (live && (kq4 + j) < kleft) {
+                const longlong2 sd = __ldg(reinterpret_cast<const longlong2*>(eptr) + j);     // (src, dst) of one pair
+                s = sd.x < 0 ? sd.x + h_rows : sd.x;
+                d = sd.y < 0 ? sd.y + h_rows : sd.y;
+            }
+            es[j] = static_cast<int>(s);
+            ed[j] = static_cast<int>(d);
+        }
+        eptr += 2 * TBK;
+    }
+
+    __device__ __forceinline__ void init(const float* h, int64_t ld, int64_t rows_h, const int64_t* edges, int64_t n0,
+                                         int64_t n_end, int64_t kbeg, int ktot, int tid) {
+        const int rg = tid % (R / 4), kq = tid / (R / 4);
+        live = tid < (R / 4) * KQ;
+        const int64_t left = n_end - (n0 + rg * 4);
+        kq4 = kq * 4;
+        nrow = !live ? 0 : (left >= 4 ? 4 : (left > 0 ? static_cast<int>(left) : 0));
+        soff = kq * tile_lbo(R) + ((rg * 4) >> 3) * TILE_SBO + ((rg * 4) & 7) * 16;
+        hcol = h + n0 + rg * 4;
+        ldh = ld;
+        h_rows = rows_h;
+        eptr = edges + 2 * (kbeg + kq4);
+        load_ids(ktot);
+    }
+
+    __device__ __forceinline__ void fetch(int kleft, float (&reg)[NR][4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float (&d)[4] = reg[j];
+            const bool kok = (kq4 + j) < kleft;
+            const float* ps = hcol + static_cast<int64_t>(es[j]) * ldh;
+            const float* pd = hcol + static_cast<int64_t>(ed[j]) * ldh;
+            if (VEC) {
+                if (kok && nrow) {
+                    const float4 a = ld_stream4(ps), b = ld_stream4(pd);
+                    d[0] = a.x * b.x; d[1] = a.y * b.y; d[2] = a.z * b.z; d[3] = a.w * b.w;
+                } else {
+                    d[0] = d[1] = d[2] = d[3] = 0.0f;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) d[e] = (kok && e < nrow) ? __ldg(ps + e) * __ldg(pd + e) : 0.0f;
+            }
+        }
+        load_ids(kleft - TBK);          // ids of the slab the NEXT call fetches
+    }
+
+    template <bool SPLIT>
+    __device__ __forceinline__ void stash(uint8_t* hi, uint8_t* lo, const float (&reg)[NR][4]) const {
+        if (!live) return;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {      // row rg*4 + e gets (k%4 = 0..3) from the 4 loads
+            const float v[4] = {reg[0][e], reg[1][e], reg[2][e], reg[3][e]};
+            put_chunk<SPLIT>(hi, lo, soff + e * 16, v);
+        }
     }
 };
 

@@ -34,10 +34,14 @@ struct Cfg2 {
     static constexpr int STAGES = SPLIT ? 3 : 6;      // 2 CTAs per SM share the 227 KB
 };
 
-// AGATHER: the A operand is gathered (GatherLoader): fused edge scoring, see plnlp_edge_mlp_fwd_tf32 below
-template <bool AMN, bool BMN, bool VA, bool VB, bool SPLIT, bool AGATHER = false>
+// AMODE: 0 = A read as stored; 1 = A gathered (GatherLoader): fused edge scoring forward, see plnlp_edge_mlp_fwd_tf32
+// below; 2 = A = dZ1 formed from the stored activation (DzLoader): fused edge scoring backward, plnlp_edge_mlp_bwd_tf32.
+// BHAD: the (MN-major) B operand is the re-gathered Hadamard product (HadamardLoaderMN).
+template <bool AMN, bool BMN, bool VA, bool VB, bool SPLIT, int AMODE = 0, bool BHAD = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 2)
     gemm_tcgen05_2cta_kernel(const TcGemmParams p) {
+    constexpr bool AGATHER = AMODE == 1;
+    static_assert(!BHAD || BMN, "the Hadamard B operand is MN-major");
     constexpr int STAGES = Cfg2<SPLIT>::STAGES;
     constexpr int A_SLOT = slot_bytes(TBM), B_SLOT = slot_bytes(BH2);
     constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_SLOT + B_SLOT);
@@ -79,14 +83,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 2)
     if (warp < 8) {
         // ============================ loaders ============================
         float ra[2][nreg(TBM, AMN)][4], rb[2][nreg(BH2, BMN)][4];
-        typename std::conditional<AGATHER, GatherLoader<TBM, VA>, Loader<TBM, AMN, VA>>::type la;
-        Loader<BH2, BMN, VB> lb;
+        typename std::conditional<AGATHER, GatherLoader<TBM, VA>,
+                                  typename std::conditional<AMODE == 2, DzLoader<TBM, AMN, VA>,
+                                                            Loader<TBM, AMN, VA>>::type>::type la;
+        typename std::conditional<BHAD, HadamardLoaderMN<BH2, VB>, Loader<BH2, BMN, VB>>::type lb;
         const int64_t b0 = n0 + static_cast<int64_t>(rank) * bhalf;
         const int64_t b_end = (b0 + bhalf) < p.N ? (b0 + bhalf) : p.N;   // rows past this CTA's half are zero
-        if constexpr (AGATHER) la.init(p.A, p.lda, p.a_rows, p.a_edges, m0, p.M, kbeg, tid);
-        else la.init(p.A, p.lda, m0, p.M, kbeg, tid);
-        lb.init(p.B, p.ldb, b0, b_end, kbeg, tid);
         const int ktot = static_cast<int>(kend - kbeg);
+        if constexpr (AGATHER) la.init(p.A, p.lda, p.a_rows, p.a_edges, m0, p.M, kbeg, tid);
+        else if constexpr (AMODE == 2) la.init(p.A, p.lda, m0, p.M, kbeg, p.dz_dscore, p.dz_w2, p.dz_scale, tid);
+        else la.init(p.A, p.lda, m0, p.M, kbeg, tid);
+        if constexpr (BHAD) lb.init(p.B, p.ldb, p.b_rows, p.b_edges, b0, b_end, kbeg, ktot, tid);
+        else lb.init(p.B, p.ldb, b0, b_end, kbeg, tid);
         auto fetch = [&](int it, float (&a)[nreg(TBM, AMN)][4], float (&b)[nreg(BH2, BMN)][4]) {
             if (it < n_iter) {
                 la.fetch(ktot - it * TBK, a);
@@ -172,11 +180,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 2)
     if (warp == 8) tc::tmem_dealloc_2cta<BN2>(tmem_d);
 }
 
-template <bool AMN, bool BMN, bool VA, bool VB, bool SPLIT, bool AGATHER = false>
+template <bool AMN, bool BMN, bool VA, bool VB, bool SPLIT, int AMODE = 0, bool BHAD = false>
 int launch_one2(const TcGemmParams& p, dim3 grid, cudaStream_t st) {
     constexpr int bytes = Cfg2<SPLIT>::STAGES * (SPLIT ? 2 : 1) * (slot_bytes(TBM) + slot_bytes(BH2));
     static_assert(bytes <= 113 * 1024, "two CTAs per SM");
-    auto kern = gemm_tcgen05_2cta_kernel<AMN, BMN, VA, VB, SPLIT, AGATHER>;
+    auto kern = gemm_tcgen05_2cta_kernel<AMN, BMN, VA, VB, SPLIT, AMODE, BHAD>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -283,12 +291,85 @@ extern "C" int plnlp_edge_mlp_fwd_tf32(int passes, const float* h, int64_t ldh, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc;
     if (va && vb) {
-        rc = passes == 3 ? launch_one2<false, false, true, true, true, true>(p, grid, st)
-                         : launch_one2<false, false, true, true, false, true>(p, grid, st);
+        rc = passes == 3 ? launch_one2<false, false, true, true, true, 1>(p, grid, st)
+                         : launch_one2<false, false, true, true, false, 1>(p, grid, st);
     } else {
-        rc = launch_one2<false, false, false, false, true, true>(p, grid, st);
+        rc = launch_one2<false, false, false, false, true, 1>(p, grid, st);
     }
     if (rc != 0) return rc;
     PLNLP_LAUNCH_CHECK();
+    return 0;
+}
+
+
+// Fused edge scoring, MLP head BACKWARD (model.py:161 through layer.py:80-87): with a1 = dropout(relu(a0 W1^T + b1))
+// stored by the forward and dscore = d loss / d score from the pair loss,
+//     dZ1 = (dscore (x) w2) . [a1 > 0] * drop_scale        formed in the loaders, never written to HBM
+//     dA0 = dZ1 @ W1                    [P, H]             (the gradient of the Hadamard product, scattered next)
+//     dW1 = dZ1^T @ (h[src] * h[dst])   [N1, H]            the Hadamard product re-gathered by the loader
+// Two launches (+ the split-k reduction of dW1).  dw2 / db2 / db1 come from plnlp_mlp_out_bwd_f32 with dz = NULL.
+extern "C" int64_t plnlp_edge_mlp_bwd_workspace_bytes(int64_t P, int64_t H, int64_t N1, int split_k) {
+    if (P <= 0 || H <= 0 || N1 <= 0) return 0;
+    if (split_k < 1) split_k = 1;
+    return static_cast<int64_t>(split_k) * N1 * H * 4 + 16;
+}
+
+extern "C" int plnlp_edge_mlp_bwd_tf32(int passes, const float* h, int64_t ldh, int64_t n_rows, const int64_t* edges,
+                                       int64_t P, int64_t H, const float* W1, int64_t ldw, int64_t N1,
+                                       const float* a1, int64_t lda1, const float* dscore, const float* w2,
+                                       float drop_scale, float* dA0, int64_t ldda0, float* dW1, int64_t lddw1,
+                                       float* workspace, int64_t workspace_bytes, int split_k, void* stream) {
+    using namespace plnlp;
+    using namespace plnlp::tcgemm;
+    PLNLP_REQUIRE(passes == 1 || passes == 3, PLNLP_E_UNSUPPORTED);
+    PLNLP_REQUIRE(P >= 0 && H > 0 && N1 > 0 && n_rows > 0, PLNLP_E_SIZE);
+    if (P == 0) return 0;
+    PLNLP_REQUIRE(h && edges && W1 && a1 && dscore && w2 && dA0 && dW1, PLNLP_E_NULL);
+    PLNLP_REQUIRE(ldh >= H && ldw >= H && lda1 >= N1 && ldda0 >= H && lddw1 >= H, PLNLP_E_SIZE);
+    PLNLP_REQUIRE(N1 <= 1088, PLNLP_E_UNSUPPORTED);      // dA0 uses one accumulator over K = N1 (RZ error budget)
+    // the loaders use whole 16-byte vectors
+    PLNLP_REQUIRE((H % 4 == 0) && (N1 % 4 == 0) && (ldh % 4 == 0) && (ldw % 4 == 0) && (lda1 % 4 == 0), PLNLP_E_ALIGN);
+    PLNLP_REQUIRE(aligned(h, 16) && aligned(W1, 16) && aligned(a1, 16), PLNLP_E_ALIGN);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    // ---- dA0 = dZ1 @ W1: M = P, N = H, K = N1; A = dZ1 (K-major, from a1), B[k = c, n = j] = W1[c*ldw + j] (MN-major)
+    {
+        TcGemmParams p{};
+        p.M = P; p.N = H; p.K = N1; p.A = a1; p.lda = lda1; p.B = W1; p.ldb = ldw; p.C = dA0; p.ldc = ldda0;
+        p.passes = passes; p.split_k = 1; p.k_per_split = ceil_div(N1, TBK) * TBK;
+        p.dz_dscore = dscore; p.dz_w2 = w2; p.dz_scale = drop_scale;
+        const dim3 grid(static_cast<unsigned>(2 * ceil_div(P, 2 * TBM)), static_cast<unsigned>(ceil_div(H, BN2)), 1);
+        int rc = passes == 3 ? launch_one2<false, true, true, true, true, 2>(p, grid, st)
+                             : launch_one2<false, true, true, true, false, 2>(p, grid, st);
+        if (rc != 0) return rc;
+        PLNLP_LAUNCH_CHECK();
+    }
+    // ---- dW1 = dZ1^T @ a0: M = N1, N = H, K = P; A[m = c, k = p] = dZ1[p, c] (MN-major, from a1),
+    //      B[k = p, n = j] = h[src_p, j] * h[dst_p, j] (MN-major, gathered)
+    {
+        if (split_k < 1) split_k = 1;
+        TcGemmParams p{};
+        p.M = N1; p.N = H; p.K = P; p.A = a1; p.lda = lda1; p.B = h; p.ldb = ldh; p.C = dW1; p.ldc = lddw1;
+        p.passes = passes;
+        int64_t kper = ceil_div(ceil_div(P, split_k), TBK) * TBK;
+        p.k_per_split = kper;
+        p.split_k = split_k = static_cast<int>(ceil_div(P, kper));
+        p.ws = workspace;
+        if (split_k > 1) {
+            PLNLP_REQUIRE(workspace, PLNLP_E_NULL);
+            PLNLP_REQUIRE(workspace_bytes >= static_cast<int64_t>(split_k) * N1 * H * 4, PLNLP_E_WORKSPACE);
+            PLNLP_REQUIRE(aligned(workspace, 16), PLNLP_E_ALIGN);
+        }
+        p.dz_dscore = dscore; p.dz_w2 = w2; p.dz_scale = drop_scale;
+        p.b_edges = edges; p.b_rows = n_rows;
+        PLNLP_REQUIRE(aligned(dscore, 16), PLNLP_E_ALIGN);
+        const dim3 grid(static_cast<unsigned>(2 * ceil_div(N1, 2 * TBM)), static_cast<unsigned>(ceil_div(H, BN2)),
+                        static_cast<unsigned>(split_k));
+        int rc = passes == 3 ? launch_one2<true, true, true, true, true, 2, true>(p, grid, st)
+                             : launch_one2<true, true, true, true, false, 2, true>(p, grid, st);
+        if (rc != 0) return rc;
+        PLNLP_LAUNCH_CHECK();
+        if (split_k > 1) return tc_splitk_reduce(p, st);
+    }
     return 0;
 }

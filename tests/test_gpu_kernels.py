@@ -111,6 +111,68 @@ def test_spmm_narrow_rows_two_per_warp(ops, F, layout):
     assert torch.equal(a, b) and not torch.isnan(a).any()
 
 
+@pytest.mark.parametrize("F,layout", [(50, "own"), (50, "pitch64"), (64, "own"), (32, "offset"), (18, "own"), (2, "own")])
+def test_spmm_tuning_modes_keep_every_bit(ops, F, layout):
+    """plnlp_spmm_tune: the L2 row prefetch (modes 1, 2) and the shared-memory staged kernel (cp.async row copies,
+    every pipeline shape, 8- and 16-byte pieces) give the bits of the plain register kernels -- valued / value-less /
+    mean, hub rows cut into items (partial slots), empty rows, the fused epilogue, a row-subset plan and a column
+    slice as the output; wide operands (F = 200, prefetch only) and the row-sparse operand as well"""
+    from plnlp_b200 import _lib
+    from plnlp_b200.graph import Structure, build_subset_plan
+    lib = _lib.load()
+    N = 1500
+    ei, w = rand_graph(N, 30000, seed=300 + F, weighted=True, hub=True)
+    gen = torch.Generator().manual_seed(F)
+    x = torch.randn(N, F, generator=gen)
+    if layout == "own":
+        xg = x.cuda()
+    elif layout == "pitch64":
+        xg = torch.full((N, 64), float("nan")).cuda()[:, :F]
+        xg.copy_(x)
+    else:
+        xg = torch.full((N, 136), float("nan")).cuda()[:, 8:8 + F]
+        xg.copy_(x)
+    bias = torch.randn(F, generator=gen).cuda()
+    mask = torch.randn(N, F, generator=gen).cuda()
+    xw = torch.randn(N, 200, generator=gen).cuda()
+    xi = torch.arange(N, dtype=torch.int32)
+    xi[torch.rand(N, generator=gen) < 0.7] = -1
+    xi = xi.cuda()
+
+    def run_all():
+        outs = []
+        for weights, reduce, chunk in ((w, "sum", 1024), (None, "mean", 64), (w, "sum", 32)):
+            o = sparse.to_sparse_tensor(ei, weights, N)
+            st = Structure(_to_gpu_graph(o), chunk=chunk)
+            wide = torch.full((N, 96), -7.0).cuda()
+            ops.spmm_raw(st.fwd, xg, use_val=weights is not None, div_rows=(reduce == "mean"), out=wide[:, 6:6 + F])
+            outs.append(wide)
+            outs.append(ops.spmm_raw(st.fwd, xg, use_val=weights is not None, div_rows=False, bias=bias, relu=True,
+                                     drop_p=0.25, seed=5, mask=mask, mask_scale=1.25))
+            rows = torch.randperm(N, generator=gen)[:400].sort().values.cuda()
+            sub = build_subset_plan(st.fwd, o.csr()[0].cuda(), rows)
+            outs.append(ops.spmm_raw(sub, xg, use_val=weights is not None, div_rows=False))
+            outs.append(ops.spmm_raw(st.fwd, xw, use_val=weights is not None, div_rows=False))
+            outs.append(ops.spmm_raw(st.fwd, xw, use_val=weights is not None, div_rows=False, x_index=xi))
+        return outs
+
+    try:
+        assert lib.plnlp_spmm_tune(0, 0, 4, 0) == 0
+        gen.manual_seed(F)
+        base = run_all()
+        assert not any(torch.isnan(t).any() for t in base)
+        for pf, staged, warps in ((1, 0, 4), (2, 0, 4), (3, 0, 4), (0, 1, 4), (0, 2, 3), (0, 3, 16), (0, 4, 1), (0, 5, 8),
+                                  (0, 6, 4), (0, 7, 5), (0, 8, 2), (0, 9, 4), (0, 10, 4), (0, 11, 7), (1, 1, 2), (3, 12, 4)):
+            assert lib.plnlp_spmm_tune(pf, staged, warps, 0) == 0
+            gen.manual_seed(F)
+            got = run_all()
+            for a, b in zip(base, got):
+                assert torch.equal(a, b), (pf, staged, warps)
+    finally:
+        lib.plnlp_spmm_tune(-1, -1, 0, 0)          # leave the knobs as the package set them
+        ops.apply_spmm_defaults()
+
+
 @pytest.mark.parametrize("chunk", [32, 64])
 def test_spmm_split_rows(ops, chunk):
     from plnlp_b200.graph import Structure
@@ -801,28 +863,57 @@ def test_fused_edge_mlp_forward(ops, N, H, P):
     assert rel_err(sd, ops.mlp_out_fwd_raw(au, w2.cuda(), b2.cuda())) < TOL
 
 
-def test_fused_and_unfused_step_agree(ops):
-    """EdgeScoreLoss with the fused forward vs the unfused kernels: same loss and gradients"""
-    g = torch.Generator().manual_seed(21)
-    N, H, B, k = 300, 128, 200, 3
+@pytest.mark.parametrize("N,H,N1,B,k,drop", [(300, 128, 128, 200, 3, 0.0), (4267, 512, 512, 1500, 3, 0.3),
+                                             (999, 200, 200, 1234, 1, 0.0), (500, 64, 192, 257, 2, 0.5),
+                                             (77, 256, 320, 4100, 3, 0.0)])
+def test_fused_and_unfused_step_agree(ops, N, H, N1, B, k, drop):
+    """EdgeScoreLoss three ways -- fused forward + fused backward (dZ1 formed in the GEMM loaders, Hadamard product
+    re-gathered inside the weight-gradient GEMM), fused forward + unfused backward, everything unfused: same loss and
+    gradients; the gradients of the fused backward also against fp64 autograd on the same dropout mask"""
+    from plnlp_b200 import _lib
+    g = torch.Generator().manual_seed(21 + N)
     h0 = torch.randn(N, H, generator=g)
     pos, neg = torch.randint(0, N, (B, 2), generator=g), torch.randint(0, N, (B * k, 2), generator=g)
-    params0 = [torch.randn(H, H, generator=g) / H ** 0.5, torch.randn(H, generator=g),
-               torch.randn(1, H, generator=g) / H ** 0.5, torch.randn(1, generator=g)]
+    pos[0] = torch.tensor([-1, 3])                       # negative index = counted from the end
+    params0 = [torch.randn(N1, H, generator=g) / H ** 0.5, torch.randn(N1, generator=g),
+               torch.randn(1, N1, generator=g) / N1 ** 0.5, torch.randn(1, generator=g)]
     out = {}
-    for fused in (True, False):
-        ops.FUSED_EDGE_MLP = fused
+    for mode in ("fused", "fused_fwd", "unfused"):
+        ops.FUSED_EDGE_MLP = mode != "unfused"
+        ops.FUSED_EDGE_BWD = "1" if mode == "fused" else "0"
         try:
             h = h0.cuda().requires_grad_(True)
             params = [p.cuda().requires_grad_(True) for p in params0]
-            loss = ops.edge_score_loss(h, pos.cuda(), neg.cuda(), k, "AUC", head="MLP", params=params)
+            n0 = _lib.launch_count()
+            loss = ops.edge_score_loss(h, pos.cuda(), neg.cuda(), k, "AUC", head="MLP", params=params, drop_p=drop, seed=5)
             loss.backward()
-            out[fused] = [loss.detach(), h.grad] + [p.grad for p in params]
+            out[mode] = [loss.detach(), h.grad] + [p.grad for p in params]
+            out[mode + "_launches"] = _lib.launch_count() - n0
         finally:
             ops.FUSED_EDGE_MLP = True
-    floor = TOL * max(float(t.abs().max()) for t in out[False][1:])
-    for a, b in zip(out[True], out[False]):
-        assert rel_err(a, b) < 2e-5 or float((a - b).abs().max()) <= floor
+            ops.FUSED_EDGE_BWD = "auto"
+    assert out["fused_launches"] < out["fused_fwd_launches"] <= out["unfused_launches"]
+    floor = TOL * max(float(t.abs().max()) for t in out["unfused"][1:])
+    for mode in ("fused", "fused_fwd"):
+        for a, b in zip(out[mode], out["unfused"]):
+            assert rel_err(a, b) < 2e-5 or float((a - b).abs().max()) <= floor, mode
+    # fp64 autograd with the kernel's own dropout mask (read off the stored activation)
+    edges = torch.cat([pos, neg]).cuda()
+    _, a1 = ops.edge_mlp_fwd_raw(h0.cuda(), edges, params0[0].cuda(), params0[1].cuda(), params0[2].cuda(),
+                                 params0[3].cuda(), drop, 5 + 7919)
+    keep = (a1 > 0).double().cpu()
+    hd = h0.double().requires_grad_(True)
+    pd = [p.double().requires_grad_(True) for p in params0]
+    e = torch.cat([pos, neg])
+    a0 = hd[e[:, 0]] * hd[e[:, 1]]
+    z1 = a0 @ pd[0].t() + pd[1]
+    act = z1 * keep / (1.0 - drop)                        # keep already holds relu and dropout: a1 > 0
+    score = (act @ pd[2].t()).reshape(-1) + pd[3]
+    sp, sn = score[:B], score[B:].reshape(B, k)
+    ((1 - (sp.unsqueeze(1) - sn)) ** 2).sum().backward()
+    want = [hd.grad] + [p.grad for p in pd]
+    for a, b in zip(out["fused"][1:], want):
+        assert rel_err(a.cpu(), b) < 2e-5 or float((a.cpu().double() - b).abs().max()) <= floor
 
 
 # ------------------------------------------------------------------ dense tensor-core path of the aggregation

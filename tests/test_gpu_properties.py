@@ -45,7 +45,10 @@ def test_spmm_kernel_matches_in_order_loop(g, F, reduce, chunk):
     plan_t = st_.bwd_mean if reduce == "mean" else st_.bwd
     aty = _ops.spmm_raw(plan_t, y, use_val=True if reduce == "mean" else st_.has_value, div_rows=False)
     lhs, rhs = float((got.cuda().double() * y.double()).sum()), float((x.cuda().double() * aty.double()).sum())
-    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1e-3)
+    # <Ax, y> = <x, A^T y>: both sides are sums with cancellation, so the yardstick is the size of the summands
+    # (hypothesis found n = 51, F = 1 with |sum| = 0.02 against terms of order 1: 8e-7 apart, i.e. fp32 rounding)
+    scale = float((got.cuda().double().abs() * y.double().abs()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1e-3) or abs(lhs - rhs) <= 1e-6 * scale
 
 
 @settings(max_examples=25, deadline=None)
