@@ -179,6 +179,16 @@ int plnlp_gemm_tf32_tma(int passes, int transb, int64_t M, int64_t N, int64_t K,
                         const float* aux, int64_t ldaux, float drop_p, uint64_t seed,
                         float* workspace, int64_t workspace_bytes, void* stream);
 
+/* Weight gradients over a huge row count:  C[M, N] = A^T . B  with A [K, M] (lda) and B [K, N] (ldb) row-major, M, N <= 256
+ * (dW = dY^T [A_hat x | 1] of the first encoder layer, layer.py:20,23 backward: 200 x 179 x 2 927 963).  TMA-fed,
+ * persistent, tcgen05.mma on MN-major operands straight from the TMA boxes (nothing is transposed), hi / lo split by
+ * convert warps, one accumulator per 1088 K-rows combined with RN adds, CTA partials added in CTA order
+ * (deterministic).  lda, ldb multiples of 4, bases 16-byte aligned, N >= 8.  workspace: one [256][256] fp32 partial per SM. */
+int64_t plnlp_gemm_tf32_tma_tn_workspace_bytes(void);
+int plnlp_gemm_tf32_tma_tn(int passes, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                           const float* B, int64_t ldb, float* C, int64_t ldc, float* workspace,
+                           int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Edge scoring (replaces h[edge[0]], h[edge[1]] advanced indexing + MLPPredictor /
  * DotPredictor, model.py:152-156,180 and layer.py:80-87,174-176).

@@ -32,6 +32,8 @@ SIGNATURES = {
     "plnlp_gemm_tf32_2cta": (c_int, [_I, _I, _I, _L, _L, _L, _P, _L, _P, _L, _P, _L, _F, _P, _I, _P, _L, _F, _U, _P, _L, _I, _P]),
     "plnlp_gemm_tf32_tma_workspace_bytes": (c_int64, [_L, _L]),
     "plnlp_gemm_tf32_tma": (c_int, [_I, _I, _L, _L, _L, _P, _L, _P, _L, _P, _L, _F, _P, _I, _P, _L, _F, _U, _P, _L, _P]),
+    "plnlp_gemm_tf32_tma_tn_workspace_bytes": (c_int64, []),
+    "plnlp_gemm_tf32_tma_tn": (c_int, [_I, _L, _L, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P]),
     "plnlp_edge_mlp_fwd_tf32": (c_int, [_I, _P, _L, _L, _P, _L, _L, _P, _L, _P, _L, _F, _U, _P, _P, _L, _P, _L, _P]),
     "plnlp_gather_hadamard_f32": (c_int, [_P, _L, _L, _P, _L, _L, _P, _L, _P]),
     "plnlp_segment_softmax_fwd_f32": (c_int, [_P, _L, _P, _F, _P, _P]),

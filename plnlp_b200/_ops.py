@@ -36,6 +36,11 @@ TF32X3_KCAP = int(os.environ.get("PLNLP_GEMM_KCAP", "1088"))
 # N, K of a few hundred: "auto" = when M >= 16 384, N <= 256 and K <= 512 (the encoder's dense layers on the big
 # graphs; the large-K predictor GEMMs of the ddi shape stay on the CTA-pair kernel), "1" = whenever legal, "0" = off
 GEMM_TMA = os.environ.get("PLNLP_GEMM_TMA", "auto")
+# ... and its counterpart for weight gradients C = A^T B over a huge K with M, N <= 256 (csrc/gemm_tma_tn.cu): "auto" =
+# when every SM gets at least four 1088-row units (K >= 644 096: the layer-1 weight gradient of the citation2 shape;
+# at K = 262 144 the 241 units leave the 148 persistent CTAs unevenly loaded and the CTA-pair kernel is as fast),
+# "1" = whenever legal, "0" = off
+GEMM_TMA_TN = os.environ.get("PLNLP_GEMM_TMA_TN", "auto")
 
 # fused edge scoring for the MLP head (gather + Hadamard + layer 1 + out layer in one tcgen05 kernel)
 FUSED_EDGE_MLP = os.environ.get("PLNLP_FUSED_EDGE", "1") != "0"
@@ -190,6 +195,18 @@ def gemm_raw(A, B, transa=False, transb=False, C=None, beta=0.0, bias=None, act=
             check(lib.plnlp_gemm_tf32_tma(passes, int(transb), M, N, K, ptr(A), _ld(A), ptr(B), _ld(B), ptr(C), _ld(C),
                                           float(beta), ptr(bias), int(act), ptr(aux), _ld(aux) if aux is not None else 0,
                                           float(drop_p), int(seed), ptr(wsb), nbytes, stream()), "plnlp_gemm_tf32_tma")
+        return C
+    if (backend in ("tf32x3c2", "tf32c2", "tf32x3", "tf32") and GEMM_TMA_TN != "0" and transa and not transb
+            and M <= 256 and 8 <= N <= 256 and beta == 0.0 and bias is None and act == ACT_NONE
+            and _ld(A) % 4 == 0 and _ld(B) % 4 == 0 and A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0
+            and (GEMM_TMA_TN == "1" or K >= 4 * 148 * TF32X3_KCAP)):
+        # weight gradient over a huge row count: both operands MN-major, consumed as the TMA lands them
+        nbytes = lib.plnlp_gemm_tf32_tma_tn_workspace_bytes()
+        wsp = workspace.get("gemm_tma_tn", nbytes, A.device)
+        passes = 3 if backend.startswith("tf32x3") else 1
+        with profiling.span(f"gemm_tf32x{passes}_tma_tn {M}x{N}x{K}", 0, 2 * M * N * K):
+            check(lib.plnlp_gemm_tf32_tma_tn(passes, M, N, K, ptr(A), _ld(A), ptr(B), _ld(B), ptr(C), _ld(C), ptr(wsp),
+                                             nbytes, stream()), "plnlp_gemm_tf32_tma_tn")
         return C
     tail = (int(transa), int(transb), M, N, K, ptr(A), _ld(A), ptr(B), _ld(B), ptr(C), _ld(C),
             float(beta), ptr(bias), int(act), ptr(aux), _ld(aux) if aux is not None else 0,

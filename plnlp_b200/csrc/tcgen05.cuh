@@ -218,6 +218,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
         "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// the 3-D form (c0 innermost)
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

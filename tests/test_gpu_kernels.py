@@ -783,6 +783,34 @@ def test_gemm_tma_epilogues(ops, monkeypatch):
     assert 1e-5 < rel_err(fast, want) < 5e-3
 
 
+@pytest.mark.parametrize("M,N,K,lda,ldb", [(200, 179, 40000, 200, 180), (128, 64, 20011, 128, 64), (256, 256, 5000, 256, 256),
+                                           (72, 8, 3000, 72, 8), (200, 180, 1088 * 3 + 5, 204, 184), (33, 250, 1088, 36, 252),
+                                           (130, 17, 600, 132, 20)])
+def test_gemm_tma_tn_weight_gradient(ops, M, N, K, lda, ldb, monkeypatch):
+    """C = A^T B over a huge row count on the TMA-fed kernel (MN-major operands straight from the TMA boxes, hi / lo split
+    by convert warps, one accumulator per 1088 rows, CTA partials added in order): against fp64, deterministic, operands
+    with leading dimensions, partial units / slabs / 32-column atoms, one and two 128-row halves"""
+    from plnlp_b200 import _lib
+    monkeypatch.setattr(ops, "GEMM_TMA_TN", "1")
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(K, lda, generator=g)[:, :M]
+    B = torch.randn(K, ldb, generator=g)[:, :N]
+    Ag, Bg = torch.full((K, lda), float("nan")).cuda()[:, :M], torch.full((K, ldb), float("nan")).cuda()[:, :N]
+    Ag.copy_(A)
+    Bg.copy_(B)
+    want = A.double().t() @ B.double()
+    n0 = _lib.launch_count()
+    got = ops.gemm_raw(Ag, Bg, transa=True, backend="tf32x3c2")
+    assert _lib.launch_count() - n0 == 2                      # the TMA kernel + the reduction of the CTA partials
+    assert rel_err(got.cpu(), want) < TOL
+    assert torch.equal(got, ops.gemm_raw(Ag, Bg, transa=True, backend="tf32x3c2"))
+    wide = torch.full((M, N + 5), -2.0).cuda()
+    ops.gemm_raw(Ag, Bg, transa=True, C=wide[:, 2:2 + N], backend="tf32x3c2")
+    assert torch.equal(wide[:, 2:2 + N], got) and torch.all(wide[:, :2] == -2.0) and torch.all(wide[:, 2 + N:] == -2.0)
+    fast = ops.gemm_raw(Ag, Bg, transa=True, backend="tf32c2")
+    assert rel_err(fast.cpu(), want) < 5e-3
+
+
 def test_gemm_tf32x3_2cta_epilogues_and_splitk(ops):
     g = torch.Generator().manual_seed(6)
     A, W = torch.randn(1000, 512, generator=g), torch.randn(384, 512, generator=g)
