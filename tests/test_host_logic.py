@@ -230,3 +230,99 @@ def test_sample_perm_copy_replays_reference(golden_dir):
         assert torch.equal(e, rec["edge_index"])
         out = sample_perm_copy(e, rec["target"], rec["k"])
         assert out.dtype == torch.int64 and torch.equal(out, rec["out"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# python restatements of the index arithmetic of the shared-memory staged SpMM (csrc/spmm.cu,
+# spmm_csr_staged_kernel) and of the launch geometry of the TMA-fed weight-gradient GEMM (csrc/gemm_tma_tn.cu):
+# the GPU tests prove the kernels, these keep the reasoning behind them checkable without a GPU
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_items", [1, 31, 32, 33, 1000, 2928161])
+def test_staged_spmm_strided_item_assignment_covers_every_item_once(n_items):
+    """warp w owns items w, w + W, w + 2W, ... with W = ceil(n_items / 32): every item exactly once, at most 32 per
+    warp, and the consecutive chunk items of a hub row land in different warps"""
+    W = -(-n_items // 32)
+    seen = torch.zeros(n_items, dtype=torch.int32)
+    w = torch.arange(W)
+    cnt = torch.clamp(-(-(n_items - w) // W), max=32)            # ceil((n_items - w) / W), the kernel's `cnt`
+    assert int(cnt.min()) >= 1 and int(cnt.max()) <= 32 and int(cnt.sum()) == n_items
+    for lane in range(32):
+        item = w + lane * W
+        ok = lane < cnt
+        assert bool((item[ok] < n_items).all()) and bool((item[~ok] >= n_items).all())
+        seen[item[ok]] += 1
+    assert bool((seen == 1).all())
+    if n_items >= 64 and W >= 25:
+        hub = torch.arange(7, 7 + 25)                            # 25 consecutive chunk items of one hub row
+        assert torch.unique(hub % W).numel() == 25               # 25 different warps
+
+
+@pytest.mark.parametrize("cap", [8, 16, 32])
+def test_staged_spmm_batches_of_an_item(cap):
+    """every item yields max(1, ceil(len / CAP)) batches, the last one flagged; an empty item yields one empty batch
+    (its row still gets bias / zeros written)"""
+    for length in (0, 1, cap - 1, cap, cap + 1, 3 * cap, 3 * cap + 5, 1024):
+        beg, end = 100, 100 + length
+        base, batches = beg, []
+        while True:                                              # the kernel's iterator
+            n = max(0, min(cap, end - base))
+            last = base + cap >= end
+            batches.append((n, last))
+            base += cap
+            if base >= end:
+                break
+        assert len(batches) == max(1, -(-length // cap))
+        assert sum(n for n, _ in batches) == length
+        assert [last for _, last in batches] == [False] * (len(batches) - 1) + [True]
+
+
+@pytest.mark.parametrize("F,ldx", [(50, 50), (18, 18), (2, 2), (62, 62), (50, 54), (30, 38)])
+def test_staged_spmm_aligned_window_arithmetic(F, ldx):
+    """rows on a pitch of 4k + 2 floats, table 16-byte aligned: the copy takes the 16-byte aligned window around the row;
+    the entry record says where the row's first float landed; only the window of an EVEN last row leaves the table, and
+    cutting its last piece to 8 bytes keeps every copied byte inside"""
+    assert ldx % 4 == 2 and F % 2 == 0 and ldx >= F
+    lpr = -(-(F * 4 + 8) // 16)                                  # 16-byte pieces per row slot
+    for rows in (1, 2, 7, 8):
+        table_bytes = ((rows - 1) * ldx + F) * 4                 # the last row has no pitch padding behind it
+        for c in range(rows):
+            eoff = c * ldx                                       # element offset of the row (fits 32 bits: staged_ok)
+            start = (eoff & ~3) * 4                              # window start, bytes from the 16-byte aligned base
+            off = (eoff & 2) << 2                                # where the row's first float sits in its slot
+            assert start % 16 == 0 and off in (0, 8) and start + off == eoff * 4
+            assert off + F * 4 <= lpr * 16                       # the slot holds the whole row
+            for part in range(lpr):                              # the pieces the issue loop copies
+                lo = start + part * 16
+                cut = part == lpr - 1 and c == rows - 1 and not (eoff & 2)
+                size = 8 if cut else 16
+                needed = lo < eoff * 4 + F * 4                   # piece overlaps the row's data
+                if lo + size > table_bytes:
+                    # a piece may only stick out of the table if the row does not need it ... and then only for
+                    # the last row's tail piece, which the kernel cuts (so this must never trigger with the cut)
+                    assert not needed and c == rows - 1, (F, ldx, rows, c, part)
+                    assert False, "an uncut piece leaves the table"
+                if cut:                                          # the cut piece still covers what the row needs of it
+                    assert eoff * 4 + F * 4 <= lo + 8
+
+
+def test_weight_gradient_gemm_launch_geometry():
+    """gemm_tma_tn.cu: stage layout [4 or 8 atoms of A | atoms of B], ring depth chosen to fit 227 KB, units of 1088
+    K-rows spread contiguously over at most 148 persistent CTAs"""
+    ATOM, UNIT, SM = 16 * 128, 1088, 148
+    for M, N in ((200, 179), (128, 64), (256, 256), (72, 8), (33, 250), (130, 17), (1, 8)):
+        ma_live, ma = -(-M // 32), (8 if M > 128 else 4)
+        n_mma = -(-N // 16) * 16
+        na = -(-n_mma // 32)
+        assert ma_live <= ma and n_mma <= 256 and 32 * na >= n_mma
+        assert (M // 32) <= ma_live and (N // 32) <= na          # atoms fetched by the 3-D box are a prefix
+        stages = min(4, (227 * 1024 - 2048) // (2 * (ma + na) * ATOM))
+        assert stages >= 2
+        assert stages * 2 * (ma + na) * ATOM + 1024 <= 227 * 1024 - 1024
+        assert 2 * 256 <= 512 and n_mma <= 256                   # two accumulators of <= 256 TMEM columns
+    for K in (16, 1088, 1089, 40000, 2927963):
+        units = -(-K // UNIT)
+        grid = min(units, SM)
+        bounds = [units * b // grid for b in range(grid + 1)]
+        assert bounds[0] == 0 and bounds[-1] == units
+        sizes = [b - a for a, b in zip(bounds, bounds[1:])]
+        assert min(sizes) >= 1 and max(sizes) - min(sizes) <= 1  # every CTA has work, balanced to within one unit
