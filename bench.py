@@ -424,6 +424,8 @@ def measure(args, workload, world, rank, device, full):
                     "passes": 3, "ceiling_3xtf32": round(pk["tensor"] / 6.0, 1),
                     "frac_of_3xtf32_ceiling": round(top["achieved_tflops"] / (pk["tensor"] / 6.0), 4)}
         try:        # measured DRAM traffic per launch of that kernel, from the committed ncu --set full capture
+            if world > 1:     # the captures are single-GPU launches over the whole graph: no per-rank figure
+                raise KeyError("no ncu capture at the row-partitioned shape")
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[workload][top["kernel"]]
             roof["traffic"], roof["traffic_source"] = tr["bytes"], "profiles/" + tr["source"]
         except Exception:
