@@ -1,3 +1,6 @@
+"""index-permutation probe of the TMA-fed weight-gradient GEMM (csrc/gemm_tma_tn.cu): A and B are zero except for one
+K-row, so C[m, n] = (m + 1)(n + 1) shows which operand element every output row / column actually read.  It is how the
+MN-major layout (PLNLP_TN_DEBUG=8: plain SWIZZLE_128B returns zeros) and the TMEM lane-quarter mapping were found."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from plnlp_b200 import _lib, _ops
