@@ -436,12 +436,15 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4) ? 8 : 6) spmm_csr_narrow
 // Narrow fp32 rows staged through SHARED MEMORY (cp.async): the rows in flight live in shared memory, not registers.
 //
 // The register kernels above hold every in-flight row in registers: NB rows per (half-)warp, ~256 rows per SM at
-// full occupancy, and each step of a row's walk waits a whole DRAM round trip.  Here a warp owns 32 work items and runs a software pipeline over BATCHES (<= CAP stored entries of one item): it issues the row copies of
-// batch b + S - 1 with cp.async (LDGSTS.128: global -> shared, no register, completion tracked per commit group) and
-// then accumulates batch b out of shared memory; the column indices / values of the next batch are fetched one
-// batch ahead.  Measured on the citation2-shape graph (profiles/r02_spmm_tune_ab.txt): F = 64 3.78 -> 3.0 - 3.1 ms
-// (71 % -> 87 - 90 % of the HBM copy peak), F = 50 on a 64-float pitch 3.79 -> 3.1 ms, on its own pitch 3.88 -> 3.26 ms
-// (55 % -> 65 %; every 200-byte row costs four 64-byte DRAM sectors, so 78 % is the ceiling), F = 32 3.40 -> 1.9 ms.
+// full occupancy, and each step of a row's walk waits a whole DRAM round trip.  Here a warp owns 32 work items and
+// walks them in BATCHES (<= CAP stored entries of one item, i.e. normally the whole item): it issues the row copies
+// of a batch with cp.async (LDGSTS.128: global -> shared, no register, completion tracked per commit group), waits for
+// the group, and accumulates the batch out of shared memory; the column indices / values of the next batch are fetched
+// one batch ahead.  S > 1 makes it a software pipeline (copies of batch b + S - 1 issued before batch b is consumed);
+// measured, ONE stage per warp and twice the resident warps wins (plnlp_spmm_tune mode 10, the default).
+// Citation2-shape graph (profiles/r02_spmm_tune_ab_run*.txt, r02_spmm_insitu.txt): F = 50 on its own pitch 3.88 ->
+// 2.97 ms (55 % -> 72 % of the HBM copy peak; every 200-byte row costs four 64-byte DRAM sectors, so 78 % is the
+// ceiling of the layout), on a 64-float pitch 3.79 -> 2.47 ms, F = 64 3.78 -> 3.0 ms, F = 32 3.40 -> 1.9 ms.
 //   issue   : lane l = (sub, part): row j0 + sub of the batch, 16-byte piece `part` of it (LPR pieces per row, so one
 //             LDGSTS instruction copies 32 / LPR rows); the values of the batch go to the stage with one STS
 //   consume : lane l owns floats 2l, 2l + 1 of the row: one conflict-free LDS.64 per stored entry, strictly in CSR
