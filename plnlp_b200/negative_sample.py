@@ -46,10 +46,14 @@ def global_neg_sample(edge_index, num_nodes, num_samples, num_neg, method='spars
 def local_neg_sample(pos_edges, num_nodes, num_neg, random_src=False):
     """negative_sample.py:31-43: keep the source of every positive, draw ``num_neg`` uniform
     destinations in [0, num_nodes); nothing is filtered."""
-    if random_src:
-        raise NotImplementedError("random_src=True is never used by the reference's call sites (utils.py:17-20)")
     if not pos_edges.is_cuda:
         raise RuntimeError("plnlp_b200 samplers run on the GPU; pos_edges must be a CUDA tensor")
+    if random_src:
+        # negative_sample.py:32-34 (no call site of the reference uses it): the kept endpoint of every positive is
+        # drawn uniformly from its two ends.  Index plumbing on the device; the kernel reads column 0 as the source.
+        side = torch.randint(0, 2, (pos_edges.size(0), 1), dtype=torch.long, device=pos_edges.device)
+        src = pos_edges.gather(1, side)
+        pos_edges = torch.cat([src, src], dim=1).contiguous()
     return _ops.local_neg_sample_raw(pos_edges, num_nodes, num_neg, _ops.new_seed())
 
 

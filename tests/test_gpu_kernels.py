@@ -521,6 +521,25 @@ def test_local_neg_sample(ops):
     assert torch.equal(local_neg_sample(pos2.cuda(), N, k).cpu(), out)   # reproducible under manual_seed
 
 
+def test_local_neg_sample_random_src(ops):
+    """negative_sample.py:32-34: with random_src the kept endpoint of every positive is one of its two ends, drawn
+    uniformly; the k negatives of a positive share it; destinations as in the plain sampler"""
+    from plnlp_b200.negative_sample import local_neg_sample
+    torch.manual_seed(1)
+    N, E, k = 500, 6000, 2
+    pos = torch.stack([torch.randint(0, N, (E,)), torch.randint(0, N, (E,)) + N], 1)      # ends are distinguishable
+    out = local_neg_sample(pos.cuda(), 2 * N, k, random_src=True).cpu()
+    assert out.shape == (E, k, 2) and out.dtype == torch.int64
+    src = out[:, :, 0]
+    assert torch.equal(src[:, 0], src[:, 1])                        # one draw per positive
+    from_first, from_second = src[:, 0] == pos[:, 0], src[:, 0] == pos[:, 1]
+    assert bool((from_first ^ from_second).all())                   # always one of the two ends
+    n1 = int(from_first.sum())
+    assert abs(n1 - E / 2) < 6 * (E / 4) ** 0.5                     # a fair coin within 6 sigma
+    dst = out[:, :, 1].reshape(-1)
+    assert dst.min() >= 0 and dst.max() < 2 * N
+
+
 def test_global_neg_sample(ops):
     from plnlp_b200.negative_sample import global_neg_sample
     torch.manual_seed(1)
